@@ -1,0 +1,243 @@
+"""numpy model of the DEVICE algorithm (test infrastructure).
+
+The CUDA kernels do not evaluate the reference's formulas literally: they use
+algebraically equivalent overflow-free forms, hoist per-row constants to the
+host, and accumulate *raw sums* on the device that the host maps to parameter
+gradients.  This file states that algorithm in numpy so the algebra can be
+checked against the literal oracle (oracle/enf_oracle.py) on the CPU, before
+any GPU time is spent.  csrc/enf_math.cuh and csrc/enf_abi.cu transcribe it.
+
+Conventions: G = N * dL/d(output) (un-normalised cotangent), lb = N * dL/dladj
+= -1.  All functions take one op's per-row parameters as length-D vectors and
+x as D x N.
+"""
+import numpy as np
+
+LB = -1.0
+LOG2E = 1.4426950408889634
+
+
+# ---------------------------------------------------------------- forward
+def cs_fwd(x, a, b, c):
+    """CenterStretch forward + ladj (stable form of src/center_stretch.jl:4-8,39-43)."""
+    a, b, c = a[:, None], b[:, None], c[:, None]
+    A = np.exp(b * a)
+    ax = np.abs(x)
+    w0 = np.exp2(-b * LOG2E * ax)
+    m = A - A * w0
+    g = 0.5 * (np.sqrt(m * m + 4 * w0) + m)
+    au = ax + np.log(g) / b
+    y = np.copysign(au, x) + c
+    wu = w0 / g
+    n1 = 1 + A * wu
+    n2 = A + wu
+    num = n2 + wu * n1
+    ladj = np.log(n1 * n2 / num)          # = -log S(u)
+    return y, ladj.sum(0)
+
+
+def cc_fwd(x, a, b, c):
+    """CenterContract forward + ladj (src/center_stretch.jl:11-22,63-67)."""
+    a, b, c = a[:, None], b[:, None], c[:, None]
+    A = np.exp(b * a)
+    u = x - c
+    au = np.abs(u)
+    w = np.exp2(-b * LOG2E * au)
+    n1 = 1 + A * w
+    n2 = A + w
+    r12 = 1 / (n1 * n2)
+    y = np.copysign(au + np.log(n1 * n1 * r12) / b, u)
+    ladj = np.log((n2 + w * n1) * r12)
+    return y, ladj.sum(0)
+
+
+def jo_fwd(x, gamma, delta, xi, lam):
+    """JohnsonTrafo forward + ladj (src/johnson_trafo.jl:29-32,39-42,76-80)."""
+    gamma, delta, xi, lam = gamma[:, None], delta[:, None], xi[:, None], lam[:, None]
+    il = 1 / lam
+    z = x * il - xi * il
+    s = 1 + z * z
+    r = 1 / np.sqrt(s)
+    ash = np.copysign(np.log(np.abs(z) + s * r), z)
+    y = gamma + delta * ash
+    ladj = np.log(np.abs(delta * il)) + np.log(r)
+    return y, ladj.sum(0)
+
+
+def ji_fwd(x, gamma, delta, xi, lam):
+    """JohnsonTrafoInv forward + ladj (src/johnson_trafo.jl:34-37,101-105)."""
+    gamma, delta, xi, lam = gamma[:, None], delta[:, None], xi[:, None], lam[:, None]
+    idl = 1 / delta
+    s = x * idl - gamma * idl
+    e = np.exp2(LOG2E * s)
+    ei = 1 / e
+    sh = 0.5 * (e - ei)
+    ch = 0.5 * (e + ei)
+    y = lam * sh + xi
+    ladj = np.log(np.abs(lam * idl)) + np.log(ch)
+    return y, ladj.sum(0)
+
+
+def ss_fwd(x, a, b):
+    return x * a[:, None] + b[:, None], np.full(x.shape[1], np.log(np.abs(a)).sum())
+
+
+def hh_fwd(x, V):
+    """Householder with pre-scaled v' = v*sqrt(2/v'v): y = x - (v'.x) v'."""
+    if V.ndim == 1:
+        V = V[:, None]
+    for k in range(V.shape[1]):
+        v = V[:, k]
+        vp = v * np.sqrt(2.0 / (v @ v))
+        x = x - vp[:, None] * (vp @ x)[None, :]
+    return x, np.zeros(x.shape[1])
+
+
+# ---------------------------------------------------------------- backward
+# each returns (Gx, raw) ; finish_*() maps raw sums -> parameter gradients
+def _cc_parts(au, A, a, b):
+    w = np.exp2(-b * LOG2E * au)
+    n1 = 1 + A * w
+    n2 = A + w
+    s1 = 1 / n1
+    s2 = w / n2
+    S = s1 + s2
+    d1 = s1 * (1 - s1)
+    d2 = s2 * (1 - s2)
+    ya = au + np.log(n1 / n2) / b
+    Su = b * (d1 - d2)                       # * sgn
+    Sa = -b * (d1 + d2)
+    Sb = (au - a) * d1 - (au + a) * d2
+    ya_a = s2 - s1                           # * sgn
+    ya_b = (s1 * (au - a) + s2 * (au + a) - ya) / b   # * sgn
+    return S, Su, Sa, Sb, ya_a, ya_b
+
+
+def cc_bwd(x, G, a, b, c):
+    a, b, c = a[:, None], b[:, None], c[:, None]
+    A = np.exp(b * a)
+    u = x - c
+    sg = np.where(u < 0, -1.0, 1.0)
+    S, Su, Sa, Sb, ya_a, ya_b = _cc_parts(np.abs(u), A, a, b)
+    iS = 1 / S
+    Gx = G * S + LB * sg * Su * iS
+    ra = sg * G * ya_a + LB * Sa * iS
+    rb = sg * G * ya_b + LB * Sb * iS
+    return Gx, (Gx.sum(1), ra.sum(1), rb.sum(1))
+
+
+def cc_finish(raw, N, a, b, c):
+    R1, R2, R3 = raw
+    return {"a": R2, "b": R3, "c": -R1}
+
+
+def cs_bwd(x, G, a, b, c):
+    """x: the op's INPUT.  Recomputes u = y - c and differentiates implicitly."""
+    a, b, c = a[:, None], b[:, None], c[:, None]
+    A = np.exp(b * a)
+    ax = np.abs(x)
+    sg = np.where(x < 0, -1.0, 1.0)
+    w0 = np.exp2(-b * LOG2E * ax)
+    m = A - A * w0
+    g = 0.5 * (np.sqrt(m * m + 4 * w0) + m)
+    au = ax + np.log(g) / b
+    # contract partials at u (its output is x): pass ya = |x|
+    wu = w0 / g
+    n1 = 1 + A * wu
+    n2 = A + wu
+    s1 = 1 / n1
+    s2 = wu / n2
+    S = s1 + s2
+    d1 = s1 * (1 - s1)
+    d2 = s2 * (1 - s2)
+    Su = b * (d1 - d2)
+    Sa = -b * (d1 + d2)
+    Sb = (au - a) * d1 - (au + a) * d2
+    Ca = s2 - s1
+    Cb = (s1 * (au - a) + s2 * (au + a) - ax) / b
+    iS = 1 / S
+    Gy = G - LB * sg * Su * iS               # total cotangent on y
+    Gx = Gy * iS
+    ra = -Gx * sg * Ca - LB * Sa * iS
+    rb = -Gx * sg * Cb - LB * Sb * iS
+    return Gx, (G.sum(1), ra.sum(1), rb.sum(1))
+
+
+def cs_finish(raw, N, a, b, c):
+    R1, R2, R3 = raw
+    return {"a": R2, "b": R3, "c": R1}
+
+
+def jo_bwd(x, G, gamma, delta, xi, lam):
+    gamma, delta, xi, lam = gamma[:, None], delta[:, None], xi[:, None], lam[:, None]
+    il = 1 / lam
+    z = x * il - xi * il
+    s = 1 + z * z
+    r = 1 / np.sqrt(s)
+    ash = np.copysign(np.log(np.abs(z) + s * r), z)
+    gz = G * delta * r - LB * z * r * r
+    return gz * il, (G.sum(1), (G * ash).sum(1), gz.sum(1), (z * gz).sum(1))
+
+
+def jo_finish(raw, N, gamma, delta, xi, lam):
+    S1, S2, S3, S4 = raw
+    return {"gamma": S1, "delta": S2 + LB * N / delta, "xi": -S3 / lam, "lam": -(S4 + LB * N) / lam}
+
+
+def ji_bwd(x, G, gamma, delta, xi, lam):
+    gamma, delta, xi, lam = gamma[:, None], delta[:, None], xi[:, None], lam[:, None]
+    idl = 1 / delta
+    s = x * idl - gamma * idl
+    e = np.exp2(LOG2E * s)
+    ei = 1 / e
+    sh = 0.5 * (e - ei)
+    ch = 0.5 * (e + ei)
+    gs = G * lam * ch + LB * sh / ch
+    return gs * idl, (gs.sum(1), (s * gs).sum(1), G.sum(1), (G * sh).sum(1))
+
+
+def ji_finish(raw, N, gamma, delta, xi, lam):
+    S1, S2, S3, S4 = raw
+    return {"gamma": -S1 / delta, "delta": -(S2 + LB * N) / delta, "xi": S3, "lam": S4 + LB * N / lam}
+
+
+def ss_bwd(x, G, a, b):
+    return G * a[:, None], ((G * x).sum(1), G.sum(1))
+
+
+def ss_finish(raw, N, a, b):
+    R0, R1 = raw
+    return {"a": R0 + LB * N / a, "b": R1}
+
+
+def hh_bwd(y, G, V):
+    """y: the op's OUTPUT (the reverse sweep recovers every reflection's input
+    by re-applying it, src/householder_trafo.jl:88-103)."""
+    vec = V.ndim == 1
+    if vec:
+        V = V[:, None]
+    K = V.shape[1]
+    acc1 = np.zeros_like(V, dtype=np.float64)
+    acc2 = np.zeros(K)
+    z, Dl = y, G
+    for k in reversed(range(K)):
+        v = V[:, k]
+        vp = v * np.sqrt(2.0 / (v @ v))
+        po = vp @ z                      # v'.z_out = -(v'.z_in)
+        q = vp @ Dl
+        z = z - vp[:, None] * po[None, :]
+        p = -po
+        acc1[:, k] = (p[None, :] * Dl + q[None, :] * z).sum(1)
+        acc2[k] = (p * q).sum()
+        Dl = Dl - vp[:, None] * q[None, :]
+    return Dl, (acc1, acc2), z
+
+
+def hh_finish(raw, N, V):
+    acc1, acc2 = raw
+    vec = V.ndim == 1
+    Vm = V[:, None] if vec else V
+    n = (Vm * Vm).sum(0)
+    # acc1 was accumulated with z = reflection *input*; p' uses the input too.
+    dV = -np.sqrt(2.0 / n)[None, :] * acc1 + (2.0 / n * acc2)[None, :] * Vm
+    return {"V": dV[:, 0] if vec else dV}
