@@ -1,0 +1,820 @@
+// C ABI of libenf_b200.so (include/enf_b200.h): contexts, device buffers, chain
+// construction (derived per-row constants), kernel dispatch, mapping of the raw
+// device sums to (negll, parameter gradients), the host-buffer pipeline and the
+// NCCL group used for sharded gradient steps.
+//
+// There is no CPU fallback anywhere in this file: every compute entry point
+// launches the sm_100a kernels of enf_chain.cuh or fails with an error code.
+#include "enf_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only; the library is dlopen'ed (see NcclApi)
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "enf_chain.cuh"
+#include "enf_launch.h"
+
+using namespace enf;
+
+// ------------------------------------------------------------------ errors
+namespace {
+thread_local std::string t_last_error;
+
+int fail(enf_ctx* ctx, int code, const char* fmt, ...);
+
+constexpr double LOG2PI = 1.8378770664093454835606594728112;
+constexpr double LOG2E_D = 1.4426950408889634073599246810019;
+constexpr int HOST_SLOTS = 3;
+}  // namespace
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+struct enf_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t slot_stream[HOST_SLOTS] = {nullptr, nullptr, nullptr};
+    void* slot_buf[HOST_SLOTS] = {nullptr, nullptr, nullptr};
+    size_t slot_bytes = 0;
+    cudaEvent_t ev = nullptr;
+    int64_t launches = 0;
+    std::string last_error;
+    // NCCL group
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+namespace {
+
+int fail(enf_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    if (ctx) ctx->last_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(ctx, ENF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+std::mutex g_nccl_mu;
+NcclApi g_nccl;
+
+int load_nccl(enf_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.handle) return ENF_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(ctx, ENF_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    NcclApi a;
+    a.handle = h;
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString)
+        return fail(ctx, ENF_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
+    g_nccl = a;
+    return ENF_OK;
+}
+
+#define NC(ctx, call)                                                                              \
+    do {                                                                                           \
+        ncclResult_t r__ = (call);                                                                 \
+        if (r__ != ncclSuccess)                                                                    \
+            return fail(ctx, ENF_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__));    \
+    } while (0)
+
+struct HostOp {
+    int kind;
+    int K;
+    size_t poff;     // offset of this op's params in the packed parameter vector
+    size_t nparams;  // number of parameters (fields * D, or D * K)
+};
+
+inline size_t params_of(int kind, int K, int D) {
+    switch (kind) {
+        case OP_CS: case OP_CC: return size_t(3) * D;
+        case OP_JO: case OP_JI: return size_t(4) * D;
+        case OP_SS: return size_t(2) * D;
+        default: return size_t(D) * K;
+    }
+}
+
+}  // namespace
+
+struct enf_chain {
+    enf_ctx* ctx = nullptr;
+    int dtype = ENF_F32;
+    int D = 0;
+    std::vector<HostOp> ops;
+    std::vector<double> params;  // packed, float64 copy of what the caller passed
+    size_t n_params = 0;
+    Plan plan;
+    ChainDesc desc;
+    double ladj_const_ss = 0.0;     // sum_i log|a_i| over ScaleShift ops
+    double ladj_const_other = 0.0;  // Johnson row constants
+    // device / staging
+    void* d_consts = nullptr;
+    void* h_consts = nullptr;  // pinned
+    cudaEvent_t consts_copied = nullptr;
+    bool consts_pending = false;
+    int n_raw = 0;
+    int max_blocks = 0;
+    double* d_partials = nullptr;
+    double* d_sums = nullptr;  // n_raw + 1 (last: N_local, for the group all-reduce)
+    double* h_sums = nullptr;  // pinned, n_raw + 1
+};
+
+namespace {
+
+size_t elem_size(int dtype) { return dtype == ENF_F32 ? 4 : 8; }
+
+template <typename T>
+void put(void* base, size_t i, double v) { static_cast<T*>(base)[i] = T(v); }
+
+// Fill the constants block (layout: for each op, n_consts_of(kind) arrays of
+// length Dp) from the float64 parameters.  Padding rows get neutral values that
+// map 0 -> 0 with zero ladj, so they never need masking inside the kernels.
+int derive_constants(enf_chain* ch) {
+    enf_ctx* ctx = ch->ctx;
+    const int D = ch->D, Dp = ch->desc.Dp;
+    const bool packed = ch->plan.packed;
+    if (ch->consts_pending) {
+        CU(ctx, cudaEventSynchronize(ch->consts_copied));
+        ch->consts_pending = false;
+    }
+    auto set = [&](size_t idx, double v) {
+        if (ch->dtype == ENF_F32) put<float>(ch->h_consts, idx, v);
+        else put<double>(ch->h_consts, idx, v);
+    };
+    ch->ladj_const_ss = 0.0;
+    ch->ladj_const_other = 0.0;
+    for (size_t o = 0; o < ch->ops.size(); ++o) {
+        const HostOp& op = ch->ops[o];
+        const DevOp& dop = ch->desc.ops[o];
+        const double* p = ch->params.data() + op.poff;
+        for (int r = 0; r < Dp; ++r) {
+            const bool real = packed || r < D;
+            const int i = packed ? r % D : r;
+            const size_t base = size_t(dop.coff) + r;
+            switch (op.kind) {
+                case OP_CS:
+                case OP_CC: {
+                    const double a = real ? p[i] : 0.0, b = real ? p[D + i] : 1.0, c = real ? p[2 * D + i] : 0.0;
+                    set(base + 0 * size_t(Dp), -b * LOG2E_D);
+                    set(base + 1 * size_t(Dp), std::exp(b * a));
+                    set(base + 2 * size_t(Dp), 1.0 / b);
+                    set(base + 3 * size_t(Dp), c);
+                    set(base + 4 * size_t(Dp), a);
+                    set(base + 5 * size_t(Dp), b);
+                    break;
+                }
+                case OP_JO: {
+                    const double gm = real ? p[i] : 0.0, dl = real ? p[D + i] : 1.0, xi = real ? p[2 * D + i] : 0.0,
+                                 lm = real ? p[3 * D + i] : 1.0;
+                    set(base + 0 * size_t(Dp), 1.0 / lm);
+                    set(base + 1 * size_t(Dp), -xi / lm);
+                    set(base + 2 * size_t(Dp), gm);
+                    set(base + 3 * size_t(Dp), dl);
+                    if (r < D) ch->ladj_const_other += std::log(std::fabs(dl / lm));
+                    break;
+                }
+                case OP_JI: {
+                    const double gm = real ? p[i] : 0.0, dl = real ? p[D + i] : 1.0, xi = real ? p[2 * D + i] : 0.0,
+                                 lm = real ? p[3 * D + i] : 1.0;
+                    set(base + 0 * size_t(Dp), 1.0 / dl);
+                    set(base + 1 * size_t(Dp), -gm / dl);
+                    set(base + 2 * size_t(Dp), lm);
+                    set(base + 3 * size_t(Dp), xi);
+                    if (r < D) ch->ladj_const_other += std::log(std::fabs(lm / dl));
+                    break;
+                }
+                case OP_SS: {
+                    const double a = real ? p[i] : 1.0, b = real ? p[D + i] : 0.0;
+                    set(base + 0 * size_t(Dp), a);
+                    set(base + 1 * size_t(Dp), b);
+                    if (r < D) ch->ladj_const_ss += std::log(std::fabs(a));
+                    break;
+                }
+                default: {  // OP_HH: v'_k = v_k sqrt(2 / v_k.v_k)
+                    for (int k = 0; k < op.K; ++k) {
+                        const double* v = p + size_t(k) * D;
+                        double n = 0.0;
+                        for (int j = 0; j < D; ++j) n += v[j] * v[j];
+                        const double sc = std::sqrt(2.0 / n);
+                        set(base + size_t(k) * Dp, real ? v[i] * sc : 0.0);
+                    }
+                    break;
+                }
+            }
+        }
+    }
+    CU(ctx, cudaMemcpyAsync(ch->d_consts, ch->h_consts, size_t(ch->desc.n_consts) * elem_size(ch->dtype),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaEventRecord(ch->consts_copied, ctx->stream));
+    ch->consts_pending = true;
+    return ENF_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int pick_mode(const enf_chain* ch, const void* x, const void* y) {
+    const int VE = ch->dtype == ENF_F32 ? 4 : 2;
+    const bool al = aligned16(x) && (y == nullptr || aligned16(y));
+    if (ch->plan.packed) return al ? MODE_PACK : MODE_PACKU;
+    return (al && ch->D % VE == 0) ? MODE_VEC : MODE_SCALAR;
+}
+
+// raw device sums -> (negll, grads).  Transcribes tests/device_model.py *_finish.
+void finish(const enf_chain* ch, const double* sums, int64_t N, int flags, double* negll, std::vector<double>* grads) {
+    const int D = ch->D, Dp = ch->desc.Dp;
+    const bool packed = ch->plan.packed;
+    const double Nd = double(N);
+    const double LB = -1.0;
+    const int n_raw = ch->n_raw;
+    const double sum_y = sums[n_raw - 2], sum_l = sums[n_raw - 1];
+    const double lconst = ch->ladj_const_other + ((flags & ENF_NEGLL_ZYGOTE_PRIMAL) ? 0.0 : ch->ladj_const_ss);
+    if (negll) *negll = (sum_y + 0.5 * LOG2PI * Nd * D - (sum_l + Nd * lconst)) / Nd;
+    if (!grads) return;
+    grads->assign(ch->n_params, 0.0);
+    std::vector<double> R(size_t(4) * D);
+    for (size_t o = 0; o < ch->ops.size(); ++o) {
+        const HostOp& op = ch->ops[o];
+        const DevOp& dop = ch->desc.ops[o];
+        const double* p = ch->params.data() + op.poff;
+        double* g = grads->data() + op.poff;
+        auto row_sum = [&](int slot, int i) {  // raw per-row sum `slot` of this op for row i
+            const double* base = sums + size_t(dop.roff + slot) * Dp;
+            if (!packed) return base[i];
+            double s = 0.0;
+            for (int r = i; r < Dp; r += D) s += base[r];
+            return s;
+        };
+        if (op.kind == OP_HH) {
+            for (int k = 0; k < op.K; ++k) {
+                const double* v = p + size_t(k) * D;
+                double n = 0.0;
+                for (int j = 0; j < D; ++j) n += v[j] * v[j];
+                const double acc2 = sums[size_t(ch->desc.n_rowslots) * Dp + dop.soff + k];
+                for (int i = 0; i < D; ++i)
+                    g[size_t(k) * D + i] = (-std::sqrt(2.0 / n) * row_sum(k, i) + (2.0 / n) * acc2 * v[i]) / Nd;
+            }
+            continue;
+        }
+        for (int i = 0; i < D; ++i) {
+            const double r0 = row_sum(0, i), r1 = row_sum(1, i);
+            switch (op.kind) {
+                case OP_CS: {
+                    const double r2 = row_sum(2, i);
+                    g[i] = r1 / Nd; g[D + i] = r2 / Nd; g[2 * D + i] = r0 / Nd;
+                    break;
+                }
+                case OP_CC: {
+                    const double r2 = row_sum(2, i);
+                    g[i] = r1 / Nd; g[D + i] = r2 / Nd; g[2 * D + i] = -r0 / Nd;
+                    break;
+                }
+                case OP_JO: {
+                    const double r2 = row_sum(2, i), r3 = row_sum(3, i);
+                    const double dl = p[D + i], lm = p[3 * D + i];
+                    g[i] = r0 / Nd;
+                    g[D + i] = (r1 + LB * Nd / dl) / Nd;
+                    g[2 * D + i] = (-r2 / lm) / Nd;
+                    g[3 * D + i] = (-(r3 + LB * Nd) / lm) / Nd;
+                    break;
+                }
+                case OP_JI: {
+                    const double r2 = row_sum(2, i), r3 = row_sum(3, i);
+                    const double dl = p[D + i], lm = p[3 * D + i];
+                    g[i] = (-r0 / dl) / Nd;
+                    g[D + i] = (-(r1 + LB * Nd) / dl) / Nd;
+                    g[2 * D + i] = r2 / Nd;
+                    g[3 * D + i] = (r3 + LB * Nd / lm) / Nd;
+                    break;
+                }
+                default: {  // OP_SS
+                    const double a = p[i];
+                    g[i] = (r0 + LB * Nd / a) / Nd;
+                    g[D + i] = r1 / Nd;
+                    break;
+                }
+            }
+        }
+    }
+}
+
+void export_grads(const enf_chain* ch, const std::vector<double>& g, void* out) {
+    if (ch->dtype == ENF_F32) {
+        float* o = static_cast<float*>(out);
+        for (size_t i = 0; i < g.size(); ++i) o[i] = float(g[i]);
+    } else {
+        std::memcpy(out, g.data(), g.size() * sizeof(double));
+    }
+}
+
+int run_partial(enf_chain* ch, const void* x, int64_t N, bool grad) {
+    enf_ctx* ctx = ch->ctx;
+    if (N < 0) return fail(ctx, ENF_ERR_INVALID, "N must be >= 0");
+    KernelSet ks;
+    const int mode = pick_mode(ch, x, nullptr);
+    if (!select_kernels(ch->dtype, ch->plan, mode, ks))
+        return fail(ctx, ENF_ERR_INVALID, "no kernel variant for dtype=%d D=%d", ch->dtype, ch->D);
+    const size_t smem = grad_smem_bytes(ch->dtype, ch->desc, ks, grad);
+    if (smem > 227 * 1024)
+        return fail(ctx, ENF_ERR_INVALID,
+                    "chain needs %zu bytes of shared memory per CTA for the fused %s kernel (limit 232448)", smem,
+                    grad ? "gradient" : "loss");
+    int blocks = 0;
+    CU(ctx, launch_grad(ch->dtype, ks, ch->desc, ch->d_consts, x, N, grad, ch->d_partials, ch->max_blocks, &blocks,
+                        ctx->sm_count, ctx->stream));
+    CU(ctx, launch_reduce(ch->d_partials, blocks, ch->n_raw, ch->d_sums, false, ctx->stream));
+    ctx->launches += 2;
+    return ENF_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ context
+extern "C" int enf_version(void) { return 100; }
+
+extern "C" const char* enf_last_error(const enf_ctx* ctx) {
+    if (ctx && !ctx->last_error.empty()) return ctx->last_error.c_str();
+    return t_last_error.c_str();
+}
+
+extern "C" int enf_device_count(int* n) {
+    if (!n) return fail(nullptr, ENF_ERR_INVALID, "n is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(nullptr, ENF_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    *n = c;
+    return ENF_OK;
+}
+
+extern "C" int enf_init(int device, enf_ctx** out) {
+    if (!out) return fail(nullptr, ENF_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, ENF_ERR_CUDA, "no usable CUDA device (%s); libenf_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(nullptr, ENF_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+    CU(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, ENF_ERR_CUDA, "device %d is sm_%d%d; libenf_b200 is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    enf_ctx* ctx = new enf_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < HOST_SLOTS; ++i) CU(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[i], cudaStreamNonBlocking));
+    CU(ctx, cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming));
+    *out = ctx;
+    return ENF_OK;
+}
+
+extern "C" int enf_destroy(enf_ctx* ctx) {
+    if (!ctx) return ENF_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < HOST_SLOTS; ++i) {
+        if (ctx->slot_stream[i]) { cudaStreamSynchronize(ctx->slot_stream[i]); cudaStreamDestroy(ctx->slot_stream[i]); }
+        if (ctx->slot_buf[i]) cudaFree(ctx->slot_buf[i]);
+    }
+    if (ctx->ev) cudaEventDestroy(ctx->ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ENF_OK;
+}
+
+extern "C" int enf_sync(enf_ctx* ctx) {
+    if (!ctx) return fail(nullptr, ENF_ERR_INVALID, "ctx is NULL");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ENF_OK;
+}
+
+extern "C" int enf_launch_count(const enf_ctx* ctx, int64_t* n) {
+    if (!ctx || !n) return fail(nullptr, ENF_ERR_INVALID, "NULL argument");
+    *n = ctx->launches;
+    return ENF_OK;
+}
+
+// ------------------------------------------------------------------ memory
+extern "C" int enf_alloc(enf_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    *dptr = nullptr;
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 16);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return fail(ctx, ENF_ERR_NOMEM, "cudaMalloc(%zu) failed: out of device memory", bytes);
+    }
+    CU(ctx, e);
+    return ENF_OK;
+}
+
+extern "C" int enf_free(enf_ctx* ctx, void* dptr) {
+    if (!ctx) return fail(ctx, ENF_ERR_INVALID, "ctx is NULL");
+    if (!dptr) return ENF_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaFree(dptr));
+    return ENF_OK;
+}
+
+extern "C" int enf_host_alloc(enf_ctx* ctx, size_t bytes, void** hptr) {
+    if (!ctx || !hptr) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    *hptr = nullptr;
+    cudaError_t e = cudaMallocHost(hptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, ENF_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return ENF_OK;
+}
+
+extern "C" int enf_host_free(enf_ctx* ctx, void* hptr) {
+    if (!ctx) return fail(ctx, ENF_ERR_INVALID, "ctx is NULL");
+    if (!hptr) return ENF_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaFreeHost(hptr));
+    return ENF_OK;
+}
+
+extern "C" int enf_h2d(enf_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx || (bytes && (!dst || !src))) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return ENF_OK;
+}
+
+extern "C" int enf_d2h(enf_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx || (bytes && (!dst || !src))) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ENF_OK;
+}
+
+extern "C" int enf_memset(enf_ctx* ctx, void* dst, int value, size_t bytes) {
+    if (!ctx || (bytes && !dst)) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
+    return ENF_OK;
+}
+
+extern "C" int enf_fill_normal(enf_ctx* ctx, int dtype, void* x, int D, int64_t N, int64_t col0, uint64_t seed) {
+    if (!ctx || !x) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    if (dtype != ENF_F32 && dtype != ENF_F64) return fail(ctx, ENF_ERR_INVALID, "bad dtype %d", dtype);
+    if (D < 1 || N < 0) return fail(ctx, ENF_ERR_INVALID, "bad shape D=%d N=%lld", D, (long long)N);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, launch_fill_normal(dtype, x, D, N, col0, seed, ctx->stream));
+    ctx->launches += 1;
+    return ENF_OK;
+}
+
+// ------------------------------------------------------------------ chains
+extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const enf_op* ops, enf_chain** out) {
+    if (!ctx || !ops || !out) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (dtype != ENF_F32 && dtype != ENF_F64) return fail(ctx, ENF_ERR_INVALID, "bad dtype %d", dtype);
+    if (D < 1) return fail(ctx, ENF_ERR_INVALID, "D must be >= 1 (got %d)", D);
+    if (n_ops < 1 || n_ops > MAX_OPS) return fail(ctx, ENF_ERR_INVALID, "n_ops must be in [1,%d] (got %d)", MAX_OPS, n_ops);
+    CU(ctx, cudaSetDevice(ctx->device));
+    enf_chain* ch = new enf_chain();
+    ch->ctx = ctx;
+    ch->dtype = dtype;
+    ch->D = D;
+    if (!make_plan(dtype, D, ch->plan)) {
+        delete ch;
+        return fail(ctx, ENF_ERR_INVALID, "D=%d is not supported (max %d rows for this dtype)", D,
+                    dtype == ENF_F32 ? 1024 : 512);
+    }
+    ChainDesc& d = ch->desc;
+    std::memset(&d, 0, sizeof d);
+    d.n_ops = n_ops;
+    d.D = D;
+    d.Dp = ch->plan.Dp;
+    size_t poff = 0;
+    int coff = 0, roff = 0, soff = 0, save = 0;
+    for (int o = 0; o < n_ops; ++o) {
+        const int kind = ops[o].kind;
+        int K = ops[o].K;
+        if (kind < OP_CS || kind > OP_HH) { delete ch; return fail(ctx, ENF_ERR_INVALID, "op %d: bad kind %d", o, kind); }
+        if (kind == OP_HH) {
+            if (K < 1) { delete ch; return fail(ctx, ENF_ERR_INVALID, "op %d: Householder needs K >= 1 (got %d)", o, K); }
+        } else K = 0;
+        if (!ops[o].params) { delete ch; return fail(ctx, ENF_ERR_INVALID, "op %d: params is NULL", o); }
+        HostOp h{kind, K, poff, params_of(kind, K, D)};
+        ch->ops.push_back(h);
+        DevOp& dop = d.ops[o];
+        dop.kind = kind;
+        dop.K = K;
+        dop.coff = coff;
+        dop.roff = roff;
+        dop.soff = kind == OP_HH ? soff : 0;
+        dop.save = kind == OP_HH ? -1 : save;
+        coff += n_consts_of(kind, K) * d.Dp;
+        roff += n_rowslots_of(kind, K);
+        if (kind == OP_HH) soff += K; else save += 1;
+        poff += h.nparams;
+    }
+    ch->n_params = poff;
+    d.n_consts = coff;
+    d.n_rowslots = roff;
+    d.n_scalars = soff;
+    d.n_save = save;
+    ch->n_raw = d.n_rowslots * d.Dp + d.n_scalars + 2;
+    if (fwd_smem_bytes(dtype, d) > 200 * 1024) {
+        delete ch;
+        return fail(ctx, ENF_ERR_INVALID, "chain constants (%zu bytes) exceed the shared-memory budget", fwd_smem_bytes(dtype, d));
+    }
+    // gather params (float64 host copy)
+    ch->params.resize(ch->n_params);
+    for (int o = 0; o < n_ops; ++o) {
+        const HostOp& h = ch->ops[o];
+        for (size_t i = 0; i < h.nparams; ++i)
+            ch->params[h.poff + i] = dtype == ENF_F32 ? double(static_cast<const float*>(ops[o].params)[i])
+                                                       : static_cast<const double*>(ops[o].params)[i];
+    }
+    const size_t cbytes = size_t(d.n_consts) * elem_size(dtype);
+    ch->max_blocks = 4 * ctx->sm_count;
+    cudaError_t e;
+    if ((e = cudaMalloc(&ch->d_consts, cbytes)) != cudaSuccess ||
+        (e = cudaMallocHost(&ch->h_consts, cbytes)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_partials), size_t(ch->max_blocks) * ch->n_raw * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_sums), size_t(ch->n_raw + 1) * sizeof(double))) != cudaSuccess ||
+        (e = cudaMallocHost(reinterpret_cast<void**>(&ch->h_sums), size_t(ch->n_raw + 1) * sizeof(double))) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ch->consts_copied, cudaEventDisableTiming)) != cudaSuccess) {
+        enf_chain_destroy(ch);
+        return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
+    }
+    int rc = derive_constants(ch);
+    if (rc != ENF_OK) { enf_chain_destroy(ch); return rc; }
+    *out = ch;
+    return ENF_OK;
+}
+
+extern "C" int enf_chain_set_params(enf_chain* ch, const void* packed) {
+    if (!ch || !packed) return fail(ch ? ch->ctx : nullptr, ENF_ERR_INVALID, "NULL argument");
+    CU(ch->ctx, cudaSetDevice(ch->ctx->device));
+    for (size_t i = 0; i < ch->n_params; ++i)
+        ch->params[i] = ch->dtype == ENF_F32 ? double(static_cast<const float*>(packed)[i])
+                                              : static_cast<const double*>(packed)[i];
+    return derive_constants(ch);
+}
+
+extern "C" int enf_chain_num_params(const enf_chain* ch, int64_t* n) {
+    if (!ch || !n) return fail(nullptr, ENF_ERR_INVALID, "NULL argument");
+    *n = int64_t(ch->n_params);
+    return ENF_OK;
+}
+
+extern "C" int enf_chain_destroy(enf_chain* ch) {
+    if (!ch) return ENF_OK;
+    cudaSetDevice(ch->ctx->device);
+    cudaStreamSynchronize(ch->ctx->stream);
+    for (int i = 0; i < HOST_SLOTS; ++i) cudaStreamSynchronize(ch->ctx->slot_stream[i]);
+    if (ch->d_consts) cudaFree(ch->d_consts);
+    if (ch->h_consts) cudaFreeHost(ch->h_consts);
+    if (ch->d_partials) cudaFree(ch->d_partials);
+    if (ch->d_sums) cudaFree(ch->d_sums);
+    if (ch->h_sums) cudaFreeHost(ch->h_sums);
+    if (ch->consts_copied) cudaEventDestroy(ch->consts_copied);
+    delete ch;
+    return ENF_OK;
+}
+
+extern "C" int enf_chain_describe(const enf_chain* ch, char* buf, size_t buflen) {
+    if (!ch || !buf || buflen == 0) return fail(nullptr, ENF_ERR_INVALID, "NULL argument");
+    KernelSet ks;
+    const int mode = ch->plan.packed ? MODE_PACK : ((ch->D % (ch->dtype == ENF_F32 ? 4 : 2)) == 0 ? MODE_VEC : MODE_SCALAR);
+    select_kernels(ch->dtype, ch->plan, mode, ks);
+    snprintf(buf, buflen,
+             "dtype=%s D=%d Dp=%d layout=%s lanes_per_sample=%d vectors_per_lane=%d ops=%d consts=%d "
+             "fwd_smem=%zu grad_smem=%zu n_raw=%d",
+             ch->dtype == ENF_F32 ? "f32" : "f64", ch->D, ch->desc.Dp, ch->plan.packed ? "packed" : "lane-group",
+             1 << ch->plan.LG, ch->plan.CH, ch->desc.n_ops, ch->desc.n_consts, fwd_smem_bytes(ch->dtype, ch->desc),
+             grad_smem_bytes(ch->dtype, ch->desc, ks, true), ch->n_raw);
+    return ENF_OK;
+}
+
+// ------------------------------------------------------------------ forward
+static int forward_impl(enf_chain* ch, const void* x, int64_t N, void* y, void* ladj, bool want_ladj, cudaStream_t st) {
+    enf_ctx* ctx = ch->ctx;
+    if (N < 0) return fail(ctx, ENF_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return ENF_OK;
+    if (!x || !y || (want_ladj && !ladj)) return fail(ctx, ENF_ERR_INVALID, "NULL device pointer");
+    KernelSet ks;
+    const int mode = pick_mode(ch, x, y);
+    if (!select_kernels(ch->dtype, ch->plan, mode, ks))
+        return fail(ctx, ENF_ERR_INVALID, "no kernel variant for dtype=%d D=%d", ch->dtype, ch->D);
+    const double lc = ch->ladj_const_other + ch->ladj_const_ss;
+    CU(ctx, launch_fwd(ch->dtype, ks, ch->desc, ch->d_consts, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));
+    ctx->launches += 1;
+    return ENF_OK;
+}
+
+extern "C" int enf_forward(enf_chain* ch, const void* x, int64_t N, void* y) {
+    if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
+    CU(ch->ctx, cudaSetDevice(ch->ctx->device));
+    return forward_impl(ch, x, N, y, nullptr, false, ch->ctx->stream);
+}
+
+extern "C" int enf_forward_ladj(enf_chain* ch, const void* x, int64_t N, void* y, void* ladj) {
+    if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
+    CU(ch->ctx, cudaSetDevice(ch->ctx->device));
+    return forward_impl(ch, x, N, y, ladj, true, ch->ctx->stream);
+}
+
+extern "C" int enf_forward_ladj_host(enf_chain* ch, const void* x_host, int64_t N, void* y_host, void* ladj_host) {
+    if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
+    enf_ctx* ctx = ch->ctx;
+    if (N < 0) return fail(ctx, ENF_ERR_INVALID, "N must be >= 0");
+    if (N == 0) return ENF_OK;
+    if (!x_host || !y_host) return fail(ctx, ENF_ERR_INVALID, "NULL host pointer");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t es = elem_size(ch->dtype);
+    const size_t col_bytes = size_t(ch->D) * es;
+    // chunk: ~32 MiB of samples, a multiple of 1024 columns so every chunk stays 16-byte aligned
+    int64_t chunk = int64_t((size_t(32) << 20) / col_bytes);
+    chunk = (chunk / 1024) * 1024;
+    if (chunk < 1024) chunk = 1024;
+    if (chunk > N) chunk = N;
+    const size_t x_bytes = size_t(chunk) * col_bytes, l_bytes = ((size_t(chunk) * es + 255) / 256) * 256;
+    const size_t need = 2 * ((x_bytes + 255) / 256 * 256) + l_bytes;
+    if (ctx->slot_bytes < need) {
+        for (int i = 0; i < HOST_SLOTS; ++i) {
+            CU(ctx, cudaStreamSynchronize(ctx->slot_stream[i]));
+            if (ctx->slot_buf[i]) { CU(ctx, cudaFree(ctx->slot_buf[i])); ctx->slot_buf[i] = nullptr; }
+        }
+        ctx->slot_bytes = 0;
+        for (int i = 0; i < HOST_SLOTS; ++i) CU(ctx, cudaMalloc(&ctx->slot_buf[i], need));
+        ctx->slot_bytes = need;
+    }
+    // the slot streams must see the chain's constants (uploaded on ctx->stream)
+    CU(ctx, cudaEventRecord(ctx->ev, ctx->stream));
+    for (int i = 0; i < HOST_SLOTS; ++i) CU(ctx, cudaStreamWaitEvent(ctx->slot_stream[i], ctx->ev, 0));
+    const size_t xb_al = (x_bytes + 255) / 256 * 256;
+    int64_t done = 0;
+    for (int it = 0; done < N; ++it) {
+        const int s = it % HOST_SLOTS;
+        const int64_t n = (N - done < chunk) ? (N - done) : chunk;
+        char* base = static_cast<char*>(ctx->slot_buf[s]);
+        void* dx = base;
+        void* dy = base + xb_al;
+        void* dl = base + 2 * xb_al;
+        cudaStream_t st = ctx->slot_stream[s];
+        CU(ctx, cudaMemcpyAsync(dx, static_cast<const char*>(x_host) + size_t(done) * col_bytes, size_t(n) * col_bytes,
+                                cudaMemcpyHostToDevice, st));
+        int rc = forward_impl(ch, dx, n, dy, dl, ladj_host != nullptr, st);
+        if (rc != ENF_OK) return rc;
+        CU(ctx, cudaMemcpyAsync(static_cast<char*>(y_host) + size_t(done) * col_bytes, dy, size_t(n) * col_bytes,
+                                cudaMemcpyDeviceToHost, st));
+        if (ladj_host)
+            CU(ctx, cudaMemcpyAsync(static_cast<char*>(ladj_host) + size_t(done) * es, dl, size_t(n) * es,
+                                    cudaMemcpyDeviceToHost, st));
+        done += n;
+    }
+    for (int i = 0; i < HOST_SLOTS; ++i) CU(ctx, cudaStreamSynchronize(ctx->slot_stream[i]));
+    return ENF_OK;
+}
+
+// ------------------------------------------------------------------ loss / gradient
+extern "C" int enf_negll(enf_chain* ch, const void* x, int64_t N, double* negll) {
+    if (!ch || !negll) return fail(ch ? ch->ctx : nullptr, ENF_ERR_INVALID, "NULL argument");
+    enf_ctx* ctx = ch->ctx;
+    if (N < 1) return fail(ctx, ENF_ERR_INVALID, "N must be >= 1");
+    if (!x) return fail(ctx, ENF_ERR_INVALID, "NULL device pointer");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = run_partial(ch, x, N, false);
+    if (rc != ENF_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(ch->h_sums, ch->d_sums, size_t(ch->n_raw) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    finish(ch, ch->h_sums, N, 0, negll, nullptr);
+    return ENF_OK;
+}
+
+extern "C" int enf_negll_grad_partial(enf_chain* ch, const void* x, int64_t N_local, double** sums_dev, int64_t* n) {
+    if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
+    enf_ctx* ctx = ch->ctx;
+    if (N_local > 0 && !x) return fail(ctx, ENF_ERR_INVALID, "NULL device pointer");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = run_partial(ch, x, N_local, true);
+    if (rc != ENF_OK) return rc;
+    if (sums_dev) *sums_dev = ch->d_sums;
+    if (n) *n = ch->n_raw;
+    return ENF_OK;
+}
+
+extern "C" int enf_negll_grad_finish(enf_chain* ch, const double* sums_host, int64_t N_global, int flags,
+                                     double* negll, void* grads_host) {
+    if (!ch || !sums_host) return fail(ch ? ch->ctx : nullptr, ENF_ERR_INVALID, "NULL argument");
+    if (N_global < 1) return fail(ch->ctx, ENF_ERR_INVALID, "N_global must be >= 1");
+    std::vector<double> g;
+    finish(ch, sums_host, N_global, flags, negll, grads_host ? &g : nullptr);
+    if (grads_host) export_grads(ch, g, grads_host);
+    return ENF_OK;
+}
+
+extern "C" int enf_negll_grad(enf_chain* ch, const void* x, int64_t N, int flags, double* negll, void* grads_host) {
+    if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
+    enf_ctx* ctx = ch->ctx;
+    if (N < 1) return fail(ctx, ENF_ERR_INVALID, "N must be >= 1");
+    int rc = enf_negll_grad_partial(ch, x, N, nullptr, nullptr);
+    if (rc != ENF_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(ch->h_sums, ch->d_sums, size_t(ch->n_raw) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return enf_negll_grad_finish(ch, ch->h_sums, N, flags, negll, grads_host);
+}
+
+// ------------------------------------------------------------------ NCCL group
+extern "C" int enf_group_unique_id(void* id_out) {
+    if (!id_out) return fail(nullptr, ENF_ERR_INVALID, "id_out is NULL");
+    int rc = load_nccl(nullptr);
+    if (rc != ENF_OK) return rc;
+    static_assert(sizeof(ncclUniqueId) == ENF_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NC(nullptr, g_nccl.GetUniqueId(&id));
+    std::memcpy(id_out, &id, sizeof id);
+    return ENF_OK;
+}
+
+extern "C" int enf_group_init(enf_ctx* ctx, int nranks, int rank, const void* id_bytes) {
+    if (!ctx || !id_bytes) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, ENF_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+    if (ctx->comm) return fail(ctx, ENF_ERR_INVALID, "group already initialised");
+    int rc = load_nccl(ctx);
+    if (rc != ENF_OK) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes, sizeof id);
+    NC(ctx, g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return ENF_OK;
+}
+
+extern "C" int enf_group_destroy(enf_ctx* ctx) {
+    if (!ctx) return fail(nullptr, ENF_ERR_INVALID, "ctx is NULL");
+    if (ctx->comm) {
+        CU(ctx, cudaSetDevice(ctx->device));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        NC(ctx, g_nccl.CommDestroy(ctx->comm));
+        ctx->comm = nullptr;
+    }
+    ctx->nranks = 1;
+    ctx->rank = 0;
+    return ENF_OK;
+}
+
+extern "C" int enf_negll_grad_group(enf_chain* ch, const void* x, int64_t N_local, int flags, double* negll,
+                                    void* grads_host) {
+    if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
+    enf_ctx* ctx = ch->ctx;
+    if (!ctx->comm) return fail(ctx, ENF_ERR_INVALID, "enf_group_init has not been called on this context");
+    int rc = enf_negll_grad_partial(ch, x, N_local, nullptr, nullptr);
+    if (rc != ENF_OK) return rc;
+    // append N_local so one all-reduce also yields the global batch size
+    ch->h_sums[ch->n_raw] = double(N_local);
+    CU(ctx, cudaMemcpyAsync(ch->d_sums + ch->n_raw, ch->h_sums + ch->n_raw, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx, g_nccl.AllReduce(ch->d_sums, ch->d_sums, size_t(ch->n_raw + 1), ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ch->h_sums, ch->d_sums, size_t(ch->n_raw + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t N_global = int64_t(std::llround(ch->h_sums[ch->n_raw]));
+    return enf_negll_grad_finish(ch, ch->h_sums, N_global, flags, negll, grads_host);
+}

@@ -1,0 +1,151 @@
+// Instantiation table and launchers of the fused chain kernels (enf_chain.cuh).
+#include "enf_chain.cuh"
+#include "enf_launch.h"
+
+#include <map>
+#include <mutex>
+
+namespace enf {
+
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int n_blocks, int n_raw,
+                                       double* __restrict__ sums, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_raw) return;
+    double s = accumulate ? sums[i] : 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += partials[size_t(b) * n_raw + i];
+    sums[i] = s;
+}
+
+bool select_f32_vec(int LG, int CH, KernelSet& k);
+bool select_f32_scalar(int LG, int CH, KernelSet& k);
+bool select_f64_vec(int LG, int CH, KernelSet& k);
+bool select_f64_scalar(int LG, int CH, KernelSet& k);
+bool select_pack(int dtype, int PD, int mode, KernelSet& k);
+
+bool select_kernels(int dtype, const Plan& plan, int mode, KernelSet& k) {
+    if (plan.packed) {
+        if (mode != MODE_PACK && mode != MODE_PACKU) return false;
+        return select_pack(dtype, plan.PD, mode, k);
+    }
+    if (mode != MODE_VEC && mode != MODE_SCALAR) return false;
+    if (dtype == 0) return mode == MODE_VEC ? select_f32_vec(plan.LG, plan.CH, k) : select_f32_scalar(plan.LG, plan.CH, k);
+    return mode == MODE_VEC ? select_f64_vec(plan.LG, plan.CH, k) : select_f64_scalar(plan.LG, plan.CH, k);
+}
+
+bool make_plan(int dtype, int D, Plan& plan) {
+    const int VE = dtype == 0 ? 4 : 2;
+    plan = Plan{};
+    if (D < 1) return false;
+    if (D < VE && VE % D == 0) {
+        plan.packed = true;
+        plan.PD = D;
+        plan.LG = 0;
+        plan.CH = 1;
+        plan.Dp = VE;
+        return true;
+    }
+    const int nvec = (D + VE - 1) / VE;
+    int LG = 0;
+    while ((1 << LG) < nvec && LG < 5) ++LG;
+    int CH = (nvec + (1 << LG) - 1) >> LG;
+    int CHp = 1;
+    while (CHp < CH) CHp <<= 1;
+    if (CHp > 8) return false;
+    plan.packed = false;
+    plan.PD = 0;
+    plan.LG = LG;
+    plan.CH = CHp;
+    plan.Dp = (1 << LG) * CHp * VE;
+    return true;
+}
+
+// ---- occupancy / attribute cache -------------------------------------------------
+namespace {
+std::mutex g_mu;
+std::map<std::pair<const void*, size_t>, int> g_occ;   // (kernel, smem) -> CTAs per SM
+std::map<const void*, size_t> g_smem_set;               // kernel -> max dynamic smem opted in
+
+cudaError_t prepare_kernel(const void* fn, size_t smem, int& ctas_per_sm) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (smem > 48 * 1024) {
+        auto it = g_smem_set.find(fn);
+        if (it == g_smem_set.end() || it->second < smem) {
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            g_smem_set[fn] = smem;
+        }
+    }
+    auto key = std::make_pair(fn, smem);
+    auto it = g_occ.find(key);
+    if (it == g_occ.end()) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, NT, smem);
+        if (e != cudaSuccess) return e;
+        if (nb < 1) return cudaErrorLaunchOutOfResources;
+        it = g_occ.emplace(key, nb).first;
+    }
+    ctas_per_sm = it->second;
+    return cudaSuccess;
+}
+}  // namespace
+
+size_t fwd_smem_bytes(int dtype, const ChainDesc& d) { return size_t(d.n_consts) * (dtype == 0 ? 4 : 8); }
+
+size_t grad_smem_bytes(int dtype, const ChainDesc& d, const KernelSet& k, bool grad) {
+    const size_t es = dtype == 0 ? 4 : 8;
+    size_t n = size_t((d.n_consts + 3) & ~3);
+    if (grad) {
+        n += size_t(d.n_save) * k.grad_tile_elems * NT;
+        n += size_t(d.n_rowslots) * k.CH * k.VE * NT;
+        n += size_t(d.n_scalars) * NT;
+    }
+    return n * es;
+}
+
+cudaError_t launch_fwd(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
+                       void* y, void* ladj, int64_t N, double ladj_const, int sm_count, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    const void* fn = ladj ? k.fwd_ladj : k.fwd;
+    const size_t smem = fwd_smem_bytes(dtype, desc);
+    int per_sm = 0;
+    cudaError_t e = prepare_kernel(fn, smem, per_sm);
+    if (e != cudaSuccess) return e;
+    const int64_t items = (N + k.LN - 1) / k.LN;
+    const int64_t tiles = (items + k.fwd_items_per_tile - 1) / k.fwd_items_per_tile;
+    const int64_t cap = int64_t(per_sm) * sm_count;
+    const unsigned grid = unsigned(tiles < cap ? tiles : cap);
+    float lc32 = float(ladj_const);
+    double lc64 = ladj_const;
+    void* args[] = {const_cast<ChainDesc*>(&desc), &consts, &x, &y, &ladj, &N,
+                    dtype == 0 ? static_cast<void*>(&lc32) : static_cast<void*>(&lc64)};
+    return cudaLaunchKernel(fn, dim3(grid), dim3(NT), args, smem, st);
+}
+
+cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
+                        int64_t N, bool grad, double* partials, int max_blocks, int* blocks_used, int sm_count,
+                        cudaStream_t st) {
+    const void* fn = grad ? k.grad : k.negll;
+    const size_t smem = grad_smem_bytes(dtype, desc, k, grad);
+    int per_sm = 0;
+    cudaError_t e = prepare_kernel(fn, smem, per_sm);
+    if (e != cudaSuccess) return e;
+    const int64_t items = (N + k.LN - 1) / k.LN;
+    int64_t tiles = (items + k.grad_items_per_tile - 1) / k.grad_items_per_tile;
+    if (tiles < 1) tiles = 1;
+    int64_t cap = int64_t(per_sm) * sm_count;
+    if (cap > max_blocks) cap = max_blocks;
+    const unsigned grid = unsigned(tiles < cap ? tiles : cap);
+    *blocks_used = int(grid);
+    void* args[] = {const_cast<ChainDesc*>(&desc), &consts, &x, &N, &partials};
+    return cudaLaunchKernel(fn, dim3(grid), dim3(NT), args, smem, st);
+}
+
+cudaError_t launch_reduce(const double* partials, int n_blocks, int n_raw, double* sums, bool accumulate,
+                          cudaStream_t st) {
+    const int threads = 128;
+    const int grid = (n_raw + threads - 1) / threads;
+    reduce_partials_kernel<<<grid, threads, 0, st>>>(partials, n_blocks, n_raw, sums, accumulate ? 1 : 0);
+    return cudaGetLastError();
+}
+
+}  // namespace enf

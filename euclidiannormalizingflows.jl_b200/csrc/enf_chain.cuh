@@ -1,0 +1,636 @@
+// Fused trafo-chain kernels (sm_100a): one pass over a D x N column-major sample
+// matrix applies a whole chain (CenterStretch/Contract, Johnson/Inv, ScaleShift,
+// Householder stacks), optionally with the per-sample ladj, or with the
+// whitening loss and the raw parameter-gradient sums.
+//
+// Data layout / thread mapping ("lane groups").  A sample is a contiguous column
+// of D elements.  It is split into 16-byte vectors (VE = 4 floats / 2 doubles);
+// a group of G = 2^LG adjacent lanes owns one sample, lane g of the group owns
+// vectors g, g+G, ... (CH of them).  A warp therefore reads 32 consecutive
+// 16-byte vectors per load instruction: every HBM access is a fully coalesced
+// 128-bit LDG/STG and the per-sample registers are filled without a transpose.
+// Row-wise parameters become per-lane constants (the lane's rows never change),
+// Householder dot products and the per-sample ladj are finished with log2(G)
+// xor-shuffles inside the group.  D that is not a multiple of VE, or unaligned
+// pointers, use the same mapping with masked scalar accesses (MODE_SCALAR);
+// D < VE (D dividing VE) packs VE/D samples into one vector (MODE_PACK, or
+// MODE_PACKU with scalar accesses when a pointer is not 16-byte aligned).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "enf_math.cuh"
+
+namespace enf {
+
+constexpr int MAX_OPS = 24;
+constexpr int NT = 256;  // threads per CTA of the chain kernels
+
+enum : int { OP_CS = 0, OP_CC = 1, OP_JO = 2, OP_JI = 3, OP_SS = 4, OP_HH = 5 };
+enum : int { MODE_VEC = 0, MODE_SCALAR = 1, MODE_PACK = 2, MODE_PACKU = 3 };  // PACKU: pack layout, unaligned pointers
+
+struct DevOp {
+    int kind;  // OP_*
+    int K;     // reflections (OP_HH)
+    int coff;  // offset of this op's constants (elements) in the constants block
+    int roff;  // first per-row raw-sum slot of this op
+    int soff;  // first scalar raw-sum slot (OP_HH: sum_j p'_j q'_j per reflection)
+    int save;  // index of the saved-input tile (elementwise ops), -1 for OP_HH
+};
+
+struct ChainDesc {
+    int n_ops;
+    int D;           // rows
+    int Dp;          // padded rows (G*CH*VE >= D, or VE in MODE_PACK); constants are padded with neutral values
+    int n_consts;    // elements in the constants block
+    int n_save;      // saved-input tiles the gradient kernel needs
+    int n_rowslots;  // raw-sum slots holding one value per row
+    int n_scalars;   // raw-sum slots holding one value per chain
+    DevOp ops[MAX_OPS];
+};
+
+__host__ __device__ constexpr int n_consts_of(int kind, int K) {
+    return (kind == OP_CS || kind == OP_CC) ? 6 : (kind == OP_JO || kind == OP_JI) ? 4 : kind == OP_SS ? 2 : K;
+}
+__host__ __device__ constexpr int n_rowslots_of(int kind, int K) {
+    return (kind == OP_CS || kind == OP_CC) ? 3 : (kind == OP_JO || kind == OP_JI) ? 4 : kind == OP_SS ? 2 : K;
+}
+
+// ------------------------------------------------------------------ 16-byte accessors
+template <typename T> struct Vec;
+template <> struct Vec<float> { static constexpr int VE = 4; };
+template <> struct Vec<double> { static constexpr int VE = 2; };
+
+__device__ __forceinline__ void ld16_stream(const float* p, float (&o)[4]) {
+    float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+__device__ __forceinline__ void ld16_stream(const double* p, double (&o)[2]) {
+    double2 t = __ldcs(reinterpret_cast<const double2*>(p));
+    o[0] = t.x; o[1] = t.y;
+}
+__device__ __forceinline__ void st16_stream(float* p, const float (&o)[4]) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3]));
+}
+__device__ __forceinline__ void st16_stream(double* p, const double (&o)[2]) {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(o[0], o[1]));
+}
+__device__ __forceinline__ void ld16_shared(const float* p, float (&o)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+__device__ __forceinline__ void ld16_shared(const double* p, double (&o)[2]) {
+    double2 t = *reinterpret_cast<const double2*>(p);
+    o[0] = t.x; o[1] = t.y;
+}
+
+// ------------------------------------------------------------------ configuration
+template <typename T_, int LG_, int CH_, int MODE_, int PD_, int SPT_>
+struct Cfg {
+    using T = T_;
+    static constexpr int LG = LG_;
+    static constexpr int G = 1 << LG_;
+    static constexpr int CH = CH_;
+    static constexpr int MODE = MODE_;
+    static constexpr int PD = PD_;  // rows per sample in MODE_PACK (divides VE), else 0
+    static constexpr int SPT = SPT_;
+    static constexpr int VE = Vec<T_>::VE;
+    static constexpr bool PACKED = (MODE_ == MODE_PACK || MODE_ == MODE_PACKU);
+    static constexpr int LN = PACKED ? (Vec<T_>::VE / (PD_ > 0 ? PD_ : 1)) : 1;  // samples per tile row of a thread
+    static constexpr int PDD = PD_ > 0 ? PD_ : 1;
+    static constexpr int SB = NT / G;  // samples (packed: vectors) per CTA step
+    static_assert(!PACKED || (LG_ == 0 && CH_ == 1 && PD_ > 0), "pack mode is one vector per thread");
+    // ladj / mask slot of element e of a vector
+    static __host__ __device__ constexpr int slot(int e) { return PACKED ? e / PDD : 0; }
+};
+
+template <class C> struct Tile {
+    typename C::T v[C::SPT][C::CH][C::VE];
+};
+
+// first sample (MODE_PACK: first vector) of row u of a tile, for this thread
+template <class C>
+__device__ __forceinline__ int64_t tile_item(int64_t tile, int u) {
+    return (tile * C::SPT + u) * C::SB + (threadIdx.x >> C::LG);
+}
+
+// Loads tile `tile` of this thread.  nv[u] = number of valid samples in tile row u
+// (0/1 in the lane-group modes, 0..LN in the packed modes); invalid elements read 0.
+template <class C>
+__device__ __forceinline__ void load_tile(const typename C::T* x, int64_t N, int D, int64_t tile,
+                                          Tile<C>& t, int (&nv)[C::SPT]) {
+    using T = typename C::T;
+    const int g = threadIdx.x & (C::G - 1);
+#pragma unroll
+    for (int u = 0; u < C::SPT; ++u) {
+        const int64_t s = tile_item<C>(tile, u);
+        if (C::PACKED) {
+            const int64_t left = N - s * C::LN;
+            nv[u] = left <= 0 ? 0 : (left >= C::LN ? C::LN : int(left));
+            if (C::MODE == MODE_PACK && nv[u] == C::LN) ld16_stream(x + s * C::VE, t.v[u][0]);
+            else {
+#pragma unroll
+                for (int e = 0; e < C::VE; ++e)
+                    t.v[u][0][e] = (C::slot(e) < nv[u]) ? __ldcs(x + s * C::VE + e) : T(0);
+            }
+        } else {
+            nv[u] = s < N ? 1 : 0;
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q) {
+                const int row0 = (q * C::G + g) * C::VE;
+                if (C::MODE == MODE_VEC) {
+                    if (nv[u] && row0 < D) ld16_stream(x + s * D + row0, t.v[u][q]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < C::VE; ++e) t.v[u][q][e] = T(0);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < C::VE; ++e)
+                        t.v[u][q][e] = (nv[u] && row0 + e < D) ? __ldcs(x + s * D + row0 + e) : T(0);
+                }
+            }
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void store_tile(typename C::T* y, int D, int64_t tile, const Tile<C>& t,
+                                           const int (&nv)[C::SPT]) {
+    const int g = threadIdx.x & (C::G - 1);
+#pragma unroll
+    for (int u = 0; u < C::SPT; ++u) {
+        if (nv[u] == 0) continue;
+        const int64_t s = tile_item<C>(tile, u);
+        if (C::PACKED) {
+            if (C::MODE == MODE_PACK && nv[u] == C::LN) st16_stream(y + s * C::VE, t.v[u][0]);
+            else {
+#pragma unroll
+                for (int e = 0; e < C::VE; ++e)
+                    if (C::slot(e) < nv[u]) __stcs(y + s * C::VE + e, t.v[u][0][e]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q) {
+                const int row0 = (q * C::G + g) * C::VE;
+                if (C::MODE == MODE_VEC) {
+                    if (row0 < D) st16_stream(y + s * D + row0, t.v[u][q]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < C::VE; ++e)
+                        if (row0 + e < D) __stcs(y + s * D + row0 + e, t.v[u][q][e]);
+                }
+            }
+        }
+    }
+}
+
+// xor-shuffle sum over the G lanes of a group
+template <class C, typename T>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+    for (int off = C::G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// offset of this lane's constants for vector q inside one length-Dp constant array
+template <class C>
+__device__ __forceinline__ int const_off(int q) {
+    return C::PACKED ? 0 : (q * C::G + (threadIdx.x & (C::G - 1))) * C::VE;
+}
+
+// ------------------------------------------------------------------ forward ops on a tile
+template <class C, bool LADJ>
+__device__ __forceinline__ void apply_op_fwd(const DevOp& op, const typename C::T* s_c, int Dp, Tile<C>& t,
+                                             typename C::T (&l)[C::SPT][C::LN]) {
+    using T = typename C::T;
+    constexpr int VE = C::VE;
+    const T* cb = s_c + op.coff;
+    if (op.kind == OP_HH) {
+        for (int k = 0; k < op.K; ++k) {
+            T vk[C::CH][VE];
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q) ld16_shared(cb + k * Dp + const_off<C>(q), vk[q]);
+            if (C::PACKED) {
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                    for (int p = 0; p < C::LN; ++p) {
+                        T d = T(0);
+#pragma unroll
+                        for (int e = 0; e < C::PD; ++e) d = Prim<T>::fma_(vk[0][p * C::PD + e], t.v[u][0][p * C::PD + e], d);
+#pragma unroll
+                        for (int e = 0; e < C::PD; ++e)
+                            t.v[u][0][p * C::PD + e] = Prim<T>::fma_(-d, vk[0][p * C::PD + e], t.v[u][0][p * C::PD + e]);
+                    }
+            } else {
+                T d[C::SPT];
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u) {
+                    d[u] = T(0);
+#pragma unroll
+                    for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) d[u] = Prim<T>::fma_(vk[q][e], t.v[u][q][e], d[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u) d[u] = group_sum<C>(d[u]);
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                    for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) t.v[u][q][e] = Prim<T>::fma_(-d[u], vk[q][e], t.v[u][q][e]);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < C::CH; ++q) {
+        const int co = const_off<C>(q);
+        T c0[VE], c1[VE], c2[VE], c3[VE];
+        ld16_shared(cb + 0 * Dp + co, c0);
+        ld16_shared(cb + 1 * Dp + co, c1);
+        if (op.kind != OP_SS) {
+            ld16_shared(cb + 2 * Dp + co, c2);
+            ld16_shared(cb + 3 * Dp + co, c3);
+        }
+        switch (op.kind) {
+            case OP_SS:
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                    for (int e = 0; e < VE; ++e) t.v[u][q][e] = Prim<T>::fma_(t.v[u][q][e], c0[e], c1[e]);
+                break;
+            case OP_CS:
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                    for (int e = 0; e < VE; ++e)
+                        t.v[u][q][e] = cs_fwd<T>(t.v[u][q][e], c0[e], c1[e], c2[e], c3[e], l[u][C::slot(e)]);
+                break;
+            case OP_CC:
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                    for (int e = 0; e < VE; ++e)
+                        t.v[u][q][e] = cc_fwd<T>(t.v[u][q][e], c0[e], c1[e], c2[e], c3[e], l[u][C::slot(e)]);
+                break;
+            case OP_JO:
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                    for (int e = 0; e < VE; ++e)
+                        t.v[u][q][e] = jo_fwd<T>(t.v[u][q][e], c0[e], c1[e], c2[e], c3[e], l[u][C::slot(e)]);
+                break;
+            default:  // OP_JI
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                    for (int e = 0; e < VE; ++e)
+                        t.v[u][q][e] = ji_fwd<T>(t.v[u][q][e], c0[e], c1[e], c2[e], c3[e], l[u][C::slot(e)]);
+                break;
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void stage_constants(const ChainDesc& desc, const typename C::T* consts, typename C::T* s_c) {
+    for (int i = threadIdx.x; i < desc.n_consts; i += NT) s_c[i] = consts[i];
+    __syncthreads();
+}
+
+template <class C>
+__device__ __forceinline__ int64_t num_tiles(int64_t N) {
+    const int64_t items = C::PACKED ? ((N + C::LN - 1) / C::LN) : N;
+    const int64_t per_tile = int64_t(C::SB) * C::SPT;
+    return (items + per_tile - 1) / per_tile;
+}
+
+// ------------------------------------------------------------------ forward (+ ladj) kernel
+// F1/F2 of SURVEY §2.3: (f::Trafo)(x) and with_logabsdet_jacobian(f, x) for a whole chain.
+template <class C, bool LADJ>
+__global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ ChainDesc desc,
+                                                       const typename C::T* __restrict__ consts,
+                                                       const typename C::T* x, typename C::T* y,
+                                                       typename C::T* ladj, int64_t N, typename C::T ladj_const) {
+    using T = typename C::T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_c = reinterpret_cast<T*>(smem_raw);
+    stage_constants<C>(desc, consts, s_c);
+    const int D = desc.D, Dp = desc.Dp;
+    const int64_t nt = num_tiles<C>(N);
+    for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+        Tile<C> t;
+        int nv[C::SPT];
+        T l[C::SPT][C::LN];
+        load_tile<C>(x, N, D, tile, t, nv);
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int p = 0; p < C::LN; ++p) l[u][p] = T(0);
+        for (int o = 0; o < desc.n_ops; ++o) apply_op_fwd<C, true>(desc.ops[o], s_c, Dp, t, l);
+        store_tile<C>(y, D, tile, t, nv);
+        if (LADJ) {
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u) {
+                const int64_t s = tile_item<C>(tile, u);
+                if (C::PACKED) {
+#pragma unroll
+                    for (int p = 0; p < C::LN; ++p)
+                        if (p < nv[u]) __stcs(ladj + s * C::LN + p, l[u][p] + ladj_const);
+                } else {
+                    const T tot = group_sum<C>(l[u][0]);
+                    if (nv[u] && (threadIdx.x & (C::G - 1)) == 0) __stcs(ladj + s, tot + ladj_const);
+                }
+            }
+        }
+    }
+}
+
+// backward of one elementwise op on vector q of a tile: gt <- input cotangent,
+// ra[k][e] += m[u] * raw integrand k
+template <class C, int KIND>
+__device__ __forceinline__ void bwd_elem(const Tile<C>& zt, Tile<C>& gt, int q, const typename C::T (&m)[C::SPT][C::LN],
+                                         const typename C::T (&c0)[C::VE], const typename C::T (&c1)[C::VE],
+                                         const typename C::T (&c2)[C::VE], const typename C::T (&c3)[C::VE],
+                                         const typename C::T (&c4)[C::VE], const typename C::T (&c5)[C::VE],
+                                         typename C::T (&ra)[4][C::VE]) {
+    using T = typename C::T;
+#pragma unroll
+    for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+        for (int e = 0; e < C::VE; ++e) {
+            T r[4] = {T(0), T(0), T(0), T(0)};
+            const T xin = zt.v[u][q][e], G = gt.v[u][q][e];
+            T gx;
+            if (KIND == OP_SS) {
+                r[0] = G * xin;
+                r[1] = G;
+                gx = G * c0[e];
+            } else if (KIND == OP_CS) {
+                gx = cs_bwd<T>(xin, G, c0[e], c1[e], c2[e], c3[e], c4[e], c5[e], r);
+            } else if (KIND == OP_CC) {
+                gx = cc_bwd<T>(xin, G, c0[e], c1[e], c2[e], c3[e], c4[e], c5[e], r);
+            } else if (KIND == OP_JO) {
+                gx = jo_bwd<T>(xin, G, c0[e], c1[e], c2[e], c3[e], r);
+            } else {
+                gx = ji_bwd<T>(xin, G, c0[e], c1[e], c2[e], c3[e], r);
+            }
+            gt.v[u][q][e] = gx;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ra[k][e] = Prim<T>::fma_(m[u][C::slot(e)], r[k], ra[k][e]);
+        }
+}
+
+// ------------------------------------------------------------------ loss / gradient kernel
+// F3 of SURVEY §2.3: mvnormal_negll_trafo and the reverse pass of
+// mvnormal_negll_trafograd (src/optimize_whitening.jl:7-22) in one pass over x.
+// Per CTA it emits `n_raw` float64 partial sums:
+//   [n_rowslots][Dp] per-row raw sums | [n_scalars] | sum_j 1/2 |y_j|^2 | sum_j ladj_j (variable part)
+// which reduce_partials_kernel adds up in a fixed order (bitwise reproducible).
+template <class C, bool GRAD>
+__global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ ChainDesc desc,
+                                                        const typename C::T* __restrict__ consts,
+                                                        const typename C::T* __restrict__ x, int64_t N,
+                                                        double* __restrict__ partials) {
+    using T = typename C::T;
+    using P = Prim<T>;
+    constexpr int VE = C::VE;
+    constexpr int TE = C::SPT * C::CH * VE;  // tile elements per thread
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_c = reinterpret_cast<T*>(smem_raw);
+    const int n_consts_al = (desc.n_consts + 3) & ~3;
+    T* s_save = s_c + n_consts_al;                                  // [n_save][TE][NT]
+    T* s_acc = s_save + (GRAD ? size_t(desc.n_save) * TE * NT : 0);  // [n_rowslots][CH*VE][NT]
+    T* s_sc = s_acc + (GRAD ? size_t(desc.n_rowslots) * C::CH * VE * NT : 0);  // [n_scalars][NT]
+    stage_constants<C>(desc, consts, s_c);
+    const int tid = threadIdx.x;
+    const int g = tid & (C::G - 1);
+    if (GRAD) {
+        for (int i = 0; i < desc.n_rowslots * C::CH * VE; ++i) s_acc[size_t(i) * NT + tid] = T(0);
+        for (int i = 0; i < desc.n_scalars; ++i) s_sc[size_t(i) * NT + tid] = T(0);
+    }
+    const int D = desc.D, Dp = desc.Dp;
+    T loss_y = T(0), loss_l = T(0);
+    const int64_t nt = num_tiles<C>(N);
+    for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+        Tile<C> zt;
+        int nv[C::SPT];
+        T l[C::SPT][C::LN];
+        T m[C::SPT][C::LN];  // 1 for real samples, 0 for the padding of the last tile
+        load_tile<C>(x, N, D, tile, zt, nv);
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int p = 0; p < C::LN; ++p) {
+                m[u][p] = p < nv[u] ? T(1) : T(0);
+                l[u][p] = T(0);
+            }
+        // ---- forward, saving the input of every elementwise op
+        for (int o = 0; o < desc.n_ops; ++o) {
+            const DevOp op = desc.ops[o];
+            if (GRAD && op.save >= 0) {
+                T* sv = s_save + size_t(op.save) * TE * NT + tid;
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                    for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) sv[size_t((u * C::CH + q) * VE + e) * NT] = zt.v[u][q][e];
+            }
+            apply_op_fwd<C, true>(op, s_c, Dp, zt, l);
+        }
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u) {
+            T sy = T(0);
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                for (int e = 0; e < VE; ++e) sy = P::fma_(m[u][C::slot(e)] * zt.v[u][q][e], zt.v[u][q][e], sy);
+            loss_y = P::fma_(T(0.5), sy, loss_y);
+#pragma unroll
+            for (int p = 0; p < C::LN; ++p) loss_l = P::fma_(m[u][p], l[u][p], loss_l);
+        }
+        if constexpr (!GRAD) continue;
+        // ---- backward: gt = N dL/d(activation), seeded with y (src/optimize_whitening.jl:12)
+        Tile<C> gt;
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                for (int e = 0; e < VE; ++e) gt.v[u][q][e] = zt.v[u][q][e];
+        for (int o = desc.n_ops - 1; o >= 0; --o) {
+            const DevOp op = desc.ops[o];
+            const T* cb = s_c + op.coff;
+            if (op.kind == OP_HH) {
+                // reverse sweep with recomputation (src/householder_trafo.jl:88-114)
+                for (int k = op.K - 1; k >= 0; --k) {
+                    T vk[C::CH][VE];
+#pragma unroll
+                    for (int q = 0; q < C::CH; ++q) ld16_shared(cb + k * Dp + const_off<C>(q), vk[q]);
+                    T* acc = s_acc + size_t(op.roff + k) * C::CH * VE * NT + tid;
+                    T* sc = s_sc + size_t(op.soff + k) * NT + tid;
+                    T a1[C::CH][VE];
+                    T a2 = T(0);
+#pragma unroll
+                    for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) a1[q][e] = T(0);
+                    if (C::PACKED) {
+#pragma unroll
+                        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                            for (int p = 0; p < C::LN; ++p) {
+                                T po = T(0), qd = T(0);
+#pragma unroll
+                                for (int e = 0; e < C::PD; ++e) {
+                                    po = P::fma_(vk[0][p * C::PD + e], zt.v[u][0][p * C::PD + e], po);
+                                    qd = P::fma_(vk[0][p * C::PD + e], gt.v[u][0][p * C::PD + e], qd);
+                                }
+                                const T pm = -po * m[u][p], qm = qd * m[u][p];
+#pragma unroll
+                                for (int e = 0; e < C::PD; ++e) {
+                                    const int i = p * C::PD + e;
+                                    zt.v[u][0][i] = P::fma_(-po, vk[0][i], zt.v[u][0][i]);
+                                    a1[0][i] = P::fma_(pm, gt.v[u][0][i], P::fma_(qm, zt.v[u][0][i], a1[0][i]));
+                                    gt.v[u][0][i] = P::fma_(-qd, vk[0][i], gt.v[u][0][i]);
+                                }
+                                a2 = P::fma_(pm, qd, a2);
+                            }
+                    } else {
+                        T po[C::SPT], qd[C::SPT];
+#pragma unroll
+                        for (int u = 0; u < C::SPT; ++u) {
+                            po[u] = T(0);
+                            qd[u] = T(0);
+#pragma unroll
+                            for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                                for (int e = 0; e < VE; ++e) {
+                                    po[u] = P::fma_(vk[q][e], zt.v[u][q][e], po[u]);
+                                    qd[u] = P::fma_(vk[q][e], gt.v[u][q][e], qd[u]);
+                                }
+                        }
+#pragma unroll
+                        for (int u = 0; u < C::SPT; ++u) {
+                            po[u] = group_sum<C>(po[u]);
+                            qd[u] = group_sum<C>(qd[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < C::SPT; ++u) {
+                            const T pm = -po[u] * m[u][0], qm = qd[u] * m[u][0];
+#pragma unroll
+                            for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                                for (int e = 0; e < VE; ++e) {
+                                    zt.v[u][q][e] = P::fma_(-po[u], vk[q][e], zt.v[u][q][e]);  // reflection input
+                                    a1[q][e] = P::fma_(pm, gt.v[u][q][e], P::fma_(qm, zt.v[u][q][e], a1[q][e]));
+                                    gt.v[u][q][e] = P::fma_(-qd[u], vk[q][e], gt.v[u][q][e]);
+                                }
+                            a2 = P::fma_(pm, qd[u], a2);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) acc[size_t(q * VE + e) * NT] += a1[q][e];
+                    if (g == 0) *sc += a2;
+                }
+                continue;
+            }
+            // elementwise op: reload its input, differentiate
+            {
+                const T* sv = s_save + size_t(op.save) * TE * NT + tid;
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                    for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) zt.v[u][q][e] = sv[size_t((u * C::CH + q) * VE + e) * NT];
+            }
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q) {
+                const int co = const_off<C>(q);
+                T c0[VE], c1[VE], c2[VE], c3[VE], c4[VE], c5[VE];
+                ld16_shared(cb + 0 * Dp + co, c0);
+                ld16_shared(cb + 1 * Dp + co, c1);
+                if (op.kind != OP_SS) {
+                    ld16_shared(cb + 2 * Dp + co, c2);
+                    ld16_shared(cb + 3 * Dp + co, c3);
+                }
+                if (op.kind == OP_CS || op.kind == OP_CC) {
+                    ld16_shared(cb + 4 * Dp + co, c4);
+                    ld16_shared(cb + 5 * Dp + co, c5);
+                }
+                T ra[4][VE];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int e = 0; e < VE; ++e) ra[k][e] = T(0);
+                switch (op.kind) {
+                    case OP_SS: bwd_elem<C, OP_SS>(zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                    case OP_CS: bwd_elem<C, OP_CS>(zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                    case OP_CC: bwd_elem<C, OP_CC>(zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                    case OP_JO: bwd_elem<C, OP_JO>(zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                    default: bwd_elem<C, OP_JI>(zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                }
+                const int nr = n_rowslots_of(op.kind, 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < nr) {
+                        T* acc = s_acc + (size_t(op.roff + k) * C::CH + q) * VE * NT + tid;
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) acc[size_t(e) * NT] += ra[k][e];
+                    }
+            }
+        }
+    }
+    // ---- CTA reduction in float64, fixed order
+    const int n_raw = desc.n_rowslots * Dp + desc.n_scalars + 2;
+    double* out = partials + size_t(blockIdx.x) * n_raw;
+    __syncthreads();
+    if (GRAD) {
+        for (int pi = tid; pi < desc.n_rowslots * Dp; pi += NT) {
+            const int rs = pi / Dp, row = pi - rs * Dp;
+            const int vecidx = row / VE, e = row - vecidx * VE;
+            int q, gg;
+            if (C::PACKED) { q = 0; gg = 0; }
+            else { q = vecidx >> C::LG; gg = vecidx & (C::G - 1); }
+            const T* acc = s_acc + ((size_t(rs) * C::CH + q) * VE + e) * NT;
+            double s = 0.0;
+            for (int j = gg; j < NT; j += C::G) s += double(acc[j]);
+            out[pi] = s;
+        }
+        for (int k = tid; k < desc.n_scalars; k += NT) {
+            const T* sc = s_sc + size_t(k) * NT;
+            double s = 0.0;
+            for (int j = 0; j < NT; j += C::G) s += double(sc[j]);
+            out[desc.n_rowslots * Dp + k] = s;
+        }
+    } else {
+        for (int pi = tid; pi < desc.n_rowslots * Dp + desc.n_scalars; pi += NT) out[pi] = 0.0;
+    }
+    // loss partials: warp shuffle, then one double per warp through shared memory
+    __shared__ double s_loss[2][NT / 32];
+    double ly = double(loss_y), ll = double(loss_l);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ly += __shfl_xor_sync(0xffffffffu, ly, off);
+        ll += __shfl_xor_sync(0xffffffffu, ll, off);
+    }
+    if ((tid & 31) == 0) { s_loss[0][tid >> 5] = ly; s_loss[1][tid >> 5] = ll; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < NT / 32; ++w) { a += s_loss[0][w]; b += s_loss[1][w]; }
+        out[n_raw - 2] = a;
+        out[n_raw - 1] = b;
+    }
+}
+
+// sums[i] (+)= sum_b partials[b][i], b ascending: deterministic
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int n_blocks, int n_raw,
+                                       double* __restrict__ sums, int accumulate);
+
+}  // namespace enf

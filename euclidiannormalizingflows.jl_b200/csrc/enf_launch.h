@@ -1,0 +1,47 @@
+// Host-side interface between the C ABI (enf_abi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace enf {
+
+struct ChainDesc;
+
+// How a D-row sample is mapped onto lanes (see enf_chain.cuh).
+struct Plan {
+    bool packed = false;  // D < VE, VE % D == 0: several samples per 16-byte vector
+    int PD = 0;           // rows per sample when packed
+    int LG = 0;           // log2(lanes per sample)
+    int CH = 1;           // 16-byte vectors per lane per sample
+    int Dp = 0;           // padded row count the constants block is laid out for
+};
+
+struct KernelSet {
+    const void* fwd = nullptr;
+    const void* fwd_ladj = nullptr;
+    const void* grad = nullptr;
+    const void* negll = nullptr;
+    int fwd_items_per_tile = 0;
+    int grad_items_per_tile = 0;
+    int grad_tile_elems = 0;
+    int LN = 1;  // samples per item (packed modes)
+    int G = 1, CH = 1, VE = 4;
+};
+
+bool make_plan(int dtype, int D, Plan& plan);
+bool select_kernels(int dtype, const Plan& plan, int mode, KernelSet& k);
+size_t fwd_smem_bytes(int dtype, const ChainDesc& d);
+size_t grad_smem_bytes(int dtype, const ChainDesc& d, const KernelSet& k, bool grad);
+
+cudaError_t launch_fwd(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
+                       void* y, void* ladj, int64_t N, double ladj_const, int sm_count, cudaStream_t st);
+cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
+                        int64_t N, bool grad, double* partials, int max_blocks, int* blocks_used, int sm_count,
+                        cudaStream_t st);
+cudaError_t launch_reduce(const double* partials, int n_blocks, int n_raw, double* sums, bool accumulate,
+                          cudaStream_t st);
+
+// synthetic data (enf_fill.cu)
+cudaError_t launch_fill_normal(int dtype, void* x, int D, int64_t N, int64_t col0, uint64_t seed, cudaStream_t st);
+
+}  // namespace enf

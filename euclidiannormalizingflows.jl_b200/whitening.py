@@ -1,0 +1,93 @@
+"""optimize_whitening (src/optimize_whitening.jl:25-45) on device-resident samples.
+
+The fit loop stays on the host exactly as in the reference (L3 of SURVEY §1):
+per batch one fused loss+gradient call into the library, then the optimizer
+update and the struct rebuild.  Optimisers.jl is an un-vendored dependency of
+the reference; `ADAGrad` restates its published 0.2 rule (PARITY UNPINNED,
+SURVEY §8c), including the re-normalisation of HouseholderTrafo columns that
+the reference's functor performs on every rebuild (src/householder_trafo.jl:134-146).
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .device import B200Matrix, Context, default_context
+from .trafos import (ComposedFunction, HouseholderTrafo, Trafo, mvnormal_negll_trafograd, result_dtype)
+
+
+@dataclass
+class ADAGrad:
+    """Optimisers.ADAGrad(η = 1f-1, ϵ = eps(typeof(η))): state starts at ϵ,
+    acc += g², x -= η g / (√acc + ϵ)."""
+    eta: float = float(np.float32(0.1))
+    epsilon: float = float(np.finfo(np.float32).eps)
+
+
+def setup(opt: ADAGrad, trafo):
+    """Optimisers.setup(optimizer, trafo)."""
+    if isinstance(trafo, ComposedFunction):
+        return {"outer": setup(opt, trafo.outer), "inner": setup(opt, trafo.inner)}
+    return {n: np.full_like(np.asarray(getattr(trafo, n), dtype=np.float64), opt.epsilon) for n in trafo.fields}
+
+
+def _ht_normalize(V):
+    V = np.asarray(V)
+    if V.ndim == 1:
+        return V / np.sqrt((V * V).sum())
+    return V / np.sqrt((V * V).sum(0))[None, :]
+
+
+def update(opt: ADAGrad, state, trafo, grads):
+    """Optimisers.update(state, trafo, d_trafo) -> (state, trafo)."""
+    if isinstance(trafo, ComposedFunction):
+        so, to = update(opt, state["outer"], trafo.outer, grads["outer"])
+        si, ti = update(opt, state["inner"], trafo.inner, grads["inner"])
+        return {"outer": so, "inner": si}, ComposedFunction(to, ti)
+    new_state, kw = {}, {}
+    for n in trafo.fields:
+        x = np.asarray(getattr(trafo, n))
+        g = np.asarray(grads[n], dtype=np.float64).reshape(x.shape)
+        acc = state[n] + g * g
+        kw[n] = (x - g * opt.eta / (np.sqrt(acc) + opt.epsilon)).astype(x.dtype if x.dtype.kind == "f" else np.float64)
+        new_state[n] = acc
+    new = type(trafo)(**kw)
+    if isinstance(new, HouseholderTrafo):
+        new = HouseholderTrafo(_ht_normalize(new.V))
+    return new_state, new
+
+
+def batch_ranges(nsamples: int, nbatches: int) -> List[Tuple[int, int]]:
+    """src/optimize_whitening.jl:31-32: batchsize = round(Int, N / nbatches)
+    (ties to even); contiguous column ranges in fixed order, no shuffling, the
+    last one possibly short."""
+    batchsize = int(round(nsamples / nbatches))
+    if batchsize < 1:
+        raise ValueError("nbatches exceeds the number of samples")
+    return [(s, min(s + batchsize, nsamples)) for s in range(0, nsamples, batchsize)]
+
+
+def optimize_whitening(smpls, initial_trafo, optimizer: ADAGrad, *, nbatches: int = 100, nepochs: int = 100,
+                       optstate=None, negll_history=None, group: bool = False, ctx: Optional[Context] = None):
+    """Returns {'result', 'optimizer_state', 'negll_history'} like the
+    reference's NamedTuple.  `smpls`: D x N samples (B200Matrix, or a host array
+    that is uploaded once).  group=True: `smpls` holds this rank's column block
+    of every global batch (see dist.shard_batches); all ranks apply the
+    identical update from all-reduced sums."""
+    if not isinstance(smpls, B200Matrix):
+        X = np.asarray(smpls)
+        dt = result_dtype(initial_trafo, X.dtype if X.dtype.kind == "f" else np.float64)
+        smpls = B200Matrix.from_host(np.asarray(X, dtype=dt), ctx or default_context())
+    trafo = copy.deepcopy(initial_trafo)
+    state = copy.deepcopy(optstate) if optstate is not None else setup(optimizer, trafo)
+    hist: List[float] = []
+    ranges = batch_ranges(smpls.N, nbatches)
+    for _ in range(nepochs):
+        for (s, e) in ranges:
+            negll, d_trafo = mvnormal_negll_trafograd(trafo, smpls.cols(s, e), group=group)
+            state, trafo = update(optimizer, state, trafo, d_trafo)
+            hist.append(float(negll))
+    return {"result": trafo, "optimizer_state": state, "negll_history": list(negll_history or []) + hist}

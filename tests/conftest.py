@@ -1,0 +1,51 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """One device context for the whole GPU session (fails loudly without a GPU
+    or without the built libenf_b200.so -- there is no fallback to test)."""
+    import enf_b200
+    c = enf_b200.default_context()
+    yield c
+
+
+# ---- the error metric every parity test uses (stated in DESIGN.md §parity) -------------
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+
+
+def rel_err(got, ref):
+    """max_i |got_i - ref_i| / (|ref_i| + scale),  scale = RMS(ref) (1 if ref == 0).
+
+    A mixed relative/absolute measure: plain element-wise relative error is
+    ill-posed where the reference value passes through zero (e.g. ladj ~ 0, or
+    center_stretch near x = 0 where the reference itself loses digits,
+    SURVEY §7).  Equivalent to numpy.allclose(rtol=tol, atol=tol*RMS(ref))."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if ref.size == 0:
+        return 0.0
+    scale = float(np.sqrt(np.mean(ref * ref)))
+    if not np.isfinite(scale) or scale == 0.0:
+        scale = 1.0
+    return float(np.max(np.abs(got - ref) / (np.abs(ref) + scale)))
+
+
+def assert_close(got, ref, dtype, what="", factor=1.0):
+    tol = TOL[np.dtype(dtype)] * factor
+    e = rel_err(got, ref)
+    assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e}"

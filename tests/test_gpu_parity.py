@@ -1,0 +1,227 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI
+(libenf_b200.so via enf_b200), against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): Float64 1e-12, Float32 1e-5, in the mixed
+relative measure of conftest.rel_err, on transformed values, ladj, loss and
+gradients.  Float32 results are compared with the float64 oracle evaluated on
+the float32-rounded inputs and parameters (the reference's own Float32 path
+rounds differently from any other implementation in the last bits; the float64
+values are what both approximate).
+"""
+import numpy as np
+import pytest
+
+from chains import both, flat_grads
+from conftest import assert_close, rel_err
+from oracle import enf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float32, np.float64]
+
+
+def _data(D, N, seed, dtype, spread=1.5):
+    return (np.random.default_rng(seed).standard_normal((D, N)) * spread).astype(dtype)
+
+
+def _check_wlaj(E, ctx, spec, D, N, dtype, seed=0, col0=0):
+    fo, fe = both(spec, D, seed, dtype)
+    X = _data(D, N + col0, seed + 1, dtype)
+    Xd = E.B200Matrix.from_host(X, ctx).cols(col0, col0 + N)
+    Yd, Ld = E.with_logabsdet_jacobian(fe, Xd)
+    y_ref, l_ref = O.with_logabsdet_jacobian(fo, X[:, col0:].astype(np.float64))
+    assert Ld.shape == (1, N)
+    assert_close(Yd.to_host(), y_ref, dtype, f"y {spec} D={D}")
+    assert_close(Ld.to_host()[0], l_ref, dtype, f"ladj {spec} D={D}")
+    # forward-only entry point gives the same y
+    Y2 = fe(Xd)
+    np.testing.assert_array_equal(Y2.to_host(), Yd.to_host())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("code", ["cs", "cc", "jo", "ji", "ss", "hh1", "hh3", "hhv"])
+@pytest.mark.parametrize("D", [1, 2, 3, 4, 5, 8, 16, 24, 32, 64, 100, 256])
+def test_single_trafo(ctx, dtype, code, D):
+    import enf_b200 as E
+    _check_wlaj(E, ctx, [code], D, 777, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("spec,D", [
+    (["cs", "hhv", "ss"], 2),                 # C1: examples/nf_example_2d.jl:12-15
+    (["jo", "cs"], 1),                        # C2 data chain: examples/nf_example_1d.jl:8-10
+    (["ss", "jo"], 1),                        # C2 fit chain
+    (["hh4", "jo", "cs"], 16),                # C3
+    (["hh16", "ss"], 256),                    # C4 shape (fewer reflections; SIMT path)
+    (["cc", "jo", "hh4", "ss"], 32),          # C5
+    (["cc", "ji", "hh2", "ss", "cs", "jo", "hh3"], 5),
+    (["cc", "jo", "cc", "jo"], 1),            # examples/nf_example_1d.jl:19-23 (inverted)
+])
+def test_chains(ctx, dtype, spec, D):
+    import enf_b200 as E
+    _check_wlaj(E, ctx, spec, D, 4099, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("N", [1, 2, 3, 31, 255, 256, 257, 1025, 5000])
+@pytest.mark.parametrize("D", [1, 2, 7, 16])
+def test_ragged_sizes(ctx, dtype, N, D):
+    import enf_b200 as E
+    _check_wlaj(E, ctx, ["cc", "hh2", "jo"], D, N, dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("D,col0", [(1, 1), (1, 3), (2, 1), (3, 5), (16, 7), (6, 1)])
+def test_unaligned_column_views(ctx, dtype, D, col0):
+    """Batches are column views (src/optimize_whitening.jl:32,38): their base
+    pointer need not be 16-byte aligned."""
+    import enf_b200 as E
+    _check_wlaj(E, ctx, ["cs", "hh2", "ss"], D, 1000, dtype, col0=col0)
+
+
+def test_empty_input(ctx):
+    import enf_b200 as E
+    _, fe = both(["jo"], 4, 0, np.float32)
+    Xd = E.B200Matrix(ctx, 4, 0, np.float32)
+    Y, L = E.with_logabsdet_jacobian(fe, Xd)
+    assert Y.shape == (4, 0) and L.shape == (1, 0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_inverse_roundtrip(ctx, dtype):
+    """InverseFunctions.test_inverse + `inv_ladjs ≈ -ladjs`
+    (test/test_center_stretch.jl:64-70, test/test_johnson_trafo.jl:71-77)."""
+    import enf_b200 as E
+    _, fe = both(["hh4", "jo", "cs", "ss"], 16, 3, dtype)
+    X = _data(16, 3000, 5, dtype, spread=1.0)
+    Xd = E.B200Matrix.from_host(X, ctx)
+    Y, L = E.with_logabsdet_jacobian(fe, Xd)
+    X2, L2 = E.with_logabsdet_jacobian(E.inverse(fe), Y)
+    f = 30 if dtype == np.float32 else 3000   # conditioning of the round trip, not of one pass
+    assert_close(X2.to_host(), X, dtype, "roundtrip x", factor=f)
+    assert_close(L2.to_host(), -L.to_host(), dtype, "roundtrip ladj", factor=f)
+
+
+def test_golden_known_answers(ctx):
+    """The reference's four known-answer values, through the CUDA path
+    (test/test_center_stretch.jl:18-19, test/test_johnson_trafo.jl:21-22)."""
+    import enf_b200 as E
+    y = E.CenterStretch(7.0, 2.0, 4.0)(np.array([1.0]))
+    assert abs(y[0] - 11.927293271065633) < 1e-11
+    y = E.CenterContract(7.0, 2.0, 4.0)(np.array([12.0]))
+    assert abs(y[0] - 1.0634640055214397) < 1e-12
+    y = E.JohnsonTrafo(1.0, 3.0, -4.0, 0.5)(np.array([0.3]))
+    assert abs(y[0] - 9.544817734776984) < 1e-11
+    y = E.JohnsonTrafoInv(1.0, 3.0, -4.0, 0.5)(np.array([0.3]))
+    assert abs(y[0] - (-4.1177281942392545)) < 1e-11
+    # Float32 in -> Float32 out (test/test_center_stretch.jl:15-16)
+    y32 = E.CenterStretch(np.float32(7), np.float32(2), np.float32(4))(np.array([1.0], dtype=np.float32))
+    assert y32.dtype == np.float32 and abs(float(y32[0]) - 11.927293) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_host_matrix_path(ctx, dtype):
+    """numpy in -> numpy out through enf_forward_ladj_host (chunked pipeline)."""
+    import enf_b200 as E
+    fo, fe = both(["hh4", "jo", "cs"], 16, 11, dtype)
+    X = _data(16, 700_001, 12, dtype)       # > one 32 MiB chunk for f64, ragged tail
+    Y, L = E.with_logabsdet_jacobian(fe, X)
+    y_ref, l_ref = O.with_logabsdet_jacobian(fo, X.astype(np.float64))
+    assert Y.shape == X.shape and L.shape == (1, X.shape[1])
+    assert_close(Y, y_ref, dtype, "host y")
+    assert_close(L[0], l_ref, dtype, "host ladj")
+
+
+GRAD_CHAINS = [
+    (["ss", "jo"], 1),                          # C2 fit chain
+    (["cc", "jo", "cc", "jo"], 1),              # examples/nf_example_1d.jl:19-23
+    (["ss", "hhv", "cc"], 2),                   # examples/nf_example_2d.jl:21-25
+    (["cc", "jo", "hh4", "ss"], 32),            # C5
+    (["cs", "ji", "hh3", "ss", "cc", "jo", "hh2", "ss"], 5),
+    (["hh4", "jo", "cs"], 16),
+    (["ji", "hh2", "cs"], 8),
+    (["jo", "hh5", "ss"], 100),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("spec,D", GRAD_CHAINS)
+def test_negll_and_grad(ctx, dtype, spec, D):
+    import enf_b200 as E
+    fo, fe = both(spec, D, 21, dtype)
+    N = 3001
+    X = _data(D, N, 22, dtype, spread=1.2)
+    Xd = E.B200Matrix.from_host(X, ctx)
+    v_ref = float(O.mvnormal_negll_trafo(fo, X.astype(np.float64)))
+    v = E.mvnormal_negll_trafo(fe, Xd)
+    assert abs(v - v_ref) <= (1e-5 if dtype == np.float32 else 1e-12) * (abs(v_ref) + 1), (v, v_ref)
+    for zp in (True, False):
+        vz_ref, g_ref = O.mvnormal_negll_trafograd(fo, X.astype(np.float64), zygote_primal=zp)
+        vz, g = E.mvnormal_negll_trafograd(fe, Xd, zygote_primal=zp)
+        assert abs(vz - vz_ref) <= (1e-5 if dtype == np.float32 else 1e-12) * (abs(vz_ref) + 1), (zp, vz, vz_ref)
+        got, ref = flat_grads(g, fe), flat_grads(g_ref, fo)
+        assert [k for k, _ in got] == [k for k, _ in ref]
+        # gradients: measured against the size of the whole gradient of that leaf
+        for (k, a), (_, b) in zip(got, ref):
+            assert a.dtype == dtype
+            b = b.reshape(a.shape)
+            assert_close(a, b, dtype, f"grad {k} {spec}", factor=4.0 if dtype == np.float32 else 50.0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_grad_reproducible_and_ragged(ctx, dtype):
+    """Same call twice -> bit-identical sums (fixed-order reductions); N values
+    around the tile size."""
+    import enf_b200 as E
+    fo, fe = both(["cc", "jo", "hh4", "ss"], 32, 5, dtype)
+    for N in (1, 63, 64, 65, 2049):
+        X = _data(32, N, N, dtype)
+        Xd = E.B200Matrix.from_host(X, ctx)
+        v1, g1 = E.mvnormal_negll_trafograd(fe, Xd)
+        v2, g2 = E.mvnormal_negll_trafograd(fe, Xd)
+        assert v1 == v2
+        for (k, a), (_, b) in zip(flat_grads(g1, fe), flat_grads(g2, fe)):
+            np.testing.assert_array_equal(a, b)
+        v_ref, g_ref = O.mvnormal_negll_trafograd(fo, X.astype(np.float64))
+        assert abs(v1 - v_ref) <= (1e-5 if dtype == np.float32 else 1e-12) * (abs(v_ref) + 1)
+        for (k, a), (_, b) in zip(flat_grads(g1, fe), flat_grads(g_ref, fo)):
+            assert_close(a, b.reshape(a.shape), dtype, f"grad {k} N={N}", factor=4.0 if dtype == np.float32 else 50.0)
+
+
+def test_optimize_whitening_matches_oracle(ctx):
+    """A short fit: same loss history and final parameters as the oracle's
+    restatement of the reference loop (src/optimize_whitening.jl:25-45)."""
+    import enf_b200 as E
+    rng = np.random.default_rng(0)
+    Xw = rng.standard_normal((2, 4000))
+    f_true_o = O.compose(O.ScaleShiftTrafo(np.array([1.3, 0.4]), np.array([2.5, -1.2])),
+                         O.HouseholderTrafo(np.array([1.0, 0.3])),
+                         O.CenterStretch(np.array([4.0, 4.1]), np.array([2.0, 2.1]), np.array([3.0, 3.1])))
+    X = O.apply(f_true_o, Xw)
+    v0 = rng.standard_normal(2)
+
+    def init(ns):
+        return ns.compose(ns.inverse(ns.CenterStretch(np.zeros(2), np.ones(2), np.zeros(2))),
+                          ns.inverse(ns.HouseholderTrafo(v0.copy())),
+                          ns.ScaleShiftTrafo(np.ones(2), np.zeros(2)))
+
+    r_ref = O.optimize_whitening(X, init(O), O.ADAGrad(), nbatches=20, nepochs=3)
+    r = E.optimize_whitening(E.B200Matrix.from_host(X, ctx), init(E), E.ADAGrad(), nbatches=20, nepochs=3)
+    h, h_ref = np.array(r["negll_history"]), np.array(r_ref["negll_history"])
+    assert h.shape == h_ref.shape == (60,)
+    assert np.max(np.abs(h - h_ref) / (np.abs(h_ref) + 1)) < 1e-9
+    for a, b in zip(E.flatten(r["result"]), O.flatten(r_ref["result"])):
+        for n in a.fields:
+            assert np.max(np.abs(np.asarray(getattr(a, n)) - np.asarray(getattr(b, n)))) < 1e-8
+    assert h[-1] < h[0]
+
+
+def test_errors_are_reported_not_fatal(ctx):
+    import enf_b200 as E
+    with pytest.raises(E.EnfError):
+        E.get_chain(E.ScaleShiftTrafo(np.ones(5000), np.zeros(5000)), 5000, np.float32, ctx)   # D too large
+    with pytest.raises(ValueError):
+        E.get_chain(E.ScaleShiftTrafo(np.ones(3), np.zeros(3)), 4, np.float32, ctx)            # shape mismatch
+    X = E.B200Matrix.from_host(np.zeros((4, 8), dtype=np.float32), ctx)
+    with pytest.raises(TypeError):
+        E.with_logabsdet_jacobian(E.ScaleShiftTrafo(np.ones(4), np.zeros(4)), X)               # f64 params, f32 data
