@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- trafo-chain samples/s on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm
+  python bench.py --impl reference --gpus N ...            # CPU restatement of the reference
+
+One "step" is one fused forward+ladj pass of the C3 chain
+(CenterStretch ∘ JohnsonTrafo ∘ HouseholderTrafo(16x4), Float32) over this rank's
+shard of synthetic N(0,1) samples that already sit in HBM.  Weak scaling:
+1.25e8 samples per GPU (8 GPUs = the 1e9 samples of BASELINE.json configs[2]);
+no collective is on this path (columns are independent).
+
+The JSON line also carries
+  roofline     achieved HBM GB/s of the fused kernel (algorithmic (2D+1)*4 B/sample)
+  e2e          same metric through the public host-matrix API (pinned host
+               buffers, H2D + kernel + D2H inside the timed region)
+  cpu_baseline the C restatement of the reference's unfused CPU algorithm on a
+               bounded sample of the same workload (rank 0, N=1 only)
+  extras       inverse+ladj pass, and the fused loss+gradient step of the C5
+               chain (D=32) with its NCCL all-reduce when N > 1
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+D_MAIN, K_HH = 16, 4
+N_PER_GPU = 125_000_000          # C3: 1e9 samples over 8 GPUs
+N_E2E = 1 << 25                  # samples per e2e step through host buffers (2 GiB in, 2.1 GiB out)
+D_GRAD, N_GRAD_BATCH = 32, 2_500_000   # C5: 2.5e8 samples/GPU, nbatches=100
+SEED = 42
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+
+
+def c3_chain(ns, dtype=np.float32):
+    from chains import build
+    return build(ns, ["hh%d" % K_HH, "jo", "cs"], D_MAIN, np.random.default_rng(SEED), dtype)
+
+
+def c5_chain(ns, dtype=np.float32):
+    from chains import build
+    return build(ns, ["cc", "jo", "hh4", "ss"], D_GRAD, np.random.default_rng(SEED + 1), dtype)
+
+
+# ------------------------------------------------------------------ CPU restatement
+def cpu_reference_rate(n_samples, threads, x_host=None):
+    """samples/s of the unfused C restatement (oracle/libenf_ref_cpu.so) for the
+    C3 forward+ladj pass on `n_samples` samples."""
+    from oracle import enf_oracle as O
+    so = os.path.join(ROOT, "oracle", "libenf_ref_cpu.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(so)
+    f = c3_chain(O)
+    hh, jo, cs = O.flatten(f)
+    ps = [np.asfortranarray(hh.V).ravel(order="F"), np.concatenate([jo.gamma, jo.delta, jo.xi, jo.lam]),
+          np.concatenate([cs.a, cs.b, cs.c])]
+    ps = [np.ascontiguousarray(p, dtype=np.float32) for p in ps]
+    FP = C.POINTER(C.c_float)
+    parr = (FP * 3)(*[p.ctypes.data_as(FP) for p in ps])
+    kinds, Ks = (C.c_int * 3)(5, 2, 0), (C.c_int * 3)(K_HH, 0, 0)
+    if x_host is None:
+        x_host = np.random.default_rng(SEED).standard_normal((n_samples, D_MAIN), dtype=np.float32)  # memory == D x N col-major
+    y = np.empty_like(x_host)
+    l = np.empty(n_samples, dtype=np.float32)
+    lib.ref_set_threads(int(threads))
+    t = time.perf_counter()
+    rc = lib.ref_forward_ladj_f32(D_MAIN, C.c_int64(n_samples), 3, kinds, Ks, parr, x_host.ctypes.data_as(FP),
+                                  y.ctypes.data_as(FP), l.ctypes.data_as(FP))
+    dt = time.perf_counter() - t
+    assert rc == 0
+    return n_samples / dt, dt, (y, l)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = 4_000_000
+    cpu_reference_rate(200_000, threads)                      # page in / warm
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_reference_rate(n, threads)
+    rates, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        r, _, _ = cpu_reference_rate(n, threads)
+        rates.append(r)
+    total = time.perf_counter() - t0
+    value = n * args.steps / sum(n / r for r in rates)
+    line = {
+        "impl": "reference", "metric": "trafo-chain fwd+ladj samples/s", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(n / r for r in rates) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3 chain CenterStretch∘JohnsonTrafo∘HouseholderTrafo(16x4), D=16, Float32, "
+                               "forward+ladj; CPU leg on a bounded sample", "sample_per_step": n},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} samples/step of the same synthetic N(0,1) input; C restatement of the "
+                                   "reference's unfused CPU algorithm (Julia is not installed in this image)"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": total,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import enf_b200 as E
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = E.Context(local_rank)
+    hbm_peak, peak_src = peaks()
+    Nl = args.samples_per_gpu
+    fe = c3_chain(E)
+    X = E.B200Matrix.randn(D_MAIN, Nl, np.float32, seed=SEED, col0=rank * Nl, ctx=ctx)
+    Y = X.empty_like()
+    Ld = E.B200Matrix(ctx, 1, Nl, np.float32)
+    ctx.sync()
+
+    def step():
+        E.with_logabsdet_jacobian(fe, X, out=(Y, Ld))
+
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = ctx.launches
+    t_wall0 = time.time()
+    ctx.record(0)
+    for _ in range(args.steps):
+        step()
+    ctx.record(1)
+    ms = ctx.elapsed_ms(0, 1)
+    ctx.sync()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    launches = ctx.launches - l0
+    barrier()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    value = Nl * world / (ms_per_step * 1e-3)
+    bytes_per_sample = (2 * D_MAIN + 1) * 4
+    my_ms = ctx.elapsed_ms(0, 1) / args.steps                # this rank's kernel time (one launch per step)
+    achieved = bytes_per_sample * Nl / (my_ms * 1e-3) / 1e9
+
+    # ---- e2e: public host-matrix API, pinned host buffers, H2D + kernel + D2H timed
+    n_e2e = min(N_E2E, Nl)
+    xh = ctx.pinned_empty((D_MAIN, n_e2e), np.float32)
+    yh = ctx.pinned_empty((D_MAIN, n_e2e), np.float32)
+    lh = ctx.pinned_empty((1, n_e2e), np.float32)
+    xh[...] = X.cols(0, n_e2e).to_host()
+    E.with_logabsdet_jacobian(fe, xh, out=(yh, lh))          # warm (allocates the staging slots)
+    e2e_steps = max(3, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        E.with_logabsdet_jacobian(fe, xh, out=(yh, lh))
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n_e2e * world * e2e_steps / e2e_s
+
+    extras = {}
+    if not args.no_extras:
+        # inverse + ladj of the same chain (F2: just another chain)
+        fi = E.inverse(fe)
+        for _ in range(2):
+            E.with_logabsdet_jacobian(fi, Y, out=(X, Ld))
+        ctx.record(2)
+        for _ in range(3):
+            E.with_logabsdet_jacobian(fi, Y, out=(X, Ld))
+        ctx.record(3)
+        inv_ms = max_over_ranks(ctx.elapsed_ms(2, 3) / 3)
+        extras["inverse_ladj"] = {"samples_per_s": Nl * world / (inv_ms * 1e-3), "ms_per_pass": inv_ms,
+                                  "hbm_frac": bytes_per_sample * Nl / (inv_ms * 1e-3) / 1e9 / hbm_peak}
+        # C5: fused loss + parameter-gradient step, with the NCCL all-reduce when world > 1
+        del fi
+        ge = c5_chain(E)
+        nb = min(N_GRAD_BATCH, Nl * D_MAIN // D_GRAD)
+        Xg = E.B200Matrix(ctx, D_GRAD, nb * 8, np.float32, _ptr=X.ptr, _owner=X)   # reuse the resident samples
+        if world > 1:
+            E.dist.init_group(ctx)
+        for i in range(3):
+            E.mvnormal_negll_trafograd(ge, Xg.cols(i * nb, (i + 1) * nb), group=world > 1)
+        barrier()
+        t0 = time.perf_counter()
+        nsteps = 8
+        for i in range(nsteps):
+            E.mvnormal_negll_trafograd(ge, Xg.cols(i * nb, (i + 1) * nb), group=world > 1)
+        g_s = max_over_ranks(time.perf_counter() - t0) / nsteps
+        extras["grad_step_c5"] = {"samples_per_s": nb * world / g_s, "ms_per_step": g_s * 1e3, "batch_per_gpu": nb,
+                                  "hbm_frac": D_GRAD * 4 * nb / g_s / 1e9 / hbm_peak,
+                                  "includes": "kernel + reduce + D2H of sums + host finish" + (" + ncclAllReduce" if world > 1 else "")}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        n_cpu = 4_000_000
+        sample = np.ascontiguousarray(X.cols(0, n_cpu).to_host().T)      # (N, D) C-order == D x N column-major
+        cpu_reference_rate(100_000, threads)
+        r, dt, (yc, lc) = cpu_reference_rate(n_cpu, threads, sample)
+        cpu = {"value": r, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"first {n_cpu} samples of the same synthetic input ({dt:.1f} s); C restatement of the "
+                         "reference's unfused CPU algorithm (Julia is not installed in this image)"}
+
+    if rank == 0:
+        line = {
+            "metric": "trafo-chain fwd+ladj samples/s", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3 chain CenterStretch∘JohnsonTrafo∘HouseholderTrafo(16x4), D=16, Float32, "
+                                   "forward+ladj, %d samples per GPU resident in HBM" % Nl,
+                       "samples_per_gpu": Nl, "D": D_MAIN, "householder_K": K_HH, "parallelism": "columns sharded, no collective",
+                       "l2": "inputs (%.1f GB per pass) >> 126 MB L2, no flush needed" % (bytes_per_sample * Nl / 1e9)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_sample": bytes_per_sample},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": n_e2e * D_MAIN * 4,
+                    "d2h_bytes_per_step": n_e2e * (D_MAIN + 1) * 4, "samples_per_step": n_e2e, "steps": e2e_steps,
+                    "api": "with_logabsdet_jacobian(chain, pinned host matrix) -> enf_forward_ladj_host"},
+            "gpu_launches": launches, "clocks": clocks, "extras": extras,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

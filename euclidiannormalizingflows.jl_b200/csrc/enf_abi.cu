@@ -52,6 +52,7 @@ struct enf_ctx {
     void* slot_buf[HOST_SLOTS] = {nullptr, nullptr, nullptr};
     size_t slot_bytes = 0;
     cudaEvent_t ev = nullptr;
+    cudaEvent_t timing[ENF_N_EVENTS] = {};
     int64_t launches = 0;
     std::string last_error;
     // NCCL group
@@ -400,6 +401,7 @@ extern "C" int enf_init(int device, enf_ctx** out) {
     CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (int i = 0; i < HOST_SLOTS; ++i) CU(ctx, cudaStreamCreateWithFlags(&ctx->slot_stream[i], cudaStreamNonBlocking));
     CU(ctx, cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming));
+    for (int i = 0; i < ENF_N_EVENTS; ++i) CU(ctx, cudaEventCreate(&ctx->timing[i]));
     *out = ctx;
     return ENF_OK;
 }
@@ -414,6 +416,8 @@ extern "C" int enf_destroy(enf_ctx* ctx) {
         if (ctx->slot_buf[i]) cudaFree(ctx->slot_buf[i]);
     }
     if (ctx->ev) cudaEventDestroy(ctx->ev);
+    for (int i = 0; i < ENF_N_EVENTS; ++i)
+        if (ctx->timing[i]) cudaEventDestroy(ctx->timing[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ENF_OK;
@@ -423,6 +427,23 @@ extern "C" int enf_sync(enf_ctx* ctx) {
     if (!ctx) return fail(nullptr, ENF_ERR_INVALID, "ctx is NULL");
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return ENF_OK;
+}
+
+extern "C" int enf_event_record(enf_ctx* ctx, int slot) {
+    if (!ctx) return fail(nullptr, ENF_ERR_INVALID, "ctx is NULL");
+    if (slot < 0 || slot >= ENF_N_EVENTS) return fail(ctx, ENF_ERR_INVALID, "event slot %d out of range", slot);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaEventRecord(ctx->timing[slot], ctx->stream));
+    return ENF_OK;
+}
+
+extern "C" int enf_event_elapsed_ms(enf_ctx* ctx, int a, int b, float* ms) {
+    if (!ctx || !ms) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    if (a < 0 || a >= ENF_N_EVENTS || b < 0 || b >= ENF_N_EVENTS) return fail(ctx, ENF_ERR_INVALID, "event slot out of range");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaEventSynchronize(ctx->timing[b]));
+    CU(ctx, cudaEventElapsedTime(ms, ctx->timing[a], ctx->timing[b]));
     return ENF_OK;
 }
 

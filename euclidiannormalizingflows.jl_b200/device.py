@@ -54,6 +54,16 @@ class Context:
     def sync(self):
         L.check(self._lib.enf_sync(self.handle), self.handle)
 
+    def record(self, slot: int):
+        """Record CUDA event `slot` on the library's stream."""
+        L.check(self._lib.enf_event_record(self.handle, int(slot)), self.handle)
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        """Device time between recorded events a and b (waits for b)."""
+        ms = C.c_float()
+        L.check(self._lib.enf_event_elapsed_ms(self.handle, int(a), int(b), C.byref(ms)), self.handle)
+        return float(ms.value)
+
     @property
     def launches(self) -> int:
         n = C.c_int64()

@@ -244,7 +244,7 @@ def get_chain(f, D: int, dtype, ctx: Optional[Context] = None) -> Chain:
 
 
 # ------------------------------------------------------------------ evaluation
-def _evaluate(f, x, want_ladj: bool):
+def _evaluate(f, x, want_ladj: bool, out=None):
     """(y, ladj) for a device matrix, a host matrix (through the host-buffer
     pipeline of enf_forward_ladj_host) or a single host sample vector."""
     if isinstance(x, B200Matrix):
@@ -253,10 +253,10 @@ def _evaluate(f, x, want_ladj: bool):
             raise TypeError(f"device samples are {x.dtype} but the chain promotes to {dt}; convert the samples "
                             "(the C ABI is all-f32 or all-f64, src/center_stretch.jl:5)")
         ch = get_chain(f, x.D, dt, x.ctx)
-        y = x.empty_like()
+        y = out[0] if out is not None else x.empty_like()
         lib = x.ctx._lib
         if want_ladj:
-            ladj = B200Matrix(x.ctx, 1, x.N, dt)
+            ladj = out[1] if out is not None else B200Matrix(x.ctx, 1, x.N, dt)
             L.check(lib.enf_forward_ladj(ch.handle, C.c_void_p(x.ptr), x.N, C.c_void_p(y.ptr), C.c_void_p(ladj.ptr)), x.ctx.handle)
             return y, ladj
         L.check(lib.enf_forward(ch.handle, C.c_void_p(x.ptr), x.N, C.c_void_p(y.ptr)), x.ctx.handle)
@@ -270,8 +270,13 @@ def _evaluate(f, x, want_ladj: bool):
     ctx = default_context()
     ch = get_chain(f, X.shape[0], dt, ctx)
     Xf = np.asfortranarray(X, dtype=dt)
-    Y = np.empty_like(Xf, order="F")
-    ladj = np.empty((1, X.shape[1]), dtype=dt) if want_ladj else None
+    if out is not None:
+        Y, ladj = out
+        if not (Y.flags.f_contiguous and Y.dtype == dt and Y.shape == Xf.shape):
+            raise ValueError("out[0] must be a column-major array of the result dtype and shape")
+    else:
+        Y = np.empty_like(Xf, order="F")
+        ladj = np.empty((1, X.shape[1]), dtype=dt) if want_ladj else None
     L.check(ctx._lib.enf_forward_ladj_host(ch.handle, Xf.ctypes.data_as(C.c_void_p), X.shape[1],
                                            Y.ctypes.data_as(C.c_void_p),
                                            ladj.ctypes.data_as(C.c_void_p) if want_ladj else None), ctx.handle)
@@ -280,11 +285,13 @@ def _evaluate(f, x, want_ladj: bool):
     return Y, ladj
 
 
-def with_logabsdet_jacobian(f, x):
+def with_logabsdet_jacobian(f, x, out=None):
     """ChangesOfVariables.with_logabsdet_jacobian(f, x) -> (y, ladj).
     ladj is a 1 x N row for a D x N matrix (the reference's `Adjoint` row,
-    src/abstract_trafo.jl:9) and a scalar for a single sample vector."""
-    return _evaluate(f, x, want_ladj=True)
+    src/abstract_trafo.jl:9) and a scalar for a single sample vector.
+    out=(y, ladj): optional preallocated results (B200Matrix pair for device
+    input; column-major numpy arrays, e.g. pinned ones, for host input)."""
+    return _evaluate(f, x, want_ladj=True, out=out)
 
 
 def mvnormal_negll_trafo(trafo, X) -> float:

@@ -156,6 +156,14 @@ int enf_group_destroy(enf_ctx* ctx);
 int enf_negll_grad_group(enf_chain* chain, const void* x_dev, int64_t N_local, int flags,
                          double* negll_host, void* grads_host);
 
+/* ---- timing on the context stream ---------------------------------------------
+ * The library launches on its own stream, which events of other libraries do
+ * not see.  ENF_N_EVENTS CUDA events per context: record one, later read the
+ * elapsed device time between two recorded events (blocks until `b` is done). */
+#define ENF_N_EVENTS 16
+int enf_event_record(enf_ctx* ctx, int slot);
+int enf_event_elapsed_ms(enf_ctx* ctx, int slot_a, int slot_b, float* ms);
+
 /* ---- introspection used by bench.py / tests ----------------------------------- */
 /* Number of kernel launches issued by this context so far. */
 int enf_launch_count(const enf_ctx* ctx, int64_t* n);

@@ -33,9 +33,9 @@ def _check_wlaj(E, ctx, spec, D, N, dtype, seed=0, col0=0):
     assert Ld.shape == (1, N)
     assert_close(Yd.to_host(), y_ref, dtype, f"y {spec} D={D}")
     assert_close(Ld.to_host()[0], l_ref, dtype, f"ladj {spec} D={D}")
-    # forward-only entry point gives the same y
+    # forward-only entry point (ladj code eliminated at compile time): same y up to FMA contraction
     Y2 = fe(Xd)
-    np.testing.assert_array_equal(Y2.to_host(), Yd.to_host())
+    assert_close(Y2.to_host(), y_ref, dtype, f"y (forward only) {spec} D={D}")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
