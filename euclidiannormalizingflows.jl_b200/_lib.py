@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libenf_b200.so")
+# ENF_B200_LIB: load an alternative build of the library (tuning experiments)
+LIB_PATH = os.environ.get("ENF_B200_LIB") or os.path.join(_HERE, "libenf_b200.so")
 
 ENF_F32, ENF_F64 = 0, 1
 (ENF_CENTER_STRETCH, ENF_CENTER_CONTRACT, ENF_JOHNSON, ENF_JOHNSON_INV,

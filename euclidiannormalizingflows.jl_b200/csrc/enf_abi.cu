@@ -173,6 +173,9 @@ int derive_constants(enf_chain* ch) {
         if (ch->dtype == ENF_F32) put<float>(ch->h_consts, idx, v);
         else put<double>(ch->h_consts, idx, v);
     };
+    // unit of the device log / exp: Float32 kernels use lg2 / ex2 (enf_math.cuh Prim<float>)
+    const double lgu = ch->dtype == ENF_F32 ? 0.69314718055994530942 : 1.0;
+    const double exu = ch->dtype == ENF_F32 ? LOG2E_D : 1.0;
     ch->ladj_const_ss = 0.0;
     ch->ladj_const_other = 0.0;
     for (size_t o = 0; o < ch->ops.size(); ++o) {
@@ -187,12 +190,16 @@ int derive_constants(enf_chain* ch) {
                 case OP_CS:
                 case OP_CC: {
                     const double a = real ? p[i] : 0.0, b = real ? p[D + i] : 1.0, c = real ? p[2 * D + i] : 0.0;
+                    const double A = std::exp(b * a);
                     set(base + 0 * size_t(Dp), -b * LOG2E_D);
-                    set(base + 1 * size_t(Dp), std::exp(b * a));
-                    set(base + 2 * size_t(Dp), 1.0 / b);
+                    set(base + 1 * size_t(Dp), A);
+                    set(base + 2 * size_t(Dp), lgu / b);
                     set(base + 3 * size_t(Dp), c);
                     set(base + 4 * size_t(Dp), a);
                     set(base + 5 * size_t(Dp), b);
+                    set(base + 6 * size_t(Dp), 0.5 * A);
+                    set(base + 7 * size_t(Dp), 2.0 / A);
+                    set(base + 8 * size_t(Dp), (1.0 + A * A) / A);
                     break;
                 }
                 case OP_JO: {
@@ -201,17 +208,19 @@ int derive_constants(enf_chain* ch) {
                     set(base + 0 * size_t(Dp), 1.0 / lm);
                     set(base + 1 * size_t(Dp), -xi / lm);
                     set(base + 2 * size_t(Dp), gm);
-                    set(base + 3 * size_t(Dp), dl);
+                    set(base + 3 * size_t(Dp), dl * lgu);
+                    set(base + 4 * size_t(Dp), dl);
                     if (r < D) ch->ladj_const_other += std::log(std::fabs(dl / lm));
                     break;
                 }
                 case OP_JI: {
                     const double gm = real ? p[i] : 0.0, dl = real ? p[D + i] : 1.0, xi = real ? p[2 * D + i] : 0.0,
                                  lm = real ? p[3 * D + i] : 1.0;
-                    set(base + 0 * size_t(Dp), 1.0 / dl);
-                    set(base + 1 * size_t(Dp), -gm / dl);
+                    set(base + 0 * size_t(Dp), exu / dl);
+                    set(base + 1 * size_t(Dp), -gm * exu / dl);
                     set(base + 2 * size_t(Dp), lm);
                     set(base + 3 * size_t(Dp), xi);
+                    set(base + 4 * size_t(Dp), 1.0 / dl);
                     if (r < D) ch->ladj_const_other += std::log(std::fabs(lm / dl));
                     break;
                 }
@@ -662,9 +671,16 @@ static int forward_impl(enf_chain* ch, const void* x, int64_t N, void* y, void* 
     if (!x || !y || (want_ladj && !ladj)) return fail(ctx, ENF_ERR_INVALID, "NULL device pointer");
     KernelSet ks;
     const int mode = pick_mode(ch, x, y);
+    const double lc = ch->ladj_const_other + ch->ladj_const_ss;
+    StaticKernel sk;
+    if (select_static(ch->dtype, ch->desc, mode, sk)) {
+        CU(ctx, launch_fwd_static(ch->dtype, sk, ch->desc, ch->d_consts, x, y, want_ladj ? ladj : nullptr, N, lc,
+                                  ctx->sm_count, st));
+        ctx->launches += 1;
+        return ENF_OK;
+    }
     if (!select_kernels(ch->dtype, ch->plan, mode, ks))
         return fail(ctx, ENF_ERR_INVALID, "no kernel variant for dtype=%d D=%d", ch->dtype, ch->D);
-    const double lc = ch->ladj_const_other + ch->ladj_const_ss;
     CU(ctx, launch_fwd(ch->dtype, ks, ch->desc, ch->d_consts, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));
     ctx->launches += 1;
     return ENF_OK;

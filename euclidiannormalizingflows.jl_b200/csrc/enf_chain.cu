@@ -2,6 +2,7 @@
 #include "enf_chain.cuh"
 #include "enf_launch.h"
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -16,10 +17,10 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
     sums[i] = s;
 }
 
-bool select_f32_vec(int LG, int CH, KernelSet& k);
-bool select_f32_scalar(int LG, int CH, KernelSet& k);
-bool select_f64_vec(int LG, int CH, KernelSet& k);
-bool select_f64_scalar(int LG, int CH, KernelSet& k);
+bool select_f32_vec(const Plan& p, KernelSet& k);
+bool select_f32_scalar(const Plan& p, KernelSet& k);
+bool select_f64_vec(const Plan& p, KernelSet& k);
+bool select_f64_scalar(const Plan& p, KernelSet& k);
 bool select_pack(int dtype, int PD, int mode, KernelSet& k);
 
 bool select_kernels(int dtype, const Plan& plan, int mode, KernelSet& k) {
@@ -28,8 +29,8 @@ bool select_kernels(int dtype, const Plan& plan, int mode, KernelSet& k) {
         return select_pack(dtype, plan.PD, mode, k);
     }
     if (mode != MODE_VEC && mode != MODE_SCALAR) return false;
-    if (dtype == 0) return mode == MODE_VEC ? select_f32_vec(plan.LG, plan.CH, k) : select_f32_scalar(plan.LG, plan.CH, k);
-    return mode == MODE_VEC ? select_f64_vec(plan.LG, plan.CH, k) : select_f64_scalar(plan.LG, plan.CH, k);
+    if (dtype == 0) return mode == MODE_VEC ? select_f32_vec(plan, k) : select_f32_scalar(plan, k);
+    return mode == MODE_VEC ? select_f64_vec(plan, k) : select_f64_scalar(plan, k);
 }
 
 bool make_plan(int dtype, int D, Plan& plan) {
@@ -41,12 +42,22 @@ bool make_plan(int dtype, int D, Plan& plan) {
         plan.PD = D;
         plan.LG = 0;
         plan.CH = 1;
+        plan.gLG = 0;
+        plan.gCH = 1;
         plan.Dp = VE;
         return true;
     }
     const int nvec = (D + VE - 1) / VE;
     int LG = 0;
     while ((1 << LG) < nvec && LG < 5) ++LG;
+    // two vectors per lane when the sample has at least two: half the shuffles per Householder
+    // reflection and per ladj, still sector-coalesced (measured fastest, profiles/)
+    if (LG > 0 && nvec <= 32) --LG;
+    // tuning override: ENF_PLAN_LG=<log2 lanes per sample> (the dispatcher derives vectors per lane from it)
+    if (const char* e = getenv("ENF_PLAN_LG")) {
+        const int v = atoi(e);
+        if ((v == 0 && nvec == 4) || (v == 2 && nvec == 4)) LG = v;   // only (0,4) and (2,1) are instantiated
+    }
     int CH = (nvec + (1 << LG) - 1) >> LG;
     int CHp = 1;
     while (CHp < CH) CHp <<= 1;
@@ -56,6 +67,10 @@ bool make_plan(int dtype, int D, Plan& plan) {
     plan.LG = LG;
     plan.CH = CHp;
     plan.Dp = (1 << LG) * CHp * VE;
+    // gradient kernels: as many lanes per sample as possible (same padded row count)
+    plan.gLG = LG;
+    plan.gCH = CHp;
+    while (plan.gCH > 1 && plan.gLG < 5) { ++plan.gLG; plan.gCH >>= 1; }
     return true;
 }
 
@@ -65,7 +80,7 @@ std::mutex g_mu;
 std::map<std::pair<const void*, size_t>, int> g_occ;   // (kernel, smem) -> CTAs per SM
 std::map<const void*, size_t> g_smem_set;               // kernel -> max dynamic smem opted in
 
-cudaError_t prepare_kernel(const void* fn, size_t smem, int& ctas_per_sm) {
+cudaError_t prepare_kernel(const void* fn, size_t smem, int& ctas_per_sm, int threads = NT) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (smem > 48 * 1024) {
         auto it = g_smem_set.find(fn);
@@ -79,7 +94,7 @@ cudaError_t prepare_kernel(const void* fn, size_t smem, int& ctas_per_sm) {
     auto it = g_occ.find(key);
     if (it == g_occ.end()) {
         int nb = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, NT, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem);
         if (e != cudaSuccess) return e;
         if (nb < 1) return cudaErrorLaunchOutOfResources;
         it = g_occ.emplace(key, nb).first;
@@ -106,9 +121,10 @@ cudaError_t launch_fwd(int dtype, const KernelSet& k, const ChainDesc& desc, con
                        void* y, void* ladj, int64_t N, double ladj_const, int sm_count, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     const void* fn = ladj ? k.fwd_ladj : k.fwd;
-    const size_t smem = fwd_smem_bytes(dtype, desc);
+    // constants | pad to 128 B | TMA ring (MODE_VEC)
+    const size_t smem = fwd_smem_bytes(dtype, desc) + (k.fwd_ring_bytes ? k.fwd_ring_bytes + 128 : 0);
     int per_sm = 0;
-    cudaError_t e = prepare_kernel(fn, smem, per_sm);
+    cudaError_t e = prepare_kernel(fn, smem, per_sm, k.fwd_threads);
     if (e != cudaSuccess) return e;
     const int64_t items = (N + k.LN - 1) / k.LN;
     const int64_t tiles = (items + k.fwd_items_per_tile - 1) / k.fwd_items_per_tile;
@@ -118,7 +134,26 @@ cudaError_t launch_fwd(int dtype, const KernelSet& k, const ChainDesc& desc, con
     double lc64 = ladj_const;
     void* args[] = {const_cast<ChainDesc*>(&desc), &consts, &x, &y, &ladj, &N,
                     dtype == 0 ? static_cast<void*>(&lc32) : static_cast<void*>(&lc64)};
-    return cudaLaunchKernel(fn, dim3(grid), dim3(NT), args, smem, st);
+    return cudaLaunchKernel(fn, dim3(grid), dim3(k.fwd_threads), args, smem, st);
+}
+
+cudaError_t launch_fwd_static(int dtype, const StaticKernel& k, const ChainDesc& desc, const void* consts,
+                              const void* x, void* y, void* ladj, int64_t N, double ladj_const, int sm_count,
+                              cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    const void* fn = ladj ? k.fwd_ladj : k.fwd;
+    int per_sm = 0;
+    cudaError_t e = prepare_kernel(fn, k.ring_bytes, per_sm, k.threads);
+    if (e != cudaSuccess) return e;
+    const int64_t items = (N + k.LN - 1) / k.LN;
+    const int64_t tiles = (items + k.items_per_tile - 1) / k.items_per_tile;
+    const int64_t cap = int64_t(per_sm) * sm_count;
+    const unsigned grid = unsigned(tiles < cap ? tiles : cap);
+    float lc32 = float(ladj_const);
+    double lc64 = ladj_const;
+    void* args[] = {const_cast<ChainDesc*>(&desc), &consts, &x, &y, &ladj, &N,
+                    dtype == 0 ? static_cast<void*>(&lc32) : static_cast<void*>(&lc64)};
+    return cudaLaunchKernel(fn, dim3(grid), dim3(k.threads), args, k.ring_bytes, st);
 }
 
 cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,

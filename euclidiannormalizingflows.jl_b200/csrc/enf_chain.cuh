@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "enf_math.cuh"
 
 namespace enf {
@@ -49,7 +50,7 @@ struct ChainDesc {
 };
 
 __host__ __device__ constexpr int n_consts_of(int kind, int K) {
-    return (kind == OP_CS || kind == OP_CC) ? 6 : (kind == OP_JO || kind == OP_JI) ? 4 : kind == OP_SS ? 2 : K;
+    return (kind == OP_CS || kind == OP_CC) ? 9 : (kind == OP_JO || kind == OP_JI) ? 5 : kind == OP_SS ? 2 : K;
 }
 __host__ __device__ constexpr int n_rowslots_of(int kind, int K) {
     return (kind == OP_CS || kind == OP_CC) ? 3 : (kind == OP_JO || kind == OP_JI) ? 4 : kind == OP_SS ? 2 : K;
@@ -98,6 +99,7 @@ struct Cfg {
     static constexpr int LN = PACKED ? (Vec<T_>::VE / (PD_ > 0 ? PD_ : 1)) : 1;  // samples per tile row of a thread
     static constexpr int PDD = PD_ > 0 ? PD_ : 1;
     static constexpr int SB = NT / G;  // samples (packed: vectors) per CTA step
+    static constexpr int DP = PACKED ? Vec<T_>::VE : (1 << LG_) * CH_ * Vec<T_>::VE;  // padded rows == ChainDesc::Dp
     static_assert(!PACKED || (LG_ == 0 && CH_ == 1 && PD_ > 0), "pack mode is one vector per thread");
     // ladj / mask slot of element e of a vector
     static __host__ __device__ constexpr int slot(int e) { return PACKED ? e / PDD : 0; }
@@ -199,103 +201,181 @@ __device__ __forceinline__ int const_off(int q) {
 }
 
 // ------------------------------------------------------------------ forward ops on a tile
-template <class C, bool LADJ>
-__device__ __forceinline__ void apply_op_fwd(const DevOp& op, const typename C::T* s_c, int Dp, Tile<C>& t,
-                                             typename C::T (&l)[C::SPT][C::LN]) {
+// Which of an op's constant arrays the forward pass needs, in the order the
+// *_fwd_v functions take them (slot numbers: see enf_math.cuh).
+__host__ __device__ constexpr int n_fwd_consts(int kind) { return kind == OP_CS ? 6 : kind == OP_SS ? 2 : 4; }
+__host__ __device__ constexpr int fwd_const_slot(int kind, int j) {
+    return kind == OP_CS ? (j == 0 ? 0 : j == 1 ? 6 : j == 2 ? 2 : j == 3 ? 3 : j == 4 ? 7 : 8) : j;
+}
+constexpr int MAX_FWD_CONSTS = 6;
+
+// one Householder reflection y = x - (v'.x) v' with the pre-scaled v' = v sqrt(2/v.v)
+// (src/householder_trafo.jl:4-11): partial dot products per lane, xor-shuffles inside the group
+template <class C>
+__device__ __forceinline__ void hh_reflect(Tile<C>& t, const typename C::T (&vk)[C::CH][C::VE]) {
     using T = typename C::T;
     constexpr int VE = C::VE;
-    const T* cb = s_c + op.coff;
-    if (op.kind == OP_HH) {
-        for (int k = 0; k < op.K; ++k) {
-            T vk[C::CH][VE];
+    if (C::PACKED) {
 #pragma unroll
-            for (int q = 0; q < C::CH; ++q) ld16_shared(cb + k * Dp + const_off<C>(q), vk[q]);
-            if (C::PACKED) {
+        for (int u = 0; u < C::SPT; ++u)
 #pragma unroll
-                for (int u = 0; u < C::SPT; ++u)
+            for (int p = 0; p < C::LN; ++p) {
+                T d = T(0);
 #pragma unroll
-                    for (int p = 0; p < C::LN; ++p) {
-                        T d = T(0);
+                for (int e = 0; e < C::PDD; ++e) d = Prim<T>::fma_(vk[0][p * C::PDD + e], t.v[u][0][p * C::PDD + e], d);
 #pragma unroll
-                        for (int e = 0; e < C::PD; ++e) d = Prim<T>::fma_(vk[0][p * C::PD + e], t.v[u][0][p * C::PD + e], d);
-#pragma unroll
-                        for (int e = 0; e < C::PD; ++e)
-                            t.v[u][0][p * C::PD + e] = Prim<T>::fma_(-d, vk[0][p * C::PD + e], t.v[u][0][p * C::PD + e]);
-                    }
-            } else {
-                T d[C::SPT];
-#pragma unroll
-                for (int u = 0; u < C::SPT; ++u) {
-                    d[u] = T(0);
-#pragma unroll
-                    for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                        for (int e = 0; e < VE; ++e) d[u] = Prim<T>::fma_(vk[q][e], t.v[u][q][e], d[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < C::SPT; ++u) d[u] = group_sum<C>(d[u]);
-#pragma unroll
-                for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                    for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                        for (int e = 0; e < VE; ++e) t.v[u][q][e] = Prim<T>::fma_(-d[u], vk[q][e], t.v[u][q][e]);
+                for (int e = 0; e < C::PDD; ++e)
+                    t.v[u][0][p * C::PDD + e] = Prim<T>::fma_(-d, vk[0][p * C::PDD + e], t.v[u][0][p * C::PDD + e]);
             }
+    } else {
+        T d[C::SPT];
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u) {
+            d[u] = T(0);
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                for (int e = 0; e < VE; ++e) d[u] = Prim<T>::fma_(vk[q][e], t.v[u][q][e], d[u]);
         }
-        return;
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u) d[u] = group_sum<C>(d[u]);
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                for (int e = 0; e < VE; ++e) t.v[u][q][e] = Prim<T>::fma_(-d[u], vk[q][e], t.v[u][q][e]);
     }
+}
+
+// elementwise trafo KIND on vector q of every sample of the tile; k[j] = j-th forward constant of the lane's rows
+template <class C, int KIND, bool LADJ, bool SAFE>
+__device__ __forceinline__ void elem_fwd_q(Tile<C>& t, int q, const typename C::T (&k)[MAX_FWD_CONSTS][C::VE],
+                                           typename C::T (&l)[C::SPT][C::LN], bool& bad) {
+    using T = typename C::T;
+    constexpr int VE = C::VE;
+    constexpr int GR = C::PACKED ? C::PDD : VE;   // consecutive elements that belong to one sample
 #pragma unroll
-    for (int q = 0; q < C::CH; ++q) {
-        const int co = const_off<C>(q);
-        T c0[VE], c1[VE], c2[VE], c3[VE];
-        ld16_shared(cb + 0 * Dp + co, c0);
-        ld16_shared(cb + 1 * Dp + co, c1);
-        if (op.kind != OP_SS) {
-            ld16_shared(cb + 2 * Dp + co, c2);
-            ld16_shared(cb + 3 * Dp + co, c3);
-        }
-        switch (op.kind) {
-            case OP_SS:
+    for (int u = 0; u < C::SPT; ++u) {
+        if (KIND == OP_SS) {
 #pragma unroll
-                for (int u = 0; u < C::SPT; ++u)
+            for (int e = 0; e < VE; ++e) t.v[u][q][e] = Prim<T>::fma_(t.v[u][q][e], k[0][e], k[1][e]);
+        } else {
 #pragma unroll
-                    for (int e = 0; e < VE; ++e) t.v[u][q][e] = Prim<T>::fma_(t.v[u][q][e], c0[e], c1[e]);
-                break;
-            case OP_CS:
-#pragma unroll
-                for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                    for (int e = 0; e < VE; ++e)
-                        t.v[u][q][e] = cs_fwd<T>(t.v[u][q][e], c0[e], c1[e], c2[e], c3[e], l[u][C::slot(e)]);
-                break;
-            case OP_CC:
-#pragma unroll
-                for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                    for (int e = 0; e < VE; ++e)
-                        t.v[u][q][e] = cc_fwd<T>(t.v[u][q][e], c0[e], c1[e], c2[e], c3[e], l[u][C::slot(e)]);
-                break;
-            case OP_JO:
-#pragma unroll
-                for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                    for (int e = 0; e < VE; ++e)
-                        t.v[u][q][e] = jo_fwd<T>(t.v[u][q][e], c0[e], c1[e], c2[e], c3[e], l[u][C::slot(e)]);
-                break;
-            default:  // OP_JI
-#pragma unroll
-                for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                    for (int e = 0; e < VE; ++e)
-                        t.v[u][q][e] = ji_fwd<T>(t.v[u][q][e], c0[e], c1[e], c2[e], c3[e], l[u][C::slot(e)]);
-                break;
+            for (int p = 0; p < VE / GR; ++p) {
+                T* v = &t.v[u][q][p * GR];
+                T& ll = l[u][C::slot(p * GR)];
+                const int o = p * GR;
+                if (KIND == OP_CS) cs_fwd_v<T, GR, LADJ, SAFE>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, k[4] + o, k[5] + o, ll, bad);
+                else if (KIND == OP_CC) cc_fwd_v<T, GR, LADJ, SAFE>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, ll, bad);
+                else if (KIND == OP_JO) jo_fwd_v<T, GR, LADJ, SAFE>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, ll, bad);
+                else ji_fwd_v<T, GR, LADJ, SAFE>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, ll, bad);
+            }
         }
     }
 }
 
+template <class C, int KIND, bool LADJ, bool SAFE>
+__device__ __forceinline__ void elem_fwd_from(const typename C::T* cb, Tile<C>& t, typename C::T (&l)[C::SPT][C::LN],
+                                              bool& bad) {
+    using T = typename C::T;
+#pragma unroll
+    for (int q = 0; q < C::CH; ++q) {
+        T k[MAX_FWD_CONSTS][C::VE];
+#pragma unroll
+        for (int j = 0; j < n_fwd_consts(KIND); ++j) ld16_shared(cb + fwd_const_slot(KIND, j) * C::DP + const_off<C>(q), k[j]);
+        elem_fwd_q<C, KIND, LADJ, SAFE>(t, q, k, l, bad);
+    }
+}
+
+// interpretive dispatch: the op list is data (ChainDesc), constants come from shared memory
+template <class C, bool LADJ, bool SAFE>
+__device__ __forceinline__ void apply_op_fwd(const DevOp& op, const typename C::T* s_c, Tile<C>& t,
+                                             typename C::T (&l)[C::SPT][C::LN], bool& bad) {
+    using T = typename C::T;
+    const T* cb = s_c + op.coff;
+    switch (op.kind) {
+        case OP_HH:
+            for (int k = 0; k < op.K; ++k) {
+                T vk[C::CH][C::VE];
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q) ld16_shared(cb + k * C::DP + const_off<C>(q), vk[q]);
+                hh_reflect<C>(t, vk);
+            }
+            break;
+        case OP_SS: elem_fwd_from<C, OP_SS, LADJ, SAFE>(cb, t, l, bad); break;
+        case OP_CS: elem_fwd_from<C, OP_CS, LADJ, SAFE>(cb, t, l, bad); break;
+        case OP_CC: elem_fwd_from<C, OP_CC, LADJ, SAFE>(cb, t, l, bad); break;
+        case OP_JO: elem_fwd_from<C, OP_JO, LADJ, SAFE>(cb, t, l, bad); break;
+        default: elem_fwd_from<C, OP_JI, LADJ, SAFE>(cb, t, l, bad); break;
+    }
+}
+
+// ------------------------------------------------------------------ static chains
+// The same ops with the op list as a template parameter pack (CODE = kind | K << 8):
+// no dispatch, Householder loops unrolled, and every per-row constant of the lane
+// lives in registers for the whole kernel (the lane's rows never change).  Used for
+// the chain shapes in the registry of enf_chain_static.cu; everything else runs
+// the interpretive kernel above.
+template <class C, int CODE, bool LADJ> struct StaticOp {
+    using T = typename C::T;
+    static constexpr int KIND = CODE & 0xff;
+    static constexpr int K = CODE >> 8;
+    static constexpr int NK = KIND == OP_HH ? K : n_fwd_consts(KIND);
+    T k[NK][C::CH][C::VE];
+    __device__ __forceinline__ void load(const T* cb) {
+#pragma unroll
+        for (int j = 0; j < NK; ++j)
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q) {
+                const int slot = KIND == OP_HH ? j : fwd_const_slot(KIND, j);
+                const T* p = cb + slot * C::DP + const_off<C>(q);
+#pragma unroll
+                for (int e = 0; e < C::VE; ++e) k[j][q][e] = p[e];
+            }
+    }
+    template <bool SAFE>
+    __device__ __forceinline__ void apply(Tile<C>& t, T (&l)[C::SPT][C::LN], bool& bad) const {
+        if (KIND == OP_HH) {
+#pragma unroll
+            for (int j = 0; j < NK; ++j) hh_reflect<C>(t, k[j]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q) {
+                T kk[MAX_FWD_CONSTS][C::VE];
+#pragma unroll
+                for (int j = 0; j < NK; ++j)
+#pragma unroll
+                    for (int e = 0; e < C::VE; ++e) kk[j][e] = k[j][q][e];
+                elem_fwd_q<C, KIND, LADJ, SAFE>(t, q, kk, l, bad);
+            }
+        }
+    }
+};
+
+template <class C, bool LADJ, int... CODES> struct StaticStages;
+template <class C, bool LADJ> struct StaticStages<C, LADJ> {
+    __device__ __forceinline__ void load(const ChainDesc&, const typename C::T*, int) {}
+    template <bool SAFE>
+    __device__ __forceinline__ void apply(Tile<C>&, typename C::T (&)[C::SPT][C::LN], bool&) const {}
+};
+template <class C, bool LADJ, int CODE, int... REST> struct StaticStages<C, LADJ, CODE, REST...> {
+    StaticOp<C, CODE, LADJ> op;
+    StaticStages<C, LADJ, REST...> rest;
+    __device__ __forceinline__ void load(const ChainDesc& d, const typename C::T* consts, int idx) {
+        op.load(consts + d.ops[idx].coff);
+        rest.load(d, consts, idx + 1);
+    }
+    template <bool SAFE>
+    __device__ __forceinline__ void apply(Tile<C>& t, typename C::T (&l)[C::SPT][C::LN], bool& bad) const {
+        op.template apply<SAFE>(t, l, bad);
+        rest.template apply<SAFE>(t, l, bad);
+    }
+};
+
 template <class C>
 __device__ __forceinline__ void stage_constants(const ChainDesc& desc, const typename C::T* consts, typename C::T* s_c) {
-    for (int i = threadIdx.x; i < desc.n_consts; i += NT) s_c[i] = consts[i];
+    for (int i = threadIdx.x; i < desc.n_consts; i += blockDim.x) s_c[i] = consts[i];
     __syncthreads();
 }
 
@@ -306,45 +386,225 @@ __device__ __forceinline__ int64_t num_tiles(int64_t N) {
     return (items + per_tile - 1) / per_tile;
 }
 
-// ------------------------------------------------------------------ forward (+ ladj) kernel
-// F1/F2 of SURVEY §2.3: (f::Trafo)(x) and with_logabsdet_jacobian(f, x) for a whole chain.
-template <class C, bool LADJ>
-__global__ void __launch_bounds__(NT) chain_fwd_kernel(const __grid_constant__ ChainDesc desc,
-                                                       const typename C::T* __restrict__ consts,
-                                                       const typename C::T* x, typename C::T* y,
-                                                       typename C::T* ladj, int64_t N, typename C::T ladj_const) {
+// per-sample ladj: finish the sum over the lanes of a group, convert from lg units, add the row constants
+template <class C>
+__device__ __forceinline__ void store_ladj(typename C::T* ladj, int64_t tile, typename C::T (&l)[C::SPT][C::LN],
+                                           const int (&nv)[C::SPT], typename C::T ladj_const) {
     using T = typename C::T;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_c = reinterpret_cast<T*>(smem_raw);
-    stage_constants<C>(desc, consts, s_c);
-    const int D = desc.D, Dp = desc.Dp;
+#pragma unroll
+    for (int u = 0; u < C::SPT; ++u) {
+        const int64_t s = tile_item<C>(tile, u);
+        if (C::PACKED) {
+#pragma unroll
+            for (int p = 0; p < C::LN; ++p)
+                if (p < nv[u]) __stcs(ladj + s * C::LN + p, Prim<T>::fma_(l[u][p], Prim<T>::LGU, ladj_const));
+        } else {
+            const T tot = group_sum<C>(l[u][0]);
+            if (nv[u] && (threadIdx.x & (C::G - 1)) == 0) __stcs(ladj + s, Prim<T>::fma_(tot, Prim<T>::LGU, ladj_const));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ TMA input ring (MODE_VEC)
+// A CTA's tile (SPT*SB consecutive samples) is one contiguous block of global
+// memory: one elected thread brings it into shared memory with a single bulk
+// async copy (cp.async.bulk, the 1-D form of TMA) that signals an mbarrier, RING
+// tiles ahead of the math.  Every thread then picks its own 16-byte vectors out of
+// the staged tile with LDS.128, so no warp ever waits on HBM latency and no
+// registers are tied up by loads in flight.
+constexpr int RING = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <class C>
+struct Ring {
+    using T = typename C::T;
+    static constexpr bool ON = (C::MODE == MODE_VEC);
+    static constexpr int TILE_SAMPLES = C::SPT * C::SB;
+    static constexpr size_t STAGE_BYTES = ON ? size_t(TILE_SAMPLES) * C::DP * sizeof(T) : 0;   // D <= DP
+    static constexpr size_t BYTES = ON ? RING * STAGE_BYTES + 128 : 0;                          // + barriers
+    static constexpr int THREADS = ON ? NT + 32 : NT;                                           // + producer warp
+};
+
+// issue the bulk copy of tile `tile` into ring slot `slot` (one thread)
+template <class C>
+__device__ __forceinline__ void ring_issue(const typename C::T* x, int64_t N, int D, int64_t tile, unsigned char* stage0,
+                                           uint64_t* bars, int slot) {
+    using T = typename C::T;
+    const int64_t first = tile * Ring<C>::TILE_SAMPLES;
+    int64_t n = N - first;
+    if (n > Ring<C>::TILE_SAMPLES) n = Ring<C>::TILE_SAMPLES;
+    const uint32_t bytes = uint32_t(n) * uint32_t(D) * uint32_t(sizeof(T));
+    mbar_expect_tx(&bars[slot], bytes);
+    bulk_g2s(stage0 + size_t(slot) * Ring<C>::STAGE_BYTES, x + first * D, bytes, &bars[slot]);
+}
+
+// this thread's vectors of the staged tile -> registers
+template <class C>
+__device__ __forceinline__ void ring_read(const unsigned char* stage, int64_t N, int D, int64_t tile, Tile<C>& t,
+                                          int (&nv)[C::SPT]) {
+    using T = typename C::T;
+    const T* sp = reinterpret_cast<const T*>(stage);
+    const int g = threadIdx.x & (C::G - 1);
+    const int s_in = threadIdx.x >> C::LG;
+#pragma unroll
+    for (int u = 0; u < C::SPT; ++u) {
+        nv[u] = tile_item<C>(tile, u) < N ? 1 : 0;
+#pragma unroll
+        for (int q = 0; q < C::CH; ++q) {
+            const int row0 = (q * C::G + g) * C::VE;
+            if (nv[u] && row0 < D) ld16_shared(sp + (u * C::SB + s_in) * D + row0, t.v[u][q]);
+            else {
+#pragma unroll
+                for (int e = 0; e < C::VE; ++e) t.v[u][q][e] = T(0);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ forward (+ ladj) kernels
+// Grid-stride loop over tiles shared by the interpretive and the static kernel;
+// `apply(t, l)` runs the chain on one register tile.  `ring_smem` is 128-byte
+// aligned dynamic shared memory of Ring<C>::BYTES bytes (unused unless MODE_VEC).
+template <class C, bool LADJ, class Apply>
+__device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C::T* y, typename C::T* ladj, int64_t N,
+                                              int D, typename C::T ladj_const, unsigned char* ring_smem, Apply&& apply) {
+    using T = typename C::T;
     const int64_t nt = num_tiles<C>(N);
-    for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+    unsigned char* stage0 = ring_smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring_smem + RING * Ring<C>::STAGE_BYTES);   // TMA landed
+    uint64_t* empty = full + RING;                                                            // all warps have read
+    if (Ring<C>::ON) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < RING; ++i) {
+                mbar_init(&full[i], 1);
+                mbar_init(&empty[i], NT / 32);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x >= NT) {
+            // producer warp: one lane keeps the ring full; the compute warps never synchronise with
+            // each other, only with the data (warp-specialised, like the TMA warp of a GEMM)
+            if (threadIdx.x == NT) {
+                int k = 0;
+                for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x, ++k) {
+                    const int slot = k % RING;
+                    if (k >= RING) {
+                        const uint32_t parity = uint32_t(k / RING - 1) & 1u;
+                        while (!mbar_try_wait(&empty[slot], parity)) {}
+                    }
+                    ring_issue<C>(x, N, D, tile, stage0, full, slot);
+                }
+            }
+            return;
+        }
+    }
+    int k = 0;
+    for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x, ++k) {
         Tile<C> t;
         int nv[C::SPT];
         T l[C::SPT][C::LN];
-        load_tile<C>(x, N, D, tile, t, nv);
+        if (Ring<C>::ON) {
+            const int slot = k % RING;
+            const uint32_t parity = uint32_t(k / RING) & 1u;
+            while (!mbar_try_wait(&full[slot], parity)) {}
+            ring_read<C>(stage0 + size_t(slot) * Ring<C>::STAGE_BYTES, N, D, tile, t, nv);
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);
+        } else {
+            load_tile<C>(x, N, D, tile, t, nv);
+        }
 #pragma unroll
         for (int u = 0; u < C::SPT; ++u)
 #pragma unroll
             for (int p = 0; p < C::LN; ++p) l[u][p] = T(0);
-        for (int o = 0; o < desc.n_ops; ++o) apply_op_fwd<C, true>(desc.ops[o], s_c, Dp, t, l);
-        store_tile<C>(y, D, tile, t, nv);
-        if (LADJ) {
+        bool bad = false;
+        apply(std::false_type{}, t, l, bad);
+        if (LADJ && __any_sync(0xffffffffu, bad)) {
+            // a Jacobian-factor product left the float range somewhere in this warp: redo the tile
+            // with per-element logs (x is still intact: the outputs have not been stored yet)
+            load_tile<C>(x, N, D, tile, t, nv);
 #pragma unroll
-            for (int u = 0; u < C::SPT; ++u) {
-                const int64_t s = tile_item<C>(tile, u);
-                if (C::PACKED) {
+            for (int u = 0; u < C::SPT; ++u)
 #pragma unroll
-                    for (int p = 0; p < C::LN; ++p)
-                        if (p < nv[u]) __stcs(ladj + s * C::LN + p, l[u][p] + ladj_const);
-                } else {
-                    const T tot = group_sum<C>(l[u][0]);
-                    if (nv[u] && (threadIdx.x & (C::G - 1)) == 0) __stcs(ladj + s, tot + ladj_const);
-                }
-            }
+                for (int p = 0; p < C::LN; ++p) l[u][p] = T(0);
+            apply(std::true_type{}, t, l, bad);
         }
+        store_tile<C>(y, D, tile, t, nv);
+        if (LADJ) store_ladj<C>(ladj, tile, l, nv, ladj_const);
     }
+}
+
+template <class C>
+__device__ __forceinline__ unsigned char* ring_base(unsigned char* after_consts) {
+    return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(after_consts) + 127) & ~uintptr_t(127));
+}
+
+// F1/F2 of SURVEY §2.3: (f::Trafo)(x) and with_logabsdet_jacobian(f, x) for a whole chain.
+#ifndef ENF_FWD_MIN_CTAS
+#define ENF_FWD_MIN_CTAS 3
+#endif
+template <class C, bool LADJ>
+__global__ void __launch_bounds__(NT + 32, ENF_FWD_MIN_CTAS) chain_fwd_kernel(const __grid_constant__ ChainDesc desc,
+                                                                         const typename C::T* __restrict__ consts,
+                                                                         const typename C::T* x, typename C::T* y,
+                                                                         typename C::T* ladj, int64_t N,
+                                                                         typename C::T ladj_const) {
+    using T = typename C::T;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* s_c = reinterpret_cast<T*>(smem_raw);
+    stage_constants<C>(desc, consts, s_c);
+    fwd_tile_loop<C, LADJ>(x, y, ladj, N, desc.D, ladj_const, ring_base<C>(smem_raw + size_t(desc.n_consts) * sizeof(T)),
+                           [&](auto safe, Tile<C>& t, T (&l)[C::SPT][C::LN], bool& bad) {
+                               constexpr bool SAFE = decltype(safe)::value;
+                               for (int o = 0; o < desc.n_ops; ++o) apply_op_fwd<C, LADJ, SAFE>(desc.ops[o], s_c, t, l, bad);
+                           });
+}
+
+// forward (+ ladj) for a chain known at compile time
+template <class C, bool LADJ, int... CODES>
+__global__ void __launch_bounds__(NT + 32, 2) chain_fwd_static_kernel(const __grid_constant__ ChainDesc desc,
+                                                                 const typename C::T* __restrict__ consts,
+                                                                 const typename C::T* x, typename C::T* y,
+                                                                 typename C::T* ladj, int64_t N,
+                                                                 typename C::T ladj_const) {
+    using T = typename C::T;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StaticStages<C, LADJ, CODES...> stages;
+    stages.load(desc, consts, 0);
+    fwd_tile_loop<C, LADJ>(x, y, ladj, N, desc.D, ladj_const, smem_raw,
+                           [&](auto safe, Tile<C>& t, T (&l)[C::SPT][C::LN], bool& bad) {
+                               stages.template apply<decltype(safe)::value>(t, l, bad);
+                           });
 }
 
 // backward of one elementwise op on vector q of a tile: gt <- input cotangent,
@@ -372,9 +632,9 @@ __device__ __forceinline__ void bwd_elem(const Tile<C>& zt, Tile<C>& gt, int q, 
             } else if (KIND == OP_CC) {
                 gx = cc_bwd<T>(xin, G, c0[e], c1[e], c2[e], c3[e], c4[e], c5[e], r);
             } else if (KIND == OP_JO) {
-                gx = jo_bwd<T>(xin, G, c0[e], c1[e], c2[e], c3[e], r);
+                gx = jo_bwd<T>(xin, G, c0[e], c1[e], c3[e], c4[e], r);
             } else {
-                gx = ji_bwd<T>(xin, G, c0[e], c1[e], c2[e], c3[e], r);
+                gx = ji_bwd<T>(xin, G, c0[e], c1[e], c2[e], c4[e], r);
             }
             gt.v[u][q][e] = gx;
 #pragma unroll
@@ -410,7 +670,8 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
         for (int i = 0; i < desc.n_rowslots * C::CH * VE; ++i) s_acc[size_t(i) * NT + tid] = T(0);
         for (int i = 0; i < desc.n_scalars; ++i) s_sc[size_t(i) * NT + tid] = T(0);
     }
-    const int D = desc.D, Dp = desc.Dp;
+    const int D = desc.D;
+    constexpr int Dp = C::DP;
     T loss_y = T(0), loss_l = T(0);
     const int64_t nt = num_tiles<C>(N);
     for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
@@ -438,7 +699,8 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
 #pragma unroll
                         for (int e = 0; e < VE; ++e) sv[size_t((u * C::CH + q) * VE + e) * NT] = zt.v[u][q][e];
             }
-            apply_op_fwd<C, true>(op, s_c, Dp, zt, l);
+            bool bad = false;
+            apply_op_fwd<C, true, true>(op, s_c, zt, l, bad);
         }
 #pragma unroll
         for (int u = 0; u < C::SPT; ++u) {
@@ -559,10 +821,8 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
                     ld16_shared(cb + 2 * Dp + co, c2);
                     ld16_shared(cb + 3 * Dp + co, c3);
                 }
-                if (op.kind == OP_CS || op.kind == OP_CC) {
-                    ld16_shared(cb + 4 * Dp + co, c4);
-                    ld16_shared(cb + 5 * Dp + co, c5);
-                }
+                if (op.kind != OP_SS) ld16_shared(cb + 4 * Dp + co, c4);
+                if (op.kind == OP_CS || op.kind == OP_CC) ld16_shared(cb + 5 * Dp + co, c5);
                 T ra[4][VE];
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -613,7 +873,7 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
     }
     // loss partials: warp shuffle, then one double per warp through shared memory
     __shared__ double s_loss[2][NT / 32];
-    double ly = double(loss_y), ll = double(loss_l);
+    double ly = double(loss_y), ll = double(loss_l) * double(Prim<T>::LGU);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         ly += __shfl_xor_sync(0xffffffffu, ly, off);

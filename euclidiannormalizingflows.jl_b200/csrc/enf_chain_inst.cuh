@@ -7,45 +7,58 @@
 namespace enf {
 namespace {
 
+#ifndef ENF_FWD_VECS
+#define ENF_FWD_VECS 4   // 16-byte vectors per thread per tile in the forward kernels
+#endif
+
 template <typename T, int LG, int CH, int MODE, int PD>
-KernelSet make_set() {
-    using CF = Cfg<T, LG, CH, MODE, PD, (CH >= 4 ? 1 : 4 / CH)>;   // forward: 16 B x 4 in flight per thread
-    using CG = Cfg<T, LG, CH, MODE, PD, (CH >= 2 ? 1 : 2 / CH)>;   // gradient: two register tiles live
-    KernelSet k;
+void fill_fwd(KernelSet& k) {
+    using CF = Cfg<T, LG, CH, MODE, PD, (CH >= ENF_FWD_VECS ? 1 : ENF_FWD_VECS / CH)>;
     k.fwd = reinterpret_cast<const void*>(&chain_fwd_kernel<CF, false>);
     k.fwd_ladj = reinterpret_cast<const void*>(&chain_fwd_kernel<CF, true>);
+    k.fwd_items_per_tile = CF::SB * CF::SPT;
+    k.fwd_ring_bytes = Ring<CF>::BYTES;
+    k.fwd_threads = Ring<CF>::THREADS;
+    k.LN = CF::LN;
+}
+
+template <typename T, int LG, int CH, int MODE, int PD>
+void fill_grad(KernelSet& k) {
+    using CG = Cfg<T, LG, CH, MODE, PD, (CH >= 2 ? 1 : 2 / CH)>;   // gradient: two register tiles live
     k.grad = reinterpret_cast<const void*>(&chain_grad_kernel<CG, true>);
     k.negll = reinterpret_cast<const void*>(&chain_grad_kernel<CG, false>);
-    k.fwd_items_per_tile = CF::SB * CF::SPT;
     k.grad_items_per_tile = CG::SB * CG::SPT;
     k.grad_tile_elems = CG::SPT * CG::CH * CG::VE;
-    k.LN = CF::LN;
-    k.G = CF::G;
+    k.G = CG::G;
     k.CH = CH;
-    k.VE = CF::VE;
-    return k;
+    k.VE = CG::VE;
+}
+
+// (log2 lanes per sample, vectors per lane) pairs make_plan() can produce for the forward kernels
+// (two vectors per lane where possible) plus (2,1) and (0,4) for the ENF_PLAN_LG tuning override ...
+template <typename T, int MODE>
+bool select_group_fwd(int LG, int CH, KernelSet& k) {
+#define ENF_CASE(lg, ch) if (LG == lg && CH == ch) { fill_fwd<T, lg, ch, MODE, 0>(k); return true; }
+    ENF_CASE(0, 1) ENF_CASE(0, 2) ENF_CASE(1, 2) ENF_CASE(2, 2) ENF_CASE(3, 2) ENF_CASE(4, 2)
+    ENF_CASE(5, 2) ENF_CASE(5, 4) ENF_CASE(5, 8) ENF_CASE(2, 1) ENF_CASE(0, 4)
+#undef ENF_CASE
+    return false;
+}
+
+// ... and for the gradient kernels (one vector per lane where possible: their per-thread
+// accumulators and saved activations scale with the vectors a lane owns)
+template <typename T, int MODE>
+bool select_group_grad(int LG, int CH, KernelSet& k) {
+#define ENF_CASE(lg, ch) if (LG == lg && CH == ch) { fill_grad<T, lg, ch, MODE, 0>(k); return true; }
+    ENF_CASE(0, 1) ENF_CASE(1, 1) ENF_CASE(2, 1) ENF_CASE(3, 1) ENF_CASE(4, 1) ENF_CASE(5, 1)
+    ENF_CASE(5, 2) ENF_CASE(5, 4) ENF_CASE(5, 8)
+#undef ENF_CASE
+    return false;
 }
 
 template <typename T, int MODE>
-bool select_group(int LG, int CH, KernelSet& k) {
-    if (CH == 1) {
-        switch (LG) {
-            case 0: k = make_set<T, 0, 1, MODE, 0>(); return true;
-            case 1: k = make_set<T, 1, 1, MODE, 0>(); return true;
-            case 2: k = make_set<T, 2, 1, MODE, 0>(); return true;
-            case 3: k = make_set<T, 3, 1, MODE, 0>(); return true;
-            case 4: k = make_set<T, 4, 1, MODE, 0>(); return true;
-            case 5: k = make_set<T, 5, 1, MODE, 0>(); return true;
-        }
-        return false;
-    }
-    if (LG != 5) return false;
-    switch (CH) {
-        case 2: k = make_set<T, 5, 2, MODE, 0>(); return true;
-        case 4: k = make_set<T, 5, 4, MODE, 0>(); return true;
-        case 8: k = make_set<T, 5, 8, MODE, 0>(); return true;
-    }
-    return false;
+bool select_group(const Plan& p, KernelSet& k) {
+    return select_group_fwd<T, MODE>(p.LG, p.CH, k) && select_group_grad<T, MODE>(p.gLG, p.gCH, k);
 }
 
 }  // namespace

@@ -13,6 +13,7 @@ struct Plan {
     int PD = 0;           // rows per sample when packed
     int LG = 0;           // log2(lanes per sample)
     int CH = 1;           // 16-byte vectors per lane per sample
+    int gLG = 0, gCH = 1; // the same for the loss / gradient kernels
     int Dp = 0;           // padded row count the constants block is laid out for
 };
 
@@ -26,7 +27,21 @@ struct KernelSet {
     int grad_tile_elems = 0;
     int LN = 1;  // samples per item (packed modes)
     int G = 1, CH = 1, VE = 4;
+    size_t fwd_ring_bytes = 0;  // TMA input ring of the forward kernels (MODE_VEC)
+    int fwd_threads = 256;      // CTA size of the forward kernels (+1 producer warp with the ring)
 };
+
+// A chain compiled as a static op sequence (enf_chain_static.cu)
+struct StaticKernel {
+    const void* fwd = nullptr;
+    const void* fwd_ladj = nullptr;
+    int items_per_tile = 0;
+    int LN = 1;
+    int Dp = 0;
+    size_t ring_bytes = 0;
+    int threads = 256;
+};
+bool select_static(int dtype, const ChainDesc& d, int mode, StaticKernel& k);
 
 bool make_plan(int dtype, int D, Plan& plan);
 bool select_kernels(int dtype, const Plan& plan, int mode, KernelSet& k);
@@ -35,6 +50,9 @@ size_t grad_smem_bytes(int dtype, const ChainDesc& d, const KernelSet& k, bool g
 
 cudaError_t launch_fwd(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
                        void* y, void* ladj, int64_t N, double ladj_const, int sm_count, cudaStream_t st);
+cudaError_t launch_fwd_static(int dtype, const StaticKernel& k, const ChainDesc& desc, const void* consts,
+                              const void* x, void* y, void* ladj, int64_t N, double ladj_const, int sm_count,
+                              cudaStream_t st);
 cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
                         int64_t N, bool grad, double* partials, int max_blocks, int* blocks_used, int sm_count,
                         cudaStream_t st);

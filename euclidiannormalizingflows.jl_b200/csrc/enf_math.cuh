@@ -1,11 +1,20 @@
-// Per-element device math of the trafo ops: forward value + ladj term and the
-// backward pass (input cotangent + raw-sum integrands).
+// Device math of the trafo ops on one 16-byte vector of a sample: forward value +
+// ladj contribution, and the backward pass (input cotangent + raw-sum integrands).
 //
 // The reference formulas (cited per function, paths relative to the reference
 // repository) are evaluated in algebraically equivalent, overflow-free forms
 // whose per-row constants (e^{ba}, 1/b, 1/lambda, ...) are hoisted to the host
 // (enf_abi.cu: derive_constants).  tests/device_model.py states the same algebra
 // in numpy and tests/test_device_model.py checks it against the literal oracle.
+//
+// The kernels are bound by the special-function (MUFU) pipe and by instruction
+// issue, not by HBM (profiles/): every op is written to minimise both.
+//   * logs of Jacobian factors are not taken per element: the factors of the
+//     elements a lane owns are multiplied and ONE log is taken per lane
+//     (log_of_product; a range flag makes the kernel redo the rare tile whose product over/underflowed),
+//   * ladj is accumulated in the unit of the hardware log (log2 for Float32) and
+//     scaled once per sample,
+//   * 1/b, ln2/b, e^{ba}/4, (1+e^{2ba})/2 ... come in as constants.
 //
 // Conventions: G = N * dL/d(output); LB = N * dL/dladj = -1 (the seeds of
 // src/optimize_whitening.jl:12,19-20 with the 1/N pulled out).
@@ -17,16 +26,18 @@ namespace enf {
 // ---------------------------------------------------------------- primitives
 template <typename T> struct Prim;
 
+// Float32: MUFU approximations (ex2/lg2/rcp/rsqrt/sqrt, ~2^-22 relative), logs in base 2.
 template <> struct Prim<float> {
-    static constexpr float LN2 = 0.69314718055994531f;
-    static constexpr float LOG2E = 1.4426950408889634f;
+    static constexpr float LGU = 0.69314718055994531f;      // natural log of the log base: ln x = LGU * lg x
+    static constexpr float INV_LGU = 1.4426950408889634f;
+    static constexpr float LG_OF_2 = 1.0f;                   // lg(2)
+    static constexpr float LG_SAFE = 100.0f;                 // |lg(product)| below this: no over/underflow happened
     static __device__ __forceinline__ float ex2(float x) {
         float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
     }
-    static __device__ __forceinline__ float lg2(float x) {
+    static __device__ __forceinline__ float lg(float x) {
         float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
     }
-    static __device__ __forceinline__ float ln(float x) { return lg2(x) * LN2; }
     static __device__ __forceinline__ float rcp(float x) {
         float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
     }
@@ -39,114 +50,192 @@ template <> struct Prim<float> {
     static __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
     static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
     static __device__ __forceinline__ float csign(float mag, float sgn) { return copysignf(mag, sgn); }
-    // asinh(z) given s = 1 + z^2 and r = rsqrt(s)
-    static __device__ __forceinline__ float asinh_(float z, float s, float r) {
-        return copysignf(ln(fabsf(z) + s * r), z);
+    // lg(|z| + sqrt(1+z^2)) * sign(z), given s = 1 + z^2 and r = rsqrt(s)   [asinh(z) / LGU]
+    static __device__ __forceinline__ float asinh_lg(float z, float s, float r) {
+        return copysignf(lg(fma_(s, r, fabsf(z))), z);
     }
-    // ln(1/sqrt(1+z^2)) given s = 1 + z^2, r = rsqrt(s)
-    static __device__ __forceinline__ float ln_rsq(float z, float s, float r) { return ln(r); }
-    static __device__ __forceinline__ void sinhcosh(float s, float& sh, float& ch) {
-        float e = ex2(s * LOG2E);
-        float ei = rcp(e);
+    // sinh / cosh of sa * LGU (sa = argument in units of the exponential base)
+    static __device__ __forceinline__ void sinhcosh(float sa, float& sh, float& ch) {
+        const float e = ex2(sa);
+        const float ei = rcp(e);
         sh = 0.5f * (e - ei);
         ch = 0.5f * (e + ei);
-        // (e - 1/e)/2 cancels for small |s|: odd Taylor polynomial there
-        float s2 = s * s;
-        float p = fma_(s2, fma_(s2, fma_(s2, fma_(s2, 2.7557319e-6f, 1.9841270e-4f), 8.3333333e-3f), 0.16666667f), 1.0f);
-        sh = (fabsf(s) < 0.4f) ? s * p : sh;
+        // (e - 1/e)/2 cancels for small arguments: odd Taylor polynomial in sa (coefficients ln2^k / k!)
+        const float s2 = sa * sa;
+        const float p = fma_(s2, fma_(s2, fma_(s2, fma_(s2, 1.0178086e-7f, 1.5252734e-5f), 1.3333558e-3f), 5.5504109e-2f),
+                             0.69314718f);
+        sh = (fabsf(sa) < 0.55f) ? sa * p : sh;
     }
 };
 
+// Float64: correctly rounded-ish libm, natural logs.
 template <> struct Prim<double> {
-    static constexpr double LN2 = 0.69314718055994530942;
-    static constexpr double LOG2E = 1.44269504088896340736;
+    static constexpr double LGU = 1.0;
+    static constexpr double INV_LGU = 1.0;
+    static constexpr double LG_OF_2 = 0.69314718055994530942;
+    static constexpr double LG_SAFE = 600.0;
     static __device__ __forceinline__ double ex2(double x) { return exp2(x); }
-    static __device__ __forceinline__ double ln(double x) { return log(x); }
+    static __device__ __forceinline__ double lg(double x) { return log(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double rsq(double x) { return 1.0 / sqrt(x); }
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
     static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
     static __device__ __forceinline__ double csign(double mag, double sgn) { return copysign(mag, sgn); }
-    static __device__ __forceinline__ double asinh_(double z, double s, double r) { return asinh(z); }
-    static __device__ __forceinline__ double ln_rsq(double z, double s, double r) { return -0.5 * log1p(z * z); }
-    static __device__ __forceinline__ void sinhcosh(double s, double& sh, double& ch) {
-        sh = sinh(s);
-        ch = cosh(s);
+    static __device__ __forceinline__ double asinh_lg(double z, double s, double r) { return asinh(z); }
+    static __device__ __forceinline__ void sinhcosh(double sa, double& sh, double& ch) {
+        sh = sinh(sa);
+        ch = cosh(sa);
     }
 };
 
+// lg(prod_i p[i]).  Fast form (SAFE = false): ONE log of the product; if the product
+// left the safe range (over/underflow), `bad` is raised and the caller recomputes the
+// whole tile with SAFE = true (sum of per-element logs).  No branch on the fast path:
+// a branch here would serialise the warp on the MUFU latency of every vector.
+template <typename T, int N, bool SAFE>
+__device__ __forceinline__ T log_of_product(const T (&p)[N], bool& bad) {
+    using P = Prim<T>;
+    if (SAFE || N == 1) {
+        T L = P::lg(p[0]);
+#pragma unroll
+        for (int i = 1; i < N; ++i) L += P::lg(p[i]);
+        return L;
+    }
+    T prod = p[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) prod *= p[i];
+    const T L = P::lg(prod);
+    bad = bad || !(P::abs_(L) < P::LG_SAFE);
+    return L;
+}
+
+// lg(prod_i n[i] / prod_i d[i])
+template <typename T, int N, bool SAFE>
+__device__ __forceinline__ T log_of_ratio(const T (&n)[N], const T (&d)[N], bool& bad) {
+    using P = Prim<T>;
+    if (SAFE) {
+        T L = T(0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) L += P::lg(n[i]) - P::lg(d[i]);
+        return L;
+    }
+    T pn = n[0], pd = d[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) { pn *= n[i]; pd *= d[i]; }
+    const T L = P::lg(pn * P::rcp(pd));
+    bad = bad || !(P::abs_(L) < P::LG_SAFE);
+    return L;
+}
+
 // ---------------------------------------------------------------- forward
-// Every *_fwd returns y and ADDS the element's ladj term to `l` (row constants
-// such as log|delta/lambda| and sum(log|a|) are added once per sample by the
-// caller: ChainDesc::ladj_const).
+// Each *_fwd_v transforms GR consecutive elements that belong to ONE sample and
+// adds their ladj contribution, in lg units, to `l` (row constants such as
+// log|delta/lambda| and sum(log|a|) are added once per sample by the caller).
+//
+// constants (one value per row; K[k][e] = constant k of element e):
+//   CS / CC:  0 nb2 = -b log2(e)   1 A = e^{ba}   2 ib2 = LGU/b   3 c   4 a   5 b   6 A/2   7 2/A   8 (1+A^2)/A
+//   JO:       0 1/lambda   1 -xi/lambda   2 gamma   3 delta*LGU   4 delta
+//   JI:       0 U/delta    1 -gamma U/delta   2 lambda   3 xi   4 1/delta      (U = log2(e) for f32, 1 for f64)
 
 // CenterStretch: src/center_stretch.jl:4-8 (value), :39-43 (ladj = -center_contract_ladj(y)).
-// constants: nb2 = -b*log2(e), A = e^{ba}, ib = 1/b, c
-template <typename T>
-__device__ __forceinline__ T cs_fwd(T x, T nb2, T A, T ib, T c, T& l) {
+// With w = e^{-b|x|}, A = e^{ba}: e^{b(|u|-|x|)} = g = sqrt(m^2 + w) + m, m = (1-w)A/2 (the positive root of
+// the reference's quadratic, divided through by e^{b|x|} so nothing overflows), u = y - c.
+// -ladj = log S(u), S = sigma(b(u-a)) + sigma(-b(u+a)) = [P + (2/A) w g] / [P + ((1+A^2)/A) w g], P = g^2 + w^2
+// (numerator and denominator scaled by g^2 A, which cancels in the ratio: no division by g is needed).
+template <typename T, int GR, bool LADJ, bool SAFE>
+__device__ __forceinline__ void cs_fwd_v(T* v, const T* nb2, const T* Ah, const T* ib2, const T* c, const T* k1,
+                                         const T* k2, T& l, bool& bad) {
     using P = Prim<T>;
-    T ax = P::abs_(x);
-    T w0 = P::ex2(nb2 * ax);                    // e^{-b|x|}
-    T m = P::fma_(-A, w0, A);                   // (1 - w0) e^{ba}
-    T g = T(0.5) * (P::sqrt_(P::fma_(m, m, T(4) * w0)) + m);   // e^{b(|u|-|x|)}
-    T au = P::fma_(P::ln(g), ib, ax);           // |u| = |y - c|
-    T wu = w0 * P::rcp(g);                      // e^{-b|u|}
-    T n1 = P::fma_(A, wu, T(1));
-    T n2 = A + wu;
-    T num = P::fma_(wu, n1, n2);                // S = num/(n1 n2)
-    l += P::ln(n1 * n2 * P::rcp(num));          // -log S
-    return P::csign(au, x) + c;
+    T nn[GR], nd[GR];
+#pragma unroll
+    for (int e = 0; e < GR; ++e) {
+        const T x = v[e];
+        const T ax = P::abs_(x);
+        const T w = P::ex2(nb2[e] * ax);                          // e^{-b|x|}
+        const T m = P::fma_(-Ah[e], w, Ah[e]);                    // (1 - w) e^{ba} / 2
+        const T g = P::sqrt_(P::fma_(m, m, w)) + m;               // e^{b(|u|-|x|)}
+        v[e] = P::csign(P::fma_(P::lg(g), ib2[e], ax), x) + c[e];
+        if (LADJ) {
+            const T wg = w * g;
+            const T p2 = P::fma_(g, g, w * w);
+            nd[e] = P::fma_(k1[e], wg, p2);                       // S = nd / nn
+            nn[e] = P::fma_(k2[e], wg, p2);
+        }
+    }
+    if (LADJ) l += log_of_ratio<T, GR, SAFE>(nn, nd, bad);                   // -log S
 }
 
 // CenterContract: src/center_stretch.jl:11-15 (value), :17-22,63-67 (ladj).
-template <typename T>
-__device__ __forceinline__ T cc_fwd(T x, T nb2, T A, T ib, T c, T& l) {
+template <typename T, int GR, bool LADJ, bool SAFE>
+__device__ __forceinline__ void cc_fwd_v(T* v, const T* nb2, const T* A, const T* ib2, const T* c, T& l, bool& bad) {
     using P = Prim<T>;
-    T u = x - c;
-    T au = P::abs_(u);
-    T w = P::ex2(nb2 * au);                     // e^{-b|u|}
-    T n1 = P::fma_(A, w, T(1));
-    T n2 = A + w;
-    T L1 = P::ln(n1), L2 = P::ln(n2);
-    T L3 = P::ln(P::fma_(w, n1, n2));
-    l += L3 - L1 - L2;                          // log S
-    return P::csign(P::fma_(L1 - L2, ib, au), u);
+    T n3[GR];
+    T ls = T(0);
+#pragma unroll
+    for (int e = 0; e < GR; ++e) {
+        const T u = v[e] - c[e];
+        const T au = P::abs_(u);
+        const T w = P::ex2(nb2[e] * au);                          // e^{-b|u|}
+        const T n1 = P::fma_(A[e], w, T(1));
+        const T n2 = A[e] + w;
+        const T L1 = P::lg(n1), L2 = P::lg(n2);
+        v[e] = P::csign(P::fma_(L1 - L2, ib2[e], au), u);
+        if (LADJ) {
+            n3[e] = P::fma_(w, n1, n2);                           // S = n3 / (n1 n2)
+            ls -= L1 + L2;
+        }
+    }
+    if (LADJ) l += ls + log_of_product<T, GR, SAFE>(n3, bad);                // log S
 }
 
 // JohnsonTrafo: src/johnson_trafo.jl:29-32 (value), :39-42,49-52,76-80 (ladj).
-// constants: il = 1/lambda, c0 = -xi/lambda, gamma, delta
-template <typename T>
-__device__ __forceinline__ T jo_fwd(T x, T il, T c0, T gamma, T delta, T& l) {
+template <typename T, int GR, bool LADJ, bool SAFE>
+__device__ __forceinline__ void jo_fwd_v(T* v, const T* il, const T* c0, const T* gamma, const T* delta2, T& l,
+                                         bool& bad) {
     using P = Prim<T>;
-    T z = P::fma_(x, il, c0);
-    T s = P::fma_(z, z, T(1));
-    T r = P::rsq(s);
-    l += P::ln_rsq(z, s, r);                      // -log(1+z^2)/2
-    return P::fma_(delta, P::asinh_(z, s, r), gamma);
+    T f[GR];
+#pragma unroll
+    for (int e = 0; e < GR; ++e) {
+        const T z = P::fma_(v[e], il[e], c0[e]);
+        const T s = P::fma_(z, z, T(1));
+        const T r = P::rsq(s);
+        v[e] = P::fma_(delta2[e], P::asinh_lg(z, s, r), gamma[e]);
+        if (LADJ) f[e] = sizeof(T) == 4 ? r : s;
+    }
+    if (LADJ) {
+        // -log(1+z^2)/2 :  lg(prod r) for f32 (r = rsqrt(s) is already there), -lg(prod s)/2 for f64
+        const T L = log_of_product<T, GR, SAFE>(f, bad);
+        l += sizeof(T) == 4 ? L : T(-0.5) * L;
+    }
 }
 
 // JohnsonTrafoInv: src/johnson_trafo.jl:34-37 (value), :101-105 (ladj = -johnsontrafo_ladj(y)).
-// constants: idl = 1/delta, c0 = -gamma/delta, lambda, xi
-template <typename T>
-__device__ __forceinline__ T ji_fwd(T x, T idl, T c0, T lam, T xi, T& l) {
+template <typename T, int GR, bool LADJ, bool SAFE>
+__device__ __forceinline__ void ji_fwd_v(T* v, const T* k0, const T* k1, const T* lam, const T* xi, T& l, bool& bad) {
     using P = Prim<T>;
-    T s = P::fma_(x, idl, c0);
-    T sh, ch;
-    P::sinhcosh(s, sh, ch);
-    l += P::ln(ch);                             // log sqrt(1 + sinh^2)
-    return P::fma_(lam, sh, xi);
+    T chs[GR];
+#pragma unroll
+    for (int e = 0; e < GR; ++e) {
+        const T sa = P::fma_(v[e], k0[e], k1[e]);
+        T sh, ch;
+        P::sinhcosh(sa, sh, ch);
+        v[e] = P::fma_(lam[e], sh, xi[e]);
+        chs[e] = ch;
+    }
+    if (LADJ) l += log_of_product<T, GR, SAFE>(chs, bad);                    // log sqrt(1 + sinh^2)
 }
 
 // ---------------------------------------------------------------- backward
 // Every *_bwd takes the op's INPUT x and the output cotangent G, returns the
 // input cotangent and writes the raw-sum integrands r[...] (summed over samples
-// on the device, mapped to parameter gradients by enf_abi.cu: finish_grads).
+// on the device, mapped to parameter gradients by enf_abi.cu: finish).
 
-// CenterContract.  raw: r0 -> -dc, r1 -> da, r2 -> db.  extra constants a, b.
+// CenterContract.  raw: r0 -> -dc, r1 -> da, r2 -> db.
 template <typename T>
-__device__ __forceinline__ T cc_bwd(T x, T G, T nb2, T A, T ib, T c, T a, T b, T* r) {
+__device__ __forceinline__ T cc_bwd(T x, T G, T nb2, T A, T ib2, T c, T a, T b, T* r) {
     using P = Prim<T>;
+    const T ib = ib2 * P::INV_LGU;
     T u = x - c;
     T au = P::abs_(u);
     T sg = u < T(0) ? T(-1) : T(1);
@@ -158,7 +247,7 @@ __device__ __forceinline__ T cc_bwd(T x, T G, T nb2, T A, T ib, T c, T a, T b, T
     T S = s1 + s2;
     T d1 = s1 * (T(1) - s1);
     T d2 = s2 * (T(1) - s2);
-    T ya = P::fma_(P::ln(n1 * P::rcp(n2)), ib, au);
+    T ya = P::fma_(P::lg(n1 * P::rcp(n2)), ib2, au);
     T Su = b * (d1 - d2);
     T Sa = -b * (d1 + d2);
     T Sb = (au - a) * d1 - (au + a) * d2;
@@ -174,14 +263,15 @@ __device__ __forceinline__ T cc_bwd(T x, T G, T nb2, T A, T ib, T c, T a, T b, T
 
 // CenterStretch (implicit inverse of CenterContract).  raw: r0 -> dc, r1 -> da, r2 -> db.
 template <typename T>
-__device__ __forceinline__ T cs_bwd(T x, T G, T nb2, T A, T ib, T c, T a, T b, T* r) {
+__device__ __forceinline__ T cs_bwd(T x, T G, T nb2, T A, T ib2, T c, T a, T b, T* r) {
     using P = Prim<T>;
+    const T ib = ib2 * P::INV_LGU;
     T ax = P::abs_(x);
     T sg = x < T(0) ? T(-1) : T(1);
     T w0 = P::ex2(nb2 * ax);
     T m = P::fma_(-A, w0, A);
     T g = T(0.5) * (P::sqrt_(P::fma_(m, m, T(4) * w0)) + m);
-    T au = P::fma_(P::ln(g), ib, ax);
+    T au = P::fma_(P::lg(g), ib2, ax);
     T wu = w0 * P::rcp(g);
     T n1 = P::fma_(A, wu, T(1));
     T n2 = A + wu;
@@ -206,12 +296,12 @@ __device__ __forceinline__ T cs_bwd(T x, T G, T nb2, T A, T ib, T c, T a, T b, T
 
 // JohnsonTrafo.  raw: r0 = G, r1 = G asinh z, r2 = gz, r3 = z gz.
 template <typename T>
-__device__ __forceinline__ T jo_bwd(T x, T G, T il, T c0, T gamma, T delta, T* r) {
+__device__ __forceinline__ T jo_bwd(T x, T G, T il, T c0, T delta2, T delta, T* r) {
     using P = Prim<T>;
     T z = P::fma_(x, il, c0);
     T s = P::fma_(z, z, T(1));
     T rr = P::rsq(s);
-    T ash = P::asinh_(z, s, rr);
+    T ash = P::asinh_lg(z, s, rr) * P::LGU;
     T gz = P::fma_(G * delta, rr, z * rr * rr); // G delta r - LB z r^2
     r[0] = G;
     r[1] = G * ash;
@@ -222,11 +312,12 @@ __device__ __forceinline__ T jo_bwd(T x, T G, T il, T c0, T gamma, T delta, T* r
 
 // JohnsonTrafoInv.  raw: r0 = gs, r1 = s gs, r2 = G, r3 = G sinh s.
 template <typename T>
-__device__ __forceinline__ T ji_bwd(T x, T G, T idl, T c0, T lam, T xi, T* r) {
+__device__ __forceinline__ T ji_bwd(T x, T G, T k0, T k1, T lam, T idl, T* r) {
     using P = Prim<T>;
-    T s = P::fma_(x, idl, c0);
+    T sa = P::fma_(x, k0, k1);
     T sh, ch;
-    P::sinhcosh(s, sh, ch);
+    P::sinhcosh(sa, sh, ch);
+    T s = (sizeof(T) == 4) ? sa * P::LGU : sa;      // argument in natural units
     T gs = P::fma_(G * lam, ch, -sh * P::rcp(ch));  // G lam cosh + LB tanh
     r[0] = gs;
     r[1] = s * gs;
