@@ -23,16 +23,18 @@ def cs_fwd(x, a, b, c):
     a, b, c = a[:, None], b[:, None], c[:, None]
     A = np.exp(b * a)
     ax = np.abs(x)
-    w0 = np.exp2(-b * LOG2E * ax)
-    m = A - A * w0
-    g = 0.5 * (np.sqrt(m * m + 4 * w0) + m)
+    w = np.exp2(-b * LOG2E * ax)                  # e^{-b|x|}
+    m = 0.5 * A - 0.5 * A * w                     # (1 - w) A / 2
+    g = np.sqrt(m * m + w) + m                    # e^{b(|u| - |x|)}: root of the reference's quadratic / e^{b|x|}
     au = ax + np.log(g) / b
     y = np.copysign(au, x) + c
-    wu = w0 / g
-    n1 = 1 + A * wu
-    n2 = A + wu
-    num = n2 + wu * n1
-    ladj = np.log(n1 * n2 / num)          # = -log S(u)
+    # S(u) = nd / nn with numerator and denominator scaled by g^2 A (no division by g)
+    wg = w * g
+    p2 = g * g + w * w
+    nd = p2 + (2 / A) * wg
+    nn = p2 + ((1 + A * A) / A) * wg
+    # one log per lane-vector: log(prod nn / prod nd); here per element
+    ladj = np.log(nn / nd)                        # = -log S(u)
     return y, ladj.sum(0)
 
 

@@ -225,3 +225,41 @@ def test_errors_are_reported_not_fatal(ctx):
     X = E.B200Matrix.from_host(np.zeros((4, 8), dtype=np.float32), ctx)
     with pytest.raises(TypeError):
         E.with_logabsdet_jacobian(E.ScaleShiftTrafo(np.ones(4), np.zeros(4)), X)               # f64 params, f32 data
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name", ["c1_2d_example", "c2_1d_fit", "c2_1d_example_inv", "c3_d16", "c5_d32", "odd_d5"])
+def test_against_committed_golden_fixtures(ctx, dtype, name):
+    """tests/golden/*.npz (made by tests/golden/make_golden.py): fixed inputs and
+    outputs that travel to the GPU box."""
+    import importlib.util
+    import os
+    import enf_b200 as E
+    from chains import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec_ = importlib.util.spec_from_file_location("make_golden", os.path.join(root, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mg)
+    spec, D, N, seed = mg.CASES[name]
+    z = np.load(os.path.join(root, "tests", "golden", name + ".npz"))
+    fe = build(E, spec, D, np.random.default_rng(seed), dtype)
+    Xd = E.B200Matrix.from_host(z["X"].astype(dtype), ctx)
+    if dtype == np.float32:      # compare with the oracle on the float32-rounded inputs/params instead of the f64 fixture
+        fo = build(O, spec, D, np.random.default_rng(seed), dtype)
+        y_ref, l_ref = O.with_logabsdet_jacobian(fo, z["X"].astype(dtype).astype(np.float64))
+        v_ref = float(O.mvnormal_negll_trafo(fo, z["X"].astype(dtype).astype(np.float64)))
+    else:
+        y_ref, l_ref, v_ref = z["Y"], z["ladj"], float(z["negll"])
+    Y, L = E.with_logabsdet_jacobian(fe, Xd)
+    assert_close(Y.to_host(), y_ref, dtype, f"golden y {name}")
+    assert_close(L.to_host()[0], l_ref, dtype, f"golden ladj {name}")
+    v = E.mvnormal_negll_trafo(fe, Xd)
+    assert abs(v - v_ref) <= (1e-5 if dtype == np.float32 else 1e-12) * (abs(v_ref) + 1)
+    if dtype == np.float64:
+        vz, g = E.mvnormal_negll_trafograd(fe, Xd)
+        assert abs(vz - float(z["negll_zygote_primal"])) <= 1e-12 * (abs(vz) + 1)
+        keys = sorted(k for k in z.files if k.startswith("grad_"))
+        for k, (_, a) in zip(keys, flat_grads(g, fe)):
+            assert_close(a, z[k].reshape(a.shape), dtype, f"golden {k} {name}", factor=50.0)
+        X2, L2 = E.with_logabsdet_jacobian(E.inverse(fe), Y)
+        assert_close(X2.to_host(), z["X"], dtype, "golden roundtrip", factor=3000)
