@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <tuple>
 
 namespace enf {
 
@@ -77,20 +78,24 @@ bool make_plan(int dtype, int D, Plan& plan) {
 // ---- occupancy / attribute cache -------------------------------------------------
 namespace {
 std::mutex g_mu;
-std::map<std::pair<const void*, size_t>, int> g_occ;   // (kernel, smem) -> CTAs per SM
-std::map<const void*, size_t> g_smem_set;               // kernel -> max dynamic smem opted in
+// both caches are per device: function attributes live in the device's context
+std::map<std::tuple<int, const void*, size_t>, int> g_occ;   // (device, kernel, smem) -> CTAs per SM
+std::map<std::pair<int, const void*>, size_t> g_smem_set;     // (device, kernel) -> max dynamic smem opted in
 
 cudaError_t prepare_kernel(const void* fn, size_t smem, int& ctas_per_sm, int threads = NT) {
     std::lock_guard<std::mutex> lk(g_mu);
+    int dev = 0;
+    cudaError_t de = cudaGetDevice(&dev);
+    if (de != cudaSuccess) return de;
     if (smem > 48 * 1024) {
-        auto it = g_smem_set.find(fn);
+        auto it = g_smem_set.find({dev, fn});
         if (it == g_smem_set.end() || it->second < smem) {
             cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
             if (e != cudaSuccess) return e;
-            g_smem_set[fn] = smem;
+            g_smem_set[{dev, fn}] = smem;
         }
     }
-    auto key = std::make_pair(fn, smem);
+    auto key = std::make_tuple(dev, fn, smem);
     auto it = g_occ.find(key);
     if (it == g_occ.end()) {
         int nb = 0;

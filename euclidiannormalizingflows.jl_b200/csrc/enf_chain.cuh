@@ -83,6 +83,21 @@ __device__ __forceinline__ void ld16_shared(const double* p, double (&o)[2]) {
     double2 t = *reinterpret_cast<const double2*>(p);
     o[0] = t.x; o[1] = t.y;
 }
+__device__ __forceinline__ void st16_shared(float* p, const float (&o)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ void st16_shared(double* p, const double (&o)[2]) {
+    *reinterpret_cast<double2*>(p) = make_double2(o[0], o[1]);
+}
+// 16-byte read-modify-write of a per-thread accumulator vector in shared memory
+template <typename T, int VE>
+__device__ __forceinline__ void acc16_shared(T* p, const T (&a)[VE]) {
+    T cur[VE];
+    ld16_shared(p, cur);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) cur[e] += a[e];
+    st16_shared(p, cur);
+}
 
 // ------------------------------------------------------------------ configuration
 template <typename T_, int LG_, int CH_, int MODE_, int PD_, int SPT_>
@@ -656,18 +671,22 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
     using T = typename C::T;
     using P = Prim<T>;
     constexpr int VE = C::VE;
-    constexpr int TE = C::SPT * C::CH * VE;  // tile elements per thread
+    constexpr int TV = C::SPT * C::CH;  // 16-byte vectors per thread per tile
+    // shared memory: constants | saved op inputs [n_save][TV][NT] x 16 B | accumulators [n_rowslots][CH][NT] x 16 B
+    // | scalar accumulators [n_scalars][NT].  Every per-thread datum is a 16-byte vector at [..][tid]:
+    // LDS.128 / STS.128, conflict-free.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_c = reinterpret_cast<T*>(smem_raw);
     const int n_consts_al = (desc.n_consts + 3) & ~3;
-    T* s_save = s_c + n_consts_al;                                  // [n_save][TE][NT]
-    T* s_acc = s_save + (GRAD ? size_t(desc.n_save) * TE * NT : 0);  // [n_rowslots][CH*VE][NT]
-    T* s_sc = s_acc + (GRAD ? size_t(desc.n_rowslots) * C::CH * VE * NT : 0);  // [n_scalars][NT]
+    T* s_save = s_c + n_consts_al;
+    T* s_acc = s_save + (GRAD ? size_t(desc.n_save) * TV * NT * VE : 0);
+    T* s_sc = s_acc + (GRAD ? size_t(desc.n_rowslots) * C::CH * NT * VE : 0);
     stage_constants<C>(desc, consts, s_c);
     const int tid = threadIdx.x;
     const int g = tid & (C::G - 1);
     if (GRAD) {
-        for (int i = 0; i < desc.n_rowslots * C::CH * VE; ++i) s_acc[size_t(i) * NT + tid] = T(0);
+        const T zero[VE] = {};
+        for (int i = 0; i < desc.n_rowslots * C::CH; ++i) st16_shared(s_acc + (size_t(i) * NT + tid) * VE, zero);
         for (int i = 0; i < desc.n_scalars; ++i) s_sc[size_t(i) * NT + tid] = T(0);
     }
     const int D = desc.D;
@@ -679,29 +698,33 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
         int nv[C::SPT];
         T l[C::SPT][C::LN];
         T m[C::SPT][C::LN];  // 1 for real samples, 0 for the padding of the last tile
-        load_tile<C>(x, N, D, tile, zt, nv);
+        // ---- forward, saving the input of every elementwise op; fast ladj (one log per lane vector), and
+        // the whole forward again with per-element logs if a factor product left the float range
+        auto forward = [&](auto safe) {
+            constexpr bool SAFE = decltype(safe)::value;
+            load_tile<C>(x, N, D, tile, zt, nv);
 #pragma unroll
-        for (int u = 0; u < C::SPT; ++u)
+            for (int u = 0; u < C::SPT; ++u)
 #pragma unroll
-            for (int p = 0; p < C::LN; ++p) {
-                m[u][p] = p < nv[u] ? T(1) : T(0);
-                l[u][p] = T(0);
-            }
-        // ---- forward, saving the input of every elementwise op
-        for (int o = 0; o < desc.n_ops; ++o) {
-            const DevOp op = desc.ops[o];
-            if (GRAD && op.save >= 0) {
-                T* sv = s_save + size_t(op.save) * TE * NT + tid;
-#pragma unroll
-                for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                    for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                        for (int e = 0; e < VE; ++e) sv[size_t((u * C::CH + q) * VE + e) * NT] = zt.v[u][q][e];
-            }
+                for (int p = 0; p < C::LN; ++p) {
+                    m[u][p] = p < nv[u] ? T(1) : T(0);
+                    l[u][p] = T(0);
+                }
             bool bad = false;
-            apply_op_fwd<C, true, true>(op, s_c, zt, l, bad);
-        }
+            for (int o = 0; o < desc.n_ops; ++o) {
+                const DevOp op = desc.ops[o];
+                if (GRAD && op.save >= 0) {
+                    T* sv = s_save + (size_t(op.save) * TV * NT + tid) * VE;
+#pragma unroll
+                    for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                        for (int q = 0; q < C::CH; ++q) st16_shared(sv + size_t(u * C::CH + q) * NT * VE, zt.v[u][q]);
+                }
+                apply_op_fwd<C, true, SAFE>(op, s_c, zt, l, bad);
+            }
+            return bad;
+        };
+        if (__any_sync(0xffffffffu, forward(std::false_type{}))) forward(std::true_type{});
 #pragma unroll
         for (int u = 0; u < C::SPT; ++u) {
             T sy = T(0);
@@ -731,7 +754,7 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
                     T vk[C::CH][VE];
 #pragma unroll
                     for (int q = 0; q < C::CH; ++q) ld16_shared(cb + k * Dp + const_off<C>(q), vk[q]);
-                    T* acc = s_acc + size_t(op.roff + k) * C::CH * VE * NT + tid;
+                    T* acc = s_acc + (size_t(op.roff + k) * C::CH * NT + tid) * VE;
                     T* sc = s_sc + size_t(op.soff + k) * NT + tid;
                     T a1[C::CH][VE];
                     T a2 = T(0);
@@ -794,22 +817,18 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
                         }
                     }
 #pragma unroll
-                    for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                        for (int e = 0; e < VE; ++e) acc[size_t(q * VE + e) * NT] += a1[q][e];
+                    for (int q = 0; q < C::CH; ++q) acc16_shared<T, VE>(acc + size_t(q) * NT * VE, a1[q]);
                     if (g == 0) *sc += a2;
                 }
                 continue;
             }
             // elementwise op: reload its input, differentiate
             {
-                const T* sv = s_save + size_t(op.save) * TE * NT + tid;
+                const T* sv = s_save + (size_t(op.save) * TV * NT + tid) * VE;
 #pragma unroll
                 for (int u = 0; u < C::SPT; ++u)
 #pragma unroll
-                    for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                        for (int e = 0; e < VE; ++e) zt.v[u][q][e] = sv[size_t((u * C::CH + q) * VE + e) * NT];
+                    for (int q = 0; q < C::CH; ++q) ld16_shared(sv + size_t(u * C::CH + q) * NT * VE, zt.v[u][q]);
             }
 #pragma unroll
             for (int q = 0; q < C::CH; ++q) {
@@ -838,11 +857,7 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
                 const int nr = n_rowslots_of(op.kind, 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (k < nr) {
-                        T* acc = s_acc + (size_t(op.roff + k) * C::CH + q) * VE * NT + tid;
-#pragma unroll
-                        for (int e = 0; e < VE; ++e) acc[size_t(e) * NT] += ra[k][e];
-                    }
+                    if (k < nr) acc16_shared<T, VE>(s_acc + ((size_t(op.roff + k) * C::CH + q) * NT + tid) * VE, ra[k]);
             }
         }
     }
@@ -857,9 +872,9 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
             int q, gg;
             if (C::PACKED) { q = 0; gg = 0; }
             else { q = vecidx >> C::LG; gg = vecidx & (C::G - 1); }
-            const T* acc = s_acc + ((size_t(rs) * C::CH + q) * VE + e) * NT;
+            const T* acc = s_acc + (size_t(rs) * C::CH + q) * NT * VE + e;
             double s = 0.0;
-            for (int j = gg; j < NT; j += C::G) s += double(acc[j]);
+            for (int j = gg; j < NT; j += C::G) s += double(acc[size_t(j) * VE]);
             out[pi] = s;
         }
         for (int k = tid; k < desc.n_scalars; k += NT) {

@@ -24,7 +24,10 @@ void fill_fwd(KernelSet& k) {
 
 template <typename T, int LG, int CH, int MODE, int PD>
 void fill_grad(KernelSet& k) {
-    using CG = Cfg<T, LG, CH, MODE, PD, (CH >= 2 ? 1 : 2 / CH)>;   // gradient: two register tiles live
+#ifndef ENF_GRAD_VECS
+#define ENF_GRAD_VECS 2   // 16-byte vectors per thread per tile in the gradient kernels (two register tiles live)
+#endif
+    using CG = Cfg<T, LG, CH, MODE, PD, (CH >= ENF_GRAD_VECS ? 1 : ENF_GRAD_VECS / CH)>;
     k.grad = reinterpret_cast<const void*>(&chain_grad_kernel<CG, true>);
     k.negll = reinterpret_cast<const void*>(&chain_grad_kernel<CG, false>);
     k.grad_items_per_tile = CG::SB * CG::SPT;

@@ -41,7 +41,9 @@ bool same(const ChainDesc& d, std::initializer_list<int> codes) {
 
 // variant: tuning knob (ENF_STATIC_VARIANT), 0 = default mapping
 bool select_static(int dtype, const ChainDesc& d, int mode, StaticKernel& k) {
-    static const bool disabled = getenv("ENF_NO_STATIC") != nullptr;
+    // measured slower than the interpretive kernel in round 1 (register-resident constants cost
+    // occupancy, profiles/README.md): opt-in for experiments only
+    static const bool disabled = getenv("ENF_STATIC") == nullptr;
     static const int variant = getenv("ENF_STATIC_VARIANT") ? atoi(getenv("ENF_STATIC_VARIANT")) : 0;
     if (disabled || mode != MODE_VEC) return false;
     if (dtype == 0 && d.D == 16) {

@@ -244,7 +244,7 @@ def get_chain(f, D: int, dtype, ctx: Optional[Context] = None) -> Chain:
 
 
 # ------------------------------------------------------------------ evaluation
-def _evaluate(f, x, want_ladj: bool, out=None):
+def _evaluate(f, x, want_ladj: bool, out=None, ctx=None):
     """(y, ladj) for a device matrix, a host matrix (through the host-buffer
     pipeline of enf_forward_ladj_host) or a single host sample vector."""
     if isinstance(x, B200Matrix):
@@ -267,7 +267,7 @@ def _evaluate(f, x, want_ladj: bool, out=None):
     if X.ndim != 2:
         raise ValueError("expected a sample vector or a D x N sample matrix")
     dt = result_dtype(f, X.dtype if X.dtype.kind == "f" else np.float64)
-    ctx = default_context()
+    ctx = ctx or default_context()
     ch = get_chain(f, X.shape[0], dt, ctx)
     Xf = np.asfortranarray(X, dtype=dt)
     if out is not None:
@@ -285,13 +285,14 @@ def _evaluate(f, x, want_ladj: bool, out=None):
     return Y, ladj
 
 
-def with_logabsdet_jacobian(f, x, out=None):
+def with_logabsdet_jacobian(f, x, out=None, ctx=None):
     """ChangesOfVariables.with_logabsdet_jacobian(f, x) -> (y, ladj).
     ladj is a 1 x N row for a D x N matrix (the reference's `Adjoint` row,
     src/abstract_trafo.jl:9) and a scalar for a single sample vector.
     out=(y, ladj): optional preallocated results (B200Matrix pair for device
-    input; column-major numpy arrays, e.g. pinned ones, for host input)."""
-    return _evaluate(f, x, want_ladj=True, out=out)
+    input; column-major numpy arrays, e.g. pinned ones, for host input).
+    ctx: device context for host input (default: device 0)."""
+    return _evaluate(f, x, want_ladj=True, out=out, ctx=ctx)
 
 
 def mvnormal_negll_trafo(trafo, X) -> float:

@@ -1,0 +1,54 @@
+"""N>1 GPU path: sharded loss+gradient step with the library's ncclAllReduce
+(enf_negll_grad_group) equals the single-GPU result on the whole batch.  Needs
+>= 2 GPUs (skipped otherwise); launched as two processes from inside the test."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np
+    sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+    import torch, torch.distributed as dist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    import enf_b200 as E
+    from chains import both, flat_grads
+    from oracle import enf_oracle as O
+    ctx = E.Context(rank)
+    E.dist.init_group(ctx)
+    D, N = 32, 10007
+    fo, fe = both(["cc", "jo", "hh4", "ss"], D, 3, np.float64)
+    X = np.random.default_rng(4).standard_normal((D, N))
+    a, b = E.dist.shard_columns(N, rank, world)
+    v, g = E.mvnormal_negll_trafograd(fe, E.B200Matrix.from_host(X[:, a:b], ctx), group=True)
+    v_ref, g_ref = O.mvnormal_negll_trafograd(fo, X)
+    assert abs(v - v_ref) < 1e-12 * (abs(v_ref) + 1), (v, v_ref)
+    for (k, x), (_, y) in zip(flat_grads(g, fe), flat_grads(g_ref, fo)):
+        y = y.reshape(x.shape)
+        assert np.max(np.abs(x - y) / (np.abs(y) + np.sqrt(np.mean(y * y)) + 1e-30)) < 1e-10, k
+    dist.barrier(); dist.destroy_process_group()
+    print("rank", rank, "ok")
+""") % (ROOT, ROOT)
+
+
+def test_sharded_gradient_step_two_gpus(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

@@ -260,6 +260,6 @@ def test_against_committed_golden_fixtures(ctx, dtype, name):
         assert abs(vz - float(z["negll_zygote_primal"])) <= 1e-12 * (abs(vz) + 1)
         keys = sorted(k for k in z.files if k.startswith("grad_"))
         for k, (_, a) in zip(keys, flat_grads(g, fe)):
-            assert_close(a, z[k].reshape(a.shape), dtype, f"golden {k} {name}", factor=50.0)
+            assert_close(a, z[k].reshape(a.shape), dtype, f"golden {k} {name}", factor=50.0, floor=1e-3)
         X2, L2 = E.with_logabsdet_jacobian(E.inverse(fe), Y)
         assert_close(X2.to_host(), z["X"], dtype, "golden roundtrip", factor=3000)
