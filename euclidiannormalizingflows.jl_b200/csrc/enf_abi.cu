@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -21,6 +22,11 @@
 
 #include "enf_chain.cuh"
 #include "enf_launch.h"
+
+namespace enf {
+void affine_fold(int D, int n_ops, const int* kinds, const int* Ks, const double* const* params, std::vector<float>& wh,
+                 std::vector<float>& wl, std::vector<float>& bias);
+}
 
 using namespace enf;
 
@@ -149,6 +155,9 @@ struct enf_chain {
     double* d_partials = nullptr;
     double* d_sums = nullptr;  // n_raw + 1 (last: N_local, for the group all-reduce)
     double* h_sums = nullptr;  // pinned, n_raw + 1
+    // Householder/ScaleShift-only chains at large D: folded affine map for the tensor-core kernel (enf_affine.cu)
+    bool affine = false;
+    float* d_affine = nullptr;  // Wh | Wl | bias
 };
 
 namespace {
@@ -248,6 +257,23 @@ int derive_constants(enf_chain* ch) {
                             cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaEventRecord(ch->consts_copied, ctx->stream));
     ch->consts_pending = true;
+    if (ch->affine) {
+        std::vector<int> kinds, Ks;
+        std::vector<const double*> pp;
+        for (const HostOp& op : ch->ops) {
+            kinds.push_back(op.kind);
+            Ks.push_back(op.K);
+            pp.push_back(ch->params.data() + op.poff);
+        }
+        std::vector<float> wh, wl, bias;
+        affine_fold(D, int(kinds.size()), kinds.data(), Ks.data(), pp.data(), wh, wl, bias);
+        const size_t n2 = size_t(D) * D;
+        // pageable source: the copies are staged before cudaMemcpyAsync returns, so the vectors may die here
+        CU(ctx, cudaMemcpyAsync(ch->d_affine, wh.data(), n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ch->d_affine + n2, wl.data(), n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ch->d_affine + 2 * n2, bias.data(), size_t(D) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return ENF_OK;
 }
 
@@ -613,6 +639,11 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
     }
+    ch->affine = affine_supported(dtype, D, d);
+    if (ch->affine && (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_affine), (2 * size_t(D) * D + D) * sizeof(float))) != cudaSuccess) {
+        enf_chain_destroy(ch);
+        return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
+    }
     int rc = derive_constants(ch);
     if (rc != ENF_OK) { enf_chain_destroy(ch); return rc; }
     *out = ch;
@@ -644,6 +675,7 @@ extern "C" int enf_chain_destroy(enf_chain* ch) {
     if (ch->d_partials) cudaFree(ch->d_partials);
     if (ch->d_sums) cudaFree(ch->d_sums);
     if (ch->h_sums) cudaFreeHost(ch->h_sums);
+    if (ch->d_affine) cudaFree(ch->d_affine);
     if (ch->consts_copied) cudaEventDestroy(ch->consts_copied);
     delete ch;
     return ENF_OK;
@@ -672,6 +704,13 @@ static int forward_impl(enf_chain* ch, const void* x, int64_t N, void* y, void* 
     KernelSet ks;
     const int mode = pick_mode(ch, x, y);
     const double lc = ch->ladj_const_other + ch->ladj_const_ss;
+    static const bool no_affine = getenv("ENF_NO_AFFINE") != nullptr;
+    if (ch->affine && mode == MODE_VEC && !no_affine) {
+        // Householder / ScaleShift stack at large D: one tcgen05 GEMM per tile (enf_affine.cu)
+        CU(ctx, launch_affine(ch->D, ch->d_affine, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));
+        ctx->launches += 1;
+        return ENF_OK;
+    }
     StaticKernel sk;
     if (select_static(ch->dtype, ch->desc, mode, sk)) {
         CU(ctx, launch_fwd_static(ch->dtype, sk, ch->desc, ch->d_consts, x, y, want_ladj ? ladj : nullptr, N, lc,

@@ -1,0 +1,381 @@
+// F4 of SURVEY §2.3: deep Householder stacks at large D on the 5th-generation tensor cores.
+//
+// A chain that consists only of HouseholderTrafo and ScaleShiftTrafo ops is an affine
+// map y = W x + c.  The host folds the whole chain (every reflection of
+// src/householder_trafo.jl:71-78 in column order, every muladd of
+// src/scale_shift_trafo.jl:16) into W (D x D) and c in float64; the device evaluates
+//        Y^T [n x D] = X^T [n x D] . W^T [D x D] + c
+// as one GEMM per 128-sample tile with tcgen05.mma (kind::tf32, accumulators in TMEM).
+// The samples are the M dimension: a D x N column-major sample matrix IS the K-major A
+// operand (sample-major, row index contiguous), so TMA feeds it without any transpose.
+//
+// Float32 accuracy from TF32 tensor cores (3xTF32): with x = xh + xl, W = Wh + Wl
+// (h = top 19 bits, l = remainder) the kernel accumulates xh.Wh + xl.Wh + xh.Wl in the
+// f32 accumulator (the dropped xl.Wl term is 2^-22 relative).  Wh / Wl are split on
+// the host; xl is produced per K-chunk by the four worker warps between the TMA
+// arrival and the MMA issue (layout preserving: same swizzled offset, other buffer).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
+// (one elected lane), warps 2..5 = xl split during the K loop, then the epilogue
+// (tcgen05.ld -> + c -> 128-bit streaming stores, ladj = const).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "enf_chain.cuh"
+#include "enf_launch.h"
+
+namespace enf {
+namespace {
+
+constexpr int AF_TILE_M = 128;     // samples per tile (UMMA M)
+constexpr int AF_KC = 32;          // K chunk: 32 floats = one 128-byte swizzle atom
+constexpr int AF_THREADS = 192;
+constexpr int AF_WORKERS = 128;
+
+// ---- PTX wrappers -------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 bytes,
+// 8-row groups 1024 bytes apart; the tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_desc_sw128(const void* smem_ptr) {
+    const uint32_t addr = smem_u32(smem_ptr);
+    uint64_t d = 0;
+    d |= uint64_t((addr & 0x3FFFF) >> 4);            // start address, 16-byte units     [0,14)
+    d |= uint64_t(1) << 16;                           // leading byte offset (unused here) [16,30)
+    d |= uint64_t(1024 >> 4) << 32;                   // stride byte offset = 8 rows       [32,46)
+    d |= uint64_t(1) << 46;                           // descriptor version (sm_100)       [46,48)
+    d |= uint64_t(2) << 61;                           // layout type SWIZZLE_128B          [61,64)
+    return d;
+}
+
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4)                 // c_format = F32
+           | (2u << 7)               // a_format = TF32
+           | (2u << 10)              // b_format = TF32
+           | (uint32_t(N >> 3) << 17)
+           | (uint32_t(M >> 4) << 24);
+}
+
+template <int ND>
+struct AffineSmem {
+    static constexpr int STAGES = ND >= 256 ? 2 : 3;
+    static constexpr int X_BYTES = AF_TILE_M * AF_KC * 4;   // 16 KB
+    static constexpr int W_BYTES = ND * AF_KC * 4;          // 32 KB at ND = 256
+    static constexpr int STAGE_BYTES = 2 * X_BYTES + 2 * W_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;       // barriers + slack for 1024-byte alignment
+};
+
+// One CTA per SM, persistent over 128-sample tiles.
+template <int ND>
+__global__ void __launch_bounds__(AF_THREADS, 1)
+affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
+                   const __grid_constant__ CUtensorMap map_wl, const float* __restrict__ bias, float* __restrict__ y,
+                   float* __restrict__ ladj, float ladj_const, int64_t N) {
+    using S = AffineSmem<ND>;
+    constexpr int NKC = ND / AF_KC;                     // K chunks per tile (K = D = ND)
+    constexpr uint32_t TMEM_COLS = ND < 32 ? 32 : ND;  // power of two >= 32
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // TMA landed            (count 1 + tx)
+    uint64_t* split = full + S::STAGES;                                // xl written            (count 4 warps)
+    uint64_t* empty = split + S::STAGES;                               // MMAs of the stage done (tcgen05.commit)
+    uint64_t* acc_full = empty + S::STAGES;                            // tile accumulated
+    uint64_t* acc_empty = acc_full + 1;                                // epilogue drained TMEM  (count 4 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (N + AF_TILE_M - 1) / AF_TILE_M;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], AF_WORKERS / 32);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, AF_WORKERS / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < NKC; ++kc, ++it) {
+                    const int s = it % S::STAGES;
+                    if (it >= uint32_t(S::STAGES)) mbar_wait(&empty[s], ((it / S::STAGES) - 1) & 1);
+                    unsigned char* st = smem + size_t(s) * S::STAGE_BYTES;
+                    mbar_expect_tx(&full[s], S::X_BYTES + 2 * S::W_BYTES);
+                    tma_load_2d(st, &map_x, kc * AF_KC, int(tile * AF_TILE_M), &full[s]);             // x chunk  [128 x 32]
+                    tma_load_2d(st + 2 * S::X_BYTES, &map_wh, kc * AF_KC, 0, &full[s]);               // Wh chunk [ND x 32]
+                    tma_load_2d(st + 2 * S::X_BYTES + S::W_BYTES, &map_wl, kc * AF_KC, 0, &full[s]);  // Wl chunk
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_tf32(AF_TILE_M, ND);
+        uint32_t it = 0, tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            if (tcount > 0) mbar_wait(acc_empty, (tcount - 1) & 1);     // epilogue of the previous tile has drained TMEM
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kc = 0; kc < NKC; ++kc, ++it) {
+                const int s = it % S::STAGES;
+                const uint32_t ph = (it / S::STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                mbar_wait(&split[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    unsigned char* st = smem + size_t(s) * S::STAGE_BYTES;
+                    const uint64_t dxh = make_desc_sw128(st), dxl = make_desc_sw128(st + S::X_BYTES);
+                    const uint64_t dwh = make_desc_sw128(st + 2 * S::X_BYTES);
+                    const uint64_t dwl = make_desc_sw128(st + 2 * S::X_BYTES + S::W_BYTES);
+#pragma unroll
+                    for (int j = 0; j < AF_KC / 8; ++j) {          // UMMA K = 8 tf32 = 32 bytes inside the swizzle atom
+                        const uint64_t adv = uint64_t((j * 32) >> 4);
+                        umma_tf32(tmem_base, dxh + adv, dwh + adv, idesc, (kc | j) != 0);
+                        umma_tf32(tmem_base, dxl + adv, dwh + adv, idesc, 1);
+                        umma_tf32(tmem_base, dxh + adv, dwl + adv, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);                           // frees the stage when these MMAs retire
+                    if (kc == NKC - 1) umma_commit(acc_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== workers: xl split per stage, then epilogue =====
+        const int wt = threadIdx.x - 64;                             // 0..127
+        const int quarter = warp & 3;                                // TMEM lane quarter this warp may access
+        uint32_t it = 0, tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            for (int kc = 0; kc < NKC; ++kc, ++it) {
+                const int s = it % S::STAGES;
+                mbar_wait(&full[s], (it / S::STAGES) & 1);
+                const float4* xs = reinterpret_cast<const float4*>(smem + size_t(s) * S::STAGE_BYTES);
+                float4* xl = reinterpret_cast<float4*>(smem + size_t(s) * S::STAGE_BYTES + S::X_BYTES);
+#pragma unroll
+                for (int i = 0; i < S::X_BYTES / 16 / AF_WORKERS; ++i) {
+                    const float4 v = xs[wt + i * AF_WORKERS];
+                    float4 lo;
+                    lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    xl[wt + i * AF_WORKERS] = lo;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split[s]);
+            }
+            // ---- epilogue: this thread owns sample row `row` = TMEM lane 32*quarter + lane
+            mbar_wait(acc_full, tcount & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t row = tile * AF_TILE_M + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < ND / 32; ++c) {
+                float v[32];
+                tmem_ld32(taddr + uint32_t(c * 32), v);
+                if (row < N) {
+                    float* dst = y + row * ND + c * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + i);
+                        __stcs(reinterpret_cast<float4*>(dst + i),
+                               make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w));
+                    }
+                }
+            }
+            if (ladj != nullptr && row < N) __stcs(ladj + row, ladj_const);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- host side ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// row-major [rows][cols] float32 matrix, box [box_rows][32 cols], 128-byte swizzle
+bool make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * sizeof(float)};
+    const cuuint32_t box[2] = {AF_KC, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+bool affine_supported(int dtype, int D, const ChainDesc& d) {
+    if (dtype != 0 || !(D == 64 || D == 128 || D == 256)) return false;
+    int n_refl = 0;
+    for (int o = 0; o < d.n_ops; ++o) {
+        if (d.ops[o].kind != OP_HH && d.ops[o].kind != OP_SS) return false;
+        if (d.ops[o].kind == OP_HH) n_refl += d.ops[o].K;
+    }
+    return n_refl >= 8;   // shallow stacks are HBM-bound on the SIMT kernel already
+}
+
+// Fold the chain into y = W x + c (float64), split W into tf32 hi / lo.  kinds/Ks/params: the chain's ops in
+// application order; params packed like the C ABI (float64 copy).
+void affine_fold(int D, int n_ops, const int* kinds, const int* Ks, const double* const* params, std::vector<float>& wh,
+                 std::vector<float>& wl, std::vector<float>& bias) {
+    std::vector<double> W(size_t(D) * D, 0.0), c(D, 0.0), t(D);
+    for (int i = 0; i < D; ++i) W[size_t(i) * D + i] = 1.0;
+    for (int o = 0; o < n_ops; ++o) {
+        const double* p = params[o];
+        if (kinds[o] == OP_SS) {
+            for (int i = 0; i < D; ++i) {
+                for (int j = 0; j < D; ++j) W[size_t(i) * D + j] *= p[i];
+                c[i] = c[i] * p[i] + p[D + i];
+            }
+        } else {
+            for (int k = 0; k < Ks[o]; ++k) {
+                const double* v = p + size_t(k) * D;
+                double n = 0.0;
+                for (int i = 0; i < D; ++i) n += v[i] * v[i];
+                const double s = 2.0 / n;
+                for (int j = 0; j < D; ++j) {          // t = v^T W
+                    double a = 0.0;
+                    for (int i = 0; i < D; ++i) a += v[i] * W[size_t(i) * D + j];
+                    t[j] = a * s;
+                }
+                for (int i = 0; i < D; ++i)
+                    for (int j = 0; j < D; ++j) W[size_t(i) * D + j] -= v[i] * t[j];
+                double a = 0.0;
+                for (int i = 0; i < D; ++i) a += v[i] * c[i];
+                a *= s;
+                for (int i = 0; i < D; ++i) c[i] -= v[i] * a;
+            }
+        }
+    }
+    wh.resize(size_t(D) * D);
+    wl.resize(size_t(D) * D);
+    bias.resize(D);
+    for (size_t i = 0; i < W.size(); ++i) {
+        const float f = float(W[i]);
+        uint32_t bits;
+        std::memcpy(&bits, &f, 4);
+        bits = (bits + 0x1000u) & 0xFFFFE000u;          // round to tf32 (10-bit mantissa)
+        float h;
+        std::memcpy(&h, &bits, 4);
+        wh[i] = h;
+        wl[i] = float(W[i] - double(h));
+    }
+    for (int i = 0; i < D; ++i) bias[i] = float(c[i]);
+}
+
+// d_w: device buffer holding Wh | Wl | bias (2 D^2 + D floats)
+cudaError_t launch_affine(int D, const float* d_w, const void* x, void* y, void* ladj, int64_t N, double ladj_const,
+                          int sm_count, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    CUtensorMap mx, mh, ml;
+    if (!make_map(&mx, x, uint64_t(N), uint64_t(D), AF_TILE_M) || !make_map(&mh, d_w, uint64_t(D), uint64_t(D), uint32_t(D)) ||
+        !make_map(&ml, d_w + size_t(D) * D, uint64_t(D), uint64_t(D), uint32_t(D)))
+        return cudaErrorInvalidValue;
+    const float* bias = d_w + 2 * size_t(D) * D;
+    float* yf = static_cast<float*>(y);
+    float* lf = static_cast<float*>(ladj);
+    const float lc = float(ladj_const);
+    const int64_t tiles = (N + AF_TILE_M - 1) / AF_TILE_M;
+    const unsigned grid = unsigned(tiles < sm_count ? tiles : sm_count);
+    cudaError_t e = cudaSuccess;
+#define ENF_AFFINE_LAUNCH(ND)                                                                                          \
+    {                                                                                                                  \
+        const int smem = AffineSmem<ND>::TOTAL;                                                                        \
+        static bool set[64] = {};                                                                                      \
+        int dev = 0;                                                                                                   \
+        cudaGetDevice(&dev);                                                                                           \
+        if (!set[dev & 63]) {                                                                                          \
+            e = cudaFuncSetAttribute(affine_gemm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
+            if (e != cudaSuccess) return e;                                                                            \
+            set[dev & 63] = true;                                                                                      \
+        }                                                                                                              \
+        affine_gemm_kernel<ND><<<grid, AF_THREADS, smem, st>>>(mx, mh, ml, bias, yf, lf, lc, N);                       \
+    }
+    if (D == 256) ENF_AFFINE_LAUNCH(256)
+    else if (D == 128) ENF_AFFINE_LAUNCH(128)
+    else if (D == 64) ENF_AFFINE_LAUNCH(64)
+    else return cudaErrorInvalidValue;
+#undef ENF_AFFINE_LAUNCH
+    return cudaGetLastError();
+}
+
+}  // namespace enf

@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
     // shared memory: constants | saved op inputs [n_save][TV][NT] x 16 B | accumulators [n_rowslots][CH][NT] x 16 B
     // | scalar accumulators [n_scalars][NT].  Every per-thread datum is a 16-byte vector at [..][tid]:
     // LDS.128 / STS.128, conflict-free.
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T* s_c = reinterpret_cast<T*>(smem_raw);
     const int n_consts_al = (desc.n_consts + 3) & ~3;
     T* s_save = s_c + n_consts_al;

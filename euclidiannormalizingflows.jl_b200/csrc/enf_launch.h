@@ -59,6 +59,11 @@ cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, co
 cudaError_t launch_reduce(const double* partials, int n_blocks, int n_raw, double* sums, bool accumulate,
                           cudaStream_t st);
 
+// affine chains on the tensor cores (enf_affine.cu)
+bool affine_supported(int dtype, int D, const ChainDesc& d);
+cudaError_t launch_affine(int D, const float* d_w, const void* x, void* y, void* ladj, int64_t N, double ladj_const,
+                          int sm_count, cudaStream_t st);
+
 // synthetic data (enf_fill.cu)
 cudaError_t launch_fill_normal(int dtype, void* x, int D, int64_t N, int64_t col0, uint64_t seed, cudaStream_t st);
 
