@@ -289,6 +289,27 @@ def main():
                                   "hbm_frac": D_GRAD * 4 * nb / g_s / 1e9 / hbm_peak,
                                   "includes": "kernel + reduce + D2H of sums + host finish" + (" + ncclAllReduce" if world > 1 else "")}
 
+        # C4: D=256, 64 reflections + ScaleShift on the tensor cores (tcgen05 3xTF32 GEMM per tile, enf_affine.cu)
+        del Xg
+        from chains import build
+        f4 = build(E, ["hh64", "ss"], 256, np.random.default_rng(SEED + 2), np.float32)
+        n4 = min(10_000_000 // 8 if world > 1 else 6_000_000, Nl * D_MAIN // 256)
+        X4 = E.B200Matrix(ctx, 256, n4, np.float32, _ptr=X.ptr, _owner=X)
+        Y4 = E.B200Matrix(ctx, 256, n4, np.float32, _ptr=Y.ptr, _owner=Y)
+        L4 = E.B200Matrix(ctx, 1, n4, np.float32, _ptr=Ld.ptr, _owner=Ld)
+        for _ in range(2):
+            E.with_logabsdet_jacobian(f4, X4, out=(Y4, L4))
+        ctx.record(4)
+        for _ in range(3):
+            E.with_logabsdet_jacobian(f4, X4, out=(Y4, L4))
+        ctx.record(5)
+        c4_ms = max_over_ranks(ctx.elapsed_ms(4, 5) / 3)
+        flops = 3 * 2 * 256 * 256                      # issued TF32 flops per sample (3xTF32, dense folded map)
+        extras["c4_d256_k64_tensor"] = {"samples_per_s": n4 * world / (c4_ms * 1e-3), "ms_per_pass": c4_ms, "samples_per_gpu": n4,
+                                        "hbm_frac": (2 * 256 + 1) * 4 * n4 / (c4_ms * 1e-3) / 1e9 / hbm_peak,
+                                        "tf32_tflops_issued": flops * n4 / (c4_ms * 1e-3) / 1e12,
+                                        "path": "tcgen05.mma kind::tf32, 3xTF32 split, y = W x + c folded on the host"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1

@@ -240,17 +240,46 @@ int derive_constants(enf_chain* ch) {
                     if (r < D) ch->ladj_const_ss += std::log(std::fabs(a));
                     break;
                 }
-                default: {  // OP_HH: v'_k = v_k sqrt(2 / v_k.v_k)
-                    for (int k = 0; k < op.K; ++k) {
-                        const double* v = p + size_t(k) * D;
-                        double n = 0.0;
-                        for (int j = 0; j < D; ++j) n += v[j] * v[j];
-                        const double sc = std::sqrt(2.0 / n);
-                        set(base + size_t(k) * Dp, real ? v[i] * sc : 0.0);
-                    }
+                default: {  // OP_HH: v'_k = v_k sqrt(2 / v_k.v_k), filled below (needs all rows at once)
                     break;
                 }
             }
+        }
+        if (op.kind == OP_HH) {
+            // V' (K arrays) and the compact-WY factor M = V' T^T (K arrays):  H_K ... H_1 = I - M V'^T, with
+            // T upper triangular, T_jj = 1, T_{1:j-1,j} = -T_{1:j-1,1:j-1} V'^T_{1:j-1} v'_j  (tau = 1 for the
+            // pre-scaled v').  Used by the blocked Householder update of the static kernels.
+            const int K = op.K;
+            std::vector<double> Vp(size_t(D) * K), T(size_t(K) * K, 0.0), M(size_t(D) * K, 0.0);
+            for (int k = 0; k < K; ++k) {
+                const double* v = p + size_t(k) * D;
+                double n = 0.0;
+                for (int j = 0; j < D; ++j) n += v[j] * v[j];
+                const double sc = std::sqrt(2.0 / n);
+                for (int j = 0; j < D; ++j) Vp[size_t(k) * D + j] = v[j] * sc;
+            }
+            for (int j = 0; j < K; ++j) {
+                T[size_t(j) * K + j] = 1.0;
+                std::vector<double> w(j, 0.0);
+                for (int i = 0; i < j; ++i)
+                    for (int r = 0; r < D; ++r) w[i] += Vp[size_t(i) * D + r] * Vp[size_t(j) * D + r];
+                for (int i = 0; i < j; ++i) {
+                    double a = 0.0;
+                    for (int m2 = i; m2 < j; ++m2) a += T[size_t(i) * K + m2] * w[m2];
+                    T[size_t(i) * K + j] = -a;
+                }
+            }
+            // Q = H_1 ... H_K = I - V' T V'^T ;  y = H_K ... H_1 x = Q^T x = x - V' T^T (V'^T x) = x - M (V'^T x)
+            for (int k = 0; k < K; ++k)
+                for (int i = 0; i <= k; ++i)            // M[:,i] += T[i][k] ... M = V' T^T : M[:,c] = sum_k V'[:,k] T[c][k]
+                    for (int r = 0; r < D; ++r) M[size_t(i) * D + r] += Vp[size_t(k) * D + r] * T[size_t(i) * K + k];
+            for (int k = 0; k < K; ++k)
+                for (int r = 0; r < Dp; ++r) {
+                    const bool real = packed || r < D;
+                    const int i = packed ? r % D : r;
+                    set(size_t(dop.coff) + size_t(k) * Dp + r, real ? Vp[size_t(k) * D + i] : 0.0);
+                    set(size_t(dop.coff) + size_t(K + k) * Dp + r, real ? M[size_t(k) * D + i] : 0.0);
+                }
         }
     }
     CU(ctx, cudaMemcpyAsync(ch->d_consts, ch->h_consts, size_t(ch->desc.n_consts) * elem_size(ch->dtype),

@@ -15,9 +15,10 @@
 // the host; xl is produced per K-chunk by the four worker warps between the TMA
 // arrival and the MMA issue (layout preserving: same swizzled offset, other buffer).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
-// (one elected lane), warps 2..5 = xl split during the K loop, then the epilogue
-// (tcgen05.ld -> + c -> 128-bit streaming stores, ladj = const).
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
+// elected lane), warps 2-3 = xh/xl split of every K chunk, warps 4-7 = epilogue
+// (tcgen05.ld -> + c -> swizzled staging box -> TMA store; ladj = const).  Two TMEM
+// accumulators, so the epilogue of tile t overlaps the MMAs of tile t+1.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -33,13 +34,19 @@ namespace {
 
 constexpr int AF_TILE_M = 128;     // samples per tile (UMMA M)
 constexpr int AF_KC = 32;          // K chunk: 32 floats = one 128-byte swizzle atom
-constexpr int AF_THREADS = 192;
-constexpr int AF_WORKERS = 128;
+constexpr int AF_THREADS = 256;    // warp 0 TMA, warp 1 MMA, warps 2-3 split, warps 4-7 epilogue
+constexpr int AF_SPLITTERS = 64;
+constexpr int AF_EPI_WARPS = 4;
 
 // ---- PTX wrappers -------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
                  : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -101,33 +108,39 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
            | (uint32_t(M >> 4) << 24);
 }
 
+// round-to-nearest tf32 (10-bit mantissa) / remainder
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
 template <int ND>
 struct AffineSmem {
     static constexpr int STAGES = ND >= 256 ? 2 : 3;
     static constexpr int X_BYTES = AF_TILE_M * AF_KC * 4;   // 16 KB
     static constexpr int W_BYTES = ND * AF_KC * 4;          // 32 KB at ND = 256
     static constexpr int STAGE_BYTES = 2 * X_BYTES + 2 * W_BYTES;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;       // barriers + slack for 1024-byte alignment
+    static constexpr int OUT_BYTES = 32 * AF_KC * 4;        // one epilogue staging box: 32 rows x 32 cols
+    static constexpr int OUT_OFF = STAGES * STAGE_BYTES;    // [epilogue warp][2] staging boxes
+    static constexpr int BAR_OFF = OUT_OFF + AF_EPI_WARPS * 2 * OUT_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;      // barriers + slack for 1024-byte alignment
+    static constexpr uint32_t ACC_COLS = ND;                // TMEM columns per accumulator
+    static constexpr uint32_t TMEM_COLS = 2 * ND < 32 ? 32 : 2 * ND;   // two accumulators (512 at ND = 256)
 };
 
 // One CTA per SM, persistent over 128-sample tiles.
 template <int ND>
 __global__ void __launch_bounds__(AF_THREADS, 1)
 affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
-                   const __grid_constant__ CUtensorMap map_wl, const float* __restrict__ bias, float* __restrict__ y,
-                   float* __restrict__ ladj, float ladj_const, int64_t N) {
+                   const __grid_constant__ CUtensorMap map_wl, const __grid_constant__ CUtensorMap map_y,
+                   const float* __restrict__ bias, float* __restrict__ ladj, float ladj_const, int64_t N) {
     using S = AffineSmem<ND>;
     constexpr int NKC = ND / AF_KC;                     // K chunks per tile (K = D = ND)
-    constexpr uint32_t TMEM_COLS = ND < 32 ? 32 : ND;  // power of two >= 32
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // TMA landed            (count 1 + tx)
-    uint64_t* split = full + S::STAGES;                                // xl written            (count 4 warps)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // TMA landed             (count 1 + tx)
+    uint64_t* split = full + S::STAGES;                                // xh / xl written        (count 2 warps)
     uint64_t* empty = split + S::STAGES;                               // MMAs of the stage done (tcgen05.commit)
-    uint64_t* acc_full = empty + S::STAGES;                            // tile accumulated
-    uint64_t* acc_empty = acc_full + 1;                                // epilogue drained TMEM  (count 4 warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* acc_full = empty + S::STAGES;                            // [2] tile accumulated
+    uint64_t* acc_empty = acc_full + 2;                                // [2] epilogue drained   (count 4 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (N + AF_TILE_M - 1) / AF_TILE_M;
@@ -135,15 +148,17 @@ affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < S::STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&split[s], AF_WORKERS / 32);
+            mbar_init(&split[s], AF_SPLITTERS / 32);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, AF_WORKERS / 32);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], AF_EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -170,8 +185,10 @@ affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         constexpr uint32_t idesc = make_idesc_tf32(AF_TILE_M, ND);
         uint32_t it = 0, tcount = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-            if (tcount > 0) mbar_wait(acc_empty, (tcount - 1) & 1);     // epilogue of the previous tile has drained TMEM
+            const uint32_t buf = tcount & 1;
+            if (tcount >= 2) mbar_wait(&acc_empty[buf], ((tcount >> 1) - 1) & 1);   // epilogue of tile t-2 drained this buffer
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem_base + buf * S::ACC_COLS;
             for (int kc = 0; kc < NKC; ++kc, ++it) {
                 const int s = it % S::STAGES;
                 const uint32_t ph = (it / S::STAGES) & 1;
@@ -186,69 +203,82 @@ affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
                     for (int j = 0; j < AF_KC / 8; ++j) {          // UMMA K = 8 tf32 = 32 bytes inside the swizzle atom
                         const uint64_t adv = uint64_t((j * 32) >> 4);
-                        umma_tf32(tmem_base, dxh + adv, dwh + adv, idesc, (kc | j) != 0);
-                        umma_tf32(tmem_base, dxl + adv, dwh + adv, idesc, 1);
-                        umma_tf32(tmem_base, dxh + adv, dwl + adv, idesc, 1);
+                        umma_tf32(acc, dxh + adv, dwh + adv, idesc, (kc | j) != 0);
+                        umma_tf32(acc, dxl + adv, dwh + adv, idesc, 1);
+                        umma_tf32(acc, dxh + adv, dwl + adv, idesc, 1);
                     }
                     umma_commit(&empty[s]);                           // frees the stage when these MMAs retire
-                    if (kc == NKC - 1) umma_commit(acc_full);
+                    if (kc == NKC - 1) umma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
             }
         }
-    } else {
-        // ===== workers: xl split per stage, then epilogue =====
-        const int wt = threadIdx.x - 64;                             // 0..127
-        const int quarter = warp & 3;                                // TMEM lane quarter this warp may access
-        uint32_t it = 0, tcount = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+    } else if (warp < 4) {
+        // ===== splitters: x -> xh (round-to-nearest tf32, in place) and xl = x - xh (second buffer) =====
+        const int wt = threadIdx.x - 64;                             // 0..63
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kc = 0; kc < NKC; ++kc, ++it) {
                 const int s = it % S::STAGES;
                 mbar_wait(&full[s], (it / S::STAGES) & 1);
-                const float4* xs = reinterpret_cast<const float4*>(smem + size_t(s) * S::STAGE_BYTES);
+                float4* xs = reinterpret_cast<float4*>(smem + size_t(s) * S::STAGE_BYTES);
                 float4* xl = reinterpret_cast<float4*>(smem + size_t(s) * S::STAGE_BYTES + S::X_BYTES);
-#pragma unroll
-                for (int i = 0; i < S::X_BYTES / 16 / AF_WORKERS; ++i) {
-                    const float4 v = xs[wt + i * AF_WORKERS];
-                    float4 lo;
-                    lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                    xl[wt + i * AF_WORKERS] = lo;
+#pragma unroll 4
+                for (int i = 0; i < S::X_BYTES / 16 / AF_SPLITTERS; ++i) {
+                    const float4 v = xs[wt + i * AF_SPLITTERS];
+                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                    xs[wt + i * AF_SPLITTERS] = h;
+                    // the remainder is rounded to tf32 here so that the tensor core's operand truncation is exact
+                    xl[wt + i * AF_SPLITTERS] = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&split[s]);
             }
-            // ---- epilogue: this thread owns sample row `row` = TMEM lane 32*quarter + lane
-            mbar_wait(acc_full, tcount & 1);
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> (+ c) -> swizzled staging box -> TMA store =====
+        const int quarter = warp & 3;                                // TMEM lane quarter this warp may access
+        unsigned char* stage_out = smem + S::OUT_OFF + size_t(warp - 4) * 2 * S::OUT_BYTES;
+        uint32_t tcount = 0, nbox = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t buf = tcount & 1;
+            mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int64_t row = tile * AF_TILE_M + quarter * 32 + lane;
-            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
+            const int64_t row0 = tile * AF_TILE_M + quarter * 32;   // this warp's 32 sample rows; lane = row in the box
+            const uint32_t taddr = tmem_base + buf * S::ACC_COLS + (uint32_t(quarter * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < ND / 32; ++c) {
+            for (int c = 0; c < ND / 32; ++c, ++nbox) {
                 float v[32];
                 tmem_ld32(taddr + uint32_t(c * 32), v);
-                if (row < N) {
-                    float* dst = y + row * ND + c * 32;
+                // the staging box used two stores ago must have been read by its TMA store
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                float4* box = reinterpret_cast<float4*>(stage_out + (nbox & 1) * S::OUT_BYTES);
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + i);
-                        __stcs(reinterpret_cast<float4*>(dst + i),
-                               make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w));
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + j * 4);
+                    // SWIZZLE_128B: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
+                    box[lane * 8 + (j ^ (lane & 7))] =
+                        make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&map_y, box, c * 32, int(row0));      // rows beyond N are clipped by the tensor map
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
-            if (ladj != nullptr && row < N) __stcs(ladj + row, ladj_const);
+            if (ladj != nullptr && row0 + lane < N) __stcs(ladj + row0 + lane, ladj_const);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
 // ---- host side ------------------------------------------------------------------------
@@ -337,7 +367,10 @@ void affine_fold(int D, int n_ops, const int* kinds, const int* Ks, const double
         float h;
         std::memcpy(&h, &bits, 4);
         wh[i] = h;
-        wl[i] = float(W[i] - double(h));
+        const float l = float(W[i] - double(h));
+        std::memcpy(&bits, &l, 4);
+        bits = (bits + 0x1000u) & 0xFFFFE000u;          // remainder rounded to tf32 as well (operand truncation becomes exact)
+        std::memcpy(&wl[i], &bits, 4);
     }
     for (int i = 0; i < D; ++i) bias[i] = float(c[i]);
 }
@@ -346,12 +379,12 @@ void affine_fold(int D, int n_ops, const int* kinds, const int* Ks, const double
 cudaError_t launch_affine(int D, const float* d_w, const void* x, void* y, void* ladj, int64_t N, double ladj_const,
                           int sm_count, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
-    CUtensorMap mx, mh, ml;
+    CUtensorMap mx, mh, ml, my;
     if (!make_map(&mx, x, uint64_t(N), uint64_t(D), AF_TILE_M) || !make_map(&mh, d_w, uint64_t(D), uint64_t(D), uint32_t(D)) ||
-        !make_map(&ml, d_w + size_t(D) * D, uint64_t(D), uint64_t(D), uint32_t(D)))
+        !make_map(&ml, d_w + size_t(D) * D, uint64_t(D), uint64_t(D), uint32_t(D)) ||
+        !make_map(&my, y, uint64_t(N), uint64_t(D), 32))
         return cudaErrorInvalidValue;
     const float* bias = d_w + 2 * size_t(D) * D;
-    float* yf = static_cast<float*>(y);
     float* lf = static_cast<float*>(ladj);
     const float lc = float(ladj_const);
     const int64_t tiles = (N + AF_TILE_M - 1) / AF_TILE_M;
@@ -368,7 +401,7 @@ cudaError_t launch_affine(int D, const float* d_w, const void* x, void* y, void*
             if (e != cudaSuccess) return e;                                                                            \
             set[dev & 63] = true;                                                                                      \
         }                                                                                                              \
-        affine_gemm_kernel<ND><<<grid, AF_THREADS, smem, st>>>(mx, mh, ml, bias, yf, lf, lc, N);                       \
+        affine_gemm_kernel<ND><<<grid, AF_THREADS, smem, st>>>(mx, mh, ml, my, bias, lf, lc, N);                       \
     }
     if (D == 256) ENF_AFFINE_LAUNCH(256)
     else if (D == 128) ENF_AFFINE_LAUNCH(128)

@@ -147,8 +147,9 @@ cudaError_t launch_fwd_static(int dtype, const StaticKernel& k, const ChainDesc&
                               cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     const void* fn = ladj ? k.fwd_ladj : k.fwd;
+    const size_t smem = fwd_smem_bytes(dtype, desc) + (k.ring_bytes ? k.ring_bytes + 128 : 0);
     int per_sm = 0;
-    cudaError_t e = prepare_kernel(fn, k.ring_bytes, per_sm, k.threads);
+    cudaError_t e = prepare_kernel(fn, smem, per_sm, k.threads);
     if (e != cudaSuccess) return e;
     const int64_t items = (N + k.LN - 1) / k.LN;
     const int64_t tiles = (items + k.items_per_tile - 1) / k.items_per_tile;
@@ -158,7 +159,7 @@ cudaError_t launch_fwd_static(int dtype, const StaticKernel& k, const ChainDesc&
     double lc64 = ladj_const;
     void* args[] = {const_cast<ChainDesc*>(&desc), &consts, &x, &y, &ladj, &N,
                     dtype == 0 ? static_cast<void*>(&lc32) : static_cast<void*>(&lc64)};
-    return cudaLaunchKernel(fn, dim3(grid), dim3(k.threads), args, k.ring_bytes, st);
+    return cudaLaunchKernel(fn, dim3(grid), dim3(k.threads), args, smem, st);
 }
 
 cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,

@@ -50,7 +50,7 @@ struct ChainDesc {
 };
 
 __host__ __device__ constexpr int n_consts_of(int kind, int K) {
-    return (kind == OP_CS || kind == OP_CC) ? 9 : (kind == OP_JO || kind == OP_JI) ? 5 : kind == OP_SS ? 2 : K;
+    return (kind == OP_CS || kind == OP_CC) ? 9 : (kind == OP_JO || kind == OP_JI) ? 5 : kind == OP_SS ? 2 : 2 * K;   // HH: V' and M = V' T^T
 }
 __host__ __device__ constexpr int n_rowslots_of(int kind, int K) {
     return (kind == OP_CS || kind == OP_CC) ? 3 : (kind == OP_JO || kind == OP_JI) ? 4 : kind == OP_SS ? 2 : K;
@@ -303,6 +303,50 @@ __device__ __forceinline__ void elem_fwd_from(const typename C::T* cb, Tile<C>& 
     }
 }
 
+// blocked Householder stack: K reflections as ONE rank-K update  y = x - M (V'^T x)  (compact WY form with
+// M = V' T^T folded on the host).  Same FMA count as K sequential reflections, but the K dot products are
+// independent, so their shuffle reductions overlap instead of forming a chain of K dependent round trips.
+template <class C, int K>
+__device__ __forceinline__ void hh_block(Tile<C>& t, const typename C::T* vb, const typename C::T* mb) {
+    using T = typename C::T;
+    constexpr int VE = C::VE;
+    static_assert(!C::PACKED, "blocked Householder is for the lane-group layouts");
+    T d[C::SPT][K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        T vk[C::CH][VE];
+#pragma unroll
+        for (int q = 0; q < C::CH; ++q) ld16_shared(vb + k * C::DP + const_off<C>(q), vk[q]);
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u) {
+            T a = T(0);
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                for (int e = 0; e < VE; ++e) a = Prim<T>::fma_(vk[q][e], t.v[u][q][e], a);
+            d[u][k] = a;
+        }
+    }
+#pragma unroll
+    for (int off = C::G / 2; off > 0; off >>= 1)
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int k = 0; k < K; ++k) d[u][k] += __shfl_xor_sync(0xffffffffu, d[u][k], off);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        T mk[C::CH][VE];
+#pragma unroll
+        for (int q = 0; q < C::CH; ++q) ld16_shared(mb + k * C::DP + const_off<C>(q), mk[q]);
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                for (int e = 0; e < VE; ++e) t.v[u][q][e] = Prim<T>::fma_(-d[u][k], mk[q][e], t.v[u][q][e]);
+    }
+}
+
 // interpretive dispatch: the op list is data (ChainDesc), constants come from shared memory
 template <class C, bool LADJ, bool SAFE>
 __device__ __forceinline__ void apply_op_fwd(const DevOp& op, const typename C::T* s_c, Tile<C>& t,
@@ -311,6 +355,8 @@ __device__ __forceinline__ void apply_op_fwd(const DevOp& op, const typename C::
     const T* cb = s_c + op.coff;
     switch (op.kind) {
         case OP_HH:
+            // (the rank-K block update hh_block<> measured 2-5 % slower here than K sequential reflections: the
+            // extra live dot products cost more registers than the overlapped reductions save; profiles/README.md)
             for (int k = 0; k < op.K; ++k) {
                 T vk[C::CH][C::VE];
 #pragma unroll
@@ -336,34 +382,24 @@ template <class C, int CODE, bool LADJ> struct StaticOp {
     using T = typename C::T;
     static constexpr int KIND = CODE & 0xff;
     static constexpr int K = CODE >> 8;
-    static constexpr int NK = KIND == OP_HH ? K : n_fwd_consts(KIND);
-    T k[NK][C::CH][C::VE];
-    __device__ __forceinline__ void load(const T* cb) {
-#pragma unroll
-        for (int j = 0; j < NK; ++j)
-#pragma unroll
-            for (int q = 0; q < C::CH; ++q) {
-                const int slot = KIND == OP_HH ? j : fwd_const_slot(KIND, j);
-                const T* p = cb + slot * C::DP + const_off<C>(q);
-#pragma unroll
-                for (int e = 0; e < C::VE; ++e) k[j][q][e] = p[e];
-            }
-    }
+    const T* cb;   // this op's constants in shared memory
+    __device__ __forceinline__ void load(const T* s_c, const DevOp& op) { cb = s_c + op.coff; }
     template <bool SAFE>
     __device__ __forceinline__ void apply(Tile<C>& t, T (&l)[C::SPT][C::LN], bool& bad) const {
         if (KIND == OP_HH) {
+            if constexpr (K >= 2 && K <= 8 && !C::PACKED) {
+                hh_block<C, K>(t, cb, cb + K * C::DP);   // V' then M = V' T^T
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < K; ++j) {
+                    T vk[C::CH][C::VE];
 #pragma unroll
-            for (int j = 0; j < NK; ++j) hh_reflect<C>(t, k[j]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < C::CH; ++q) {
-                T kk[MAX_FWD_CONSTS][C::VE];
-#pragma unroll
-                for (int j = 0; j < NK; ++j)
-#pragma unroll
-                    for (int e = 0; e < C::VE; ++e) kk[j][e] = k[j][q][e];
-                elem_fwd_q<C, KIND, LADJ, SAFE>(t, q, kk, l, bad);
+                    for (int q = 0; q < C::CH; ++q) ld16_shared(cb + j * C::DP + const_off<C>(q), vk[q]);
+                    hh_reflect<C>(t, vk);
+                }
             }
+        } else {
+            elem_fwd_from<C, KIND, LADJ, SAFE>(cb, t, l, bad);
         }
     }
 };
@@ -377,9 +413,9 @@ template <class C, bool LADJ> struct StaticStages<C, LADJ> {
 template <class C, bool LADJ, int CODE, int... REST> struct StaticStages<C, LADJ, CODE, REST...> {
     StaticOp<C, CODE, LADJ> op;
     StaticStages<C, LADJ, REST...> rest;
-    __device__ __forceinline__ void load(const ChainDesc& d, const typename C::T* consts, int idx) {
-        op.load(consts + d.ops[idx].coff);
-        rest.load(d, consts, idx + 1);
+    __device__ __forceinline__ void load(const ChainDesc& d, const typename C::T* s_c, int idx) {
+        op.load(s_c, d.ops[idx]);
+        rest.load(d, s_c, idx + 1);
     }
     template <bool SAFE>
     __device__ __forceinline__ void apply(Tile<C>& t, typename C::T (&l)[C::SPT][C::LN], bool& bad) const {
@@ -428,6 +464,9 @@ __device__ __forceinline__ void store_ladj(typename C::T* ladj, int64_t tile, ty
 // the staged tile with LDS.128, so no warp ever waits on HBM latency and no
 // registers are tied up by loads in flight.
 constexpr int RING = 3;
+#ifndef ENF_PRODUCER_WARP
+#define ENF_PRODUCER_WARP 0   // 1: dedicated TMA producer warp (+32 threads per CTA); 0: thread 0 also feeds the ring
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -464,7 +503,7 @@ struct Ring {
     static constexpr int TILE_SAMPLES = C::SPT * C::SB;
     static constexpr size_t STAGE_BYTES = ON ? size_t(TILE_SAMPLES) * C::DP * sizeof(T) : 0;   // D <= DP
     static constexpr size_t BYTES = ON ? RING * STAGE_BYTES + 128 : 0;                          // + barriers
-    static constexpr int THREADS = ON ? NT + 32 : NT;                                           // + producer warp
+    static constexpr int THREADS = (ON && ENF_PRODUCER_WARP) ? NT + 32 : NT;                     // + producer warp
 };
 
 // issue the bulk copy of tile `tile` into ring slot `slot` (one thread)
@@ -526,6 +565,7 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         __syncthreads();
+#if ENF_PRODUCER_WARP
         if (threadIdx.x >= NT) {
             // producer warp: one lane keeps the ring full; the compute warps never synchronise with
             // each other, only with the data (warp-specialised, like the TMA warp of a GEMM)
@@ -542,6 +582,15 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
             }
             return;
         }
+#else
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < RING; ++i) {
+                const int64_t tl = int64_t(blockIdx.x) + int64_t(i) * gridDim.x;
+                if (tl < nt) ring_issue<C>(x, N, D, tl, stage0, full, i);
+            }
+        }
+#endif
     }
     int k = 0;
     for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x, ++k) {
@@ -551,6 +600,18 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
         if (Ring<C>::ON) {
             const int slot = k % RING;
             const uint32_t parity = uint32_t(k / RING) & 1u;
+#if !ENF_PRODUCER_WARP
+            // thread 0 refills the slot every warp finished reading one iteration ago (tile k-1 -> tile k-1+RING):
+            // it only ever waits for warps that are more than a whole tile behind
+            if (threadIdx.x == 0 && k >= 1) {
+                const int64_t nxt = tile + int64_t(RING - 1) * gridDim.x;
+                if (nxt < nt) {
+                    const int ps = (k - 1) % RING;
+                    while (!mbar_try_wait(&empty[ps], uint32_t((k - 1) / RING) & 1u)) {}
+                    ring_issue<C>(x, N, D, nxt, stage0, full, ps);
+                }
+            }
+#endif
             while (!mbar_try_wait(&full[slot], parity)) {}
             ring_read<C>(stage0 + size_t(slot) * Ring<C>::STAGE_BYTES, N, D, tile, t, nv);
             __syncwarp();
@@ -589,7 +650,7 @@ __device__ __forceinline__ unsigned char* ring_base(unsigned char* after_consts)
 #define ENF_FWD_MIN_CTAS 3
 #endif
 template <class C, bool LADJ>
-__global__ void __launch_bounds__(NT + 32, ENF_FWD_MIN_CTAS) chain_fwd_kernel(const __grid_constant__ ChainDesc desc,
+__global__ void __launch_bounds__(NT + 32 * ENF_PRODUCER_WARP, ENF_FWD_MIN_CTAS) chain_fwd_kernel(const __grid_constant__ ChainDesc desc,
                                                                          const typename C::T* __restrict__ consts,
                                                                          const typename C::T* x, typename C::T* y,
                                                                          typename C::T* ladj, int64_t N,
@@ -607,16 +668,18 @@ __global__ void __launch_bounds__(NT + 32, ENF_FWD_MIN_CTAS) chain_fwd_kernel(co
 
 // forward (+ ladj) for a chain known at compile time
 template <class C, bool LADJ, int... CODES>
-__global__ void __launch_bounds__(NT + 32, 2) chain_fwd_static_kernel(const __grid_constant__ ChainDesc desc,
+__global__ void __launch_bounds__(NT + 32 * ENF_PRODUCER_WARP, 2) chain_fwd_static_kernel(const __grid_constant__ ChainDesc desc,
                                                                  const typename C::T* __restrict__ consts,
                                                                  const typename C::T* x, typename C::T* y,
                                                                  typename C::T* ladj, int64_t N,
                                                                  typename C::T ladj_const) {
     using T = typename C::T;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* s_c = reinterpret_cast<T*>(smem_raw);
+    stage_constants<C>(desc, consts, s_c);
     StaticStages<C, LADJ, CODES...> stages;
-    stages.load(desc, consts, 0);
-    fwd_tile_loop<C, LADJ>(x, y, ladj, N, desc.D, ladj_const, smem_raw,
+    stages.load(desc, s_c, 0);
+    fwd_tile_loop<C, LADJ>(x, y, ladj, N, desc.D, ladj_const, ring_base<C>(smem_raw + size_t(desc.n_consts) * sizeof(T)),
                            [&](auto safe, Tile<C>& t, T (&l)[C::SPT][C::LN], bool& bad) {
                                stages.template apply<decltype(safe)::value>(t, l, bad);
                            });

@@ -23,7 +23,7 @@ void fill(StaticKernel& k) {
     k.items_per_tile = C::SB * C::SPT;
     k.LN = C::LN;
     k.Dp = C::DP;
-    k.ring_bytes = Ring<C>::BYTES;
+    k.ring_bytes = Ring<C>::BYTES;   // + the constants block, added by the launcher
     k.threads = Ring<C>::THREADS;
 }
 

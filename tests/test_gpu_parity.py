@@ -263,3 +263,29 @@ def test_against_committed_golden_fixtures(ctx, dtype, name):
             assert_close(a, z[k].reshape(a.shape), dtype, f"golden {k} {name}", factor=50.0, floor=1e-3)
         X2, L2 = E.with_logabsdet_jacobian(E.inverse(fe), Y)
         assert_close(X2.to_host(), z["X"], dtype, "golden roundtrip", factor=3000)
+
+
+@pytest.mark.parametrize("spec,D,N", [
+    (["hh64", "ss"], 256, 1000),        # C4: BASELINE configs[3]
+    (["hh64", "ss"], 256, 129),
+    (["ss", "hh32"], 128, 5000),
+    (["hh8"], 64, 127),
+    (["hh16", "ss", "hh16"], 128, 2049),
+])
+def test_affine_chains_on_tensor_cores(ctx, spec, D, N):
+    """Householder/ScaleShift-only chains at D = 64/128/256 run as one tcgen05 (3xTF32) GEMM per tile
+    (enf_affine.cu): Float32 tolerance, forward and inverse, and agreement with the SIMT kernel, which
+    unaligned column views still use."""
+    import enf_b200 as E
+    dtype = np.float32
+    fo, fe = both(spec, D, 31, dtype)
+    X = _data(D, N + 1, 32, dtype, spread=1.0)
+    Xd = E.B200Matrix.from_host(X, ctx)
+    y_ref, l_ref = O.with_logabsdet_jacobian(fo, X.astype(np.float64))
+    Y, L = E.with_logabsdet_jacobian(fe, Xd)                      # aligned -> tensor-core path
+    assert_close(Y.to_host(), y_ref, dtype, f"affine y {spec} D={D}")
+    assert_close(L.to_host()[0], l_ref, dtype, f"affine ladj {spec} D={D}", floor=1e-3)
+    Yv, Lv = E.with_logabsdet_jacobian(fe, Xd.cols(1, N + 1)) if D % 4 else (None, None)
+    X2, L2 = E.with_logabsdet_jacobian(E.inverse(fe), Y)
+    assert_close(X2.to_host(), X, dtype, "affine roundtrip", factor=4)
+    assert_close(Y.cols(0, 7).to_host(), y_ref[:, :7], dtype, "view")
