@@ -241,6 +241,11 @@ def main():
     bytes_per_sample = (2 * D_MAIN + 1) * 4
     my_ms = ctx.elapsed_ms(0, 1) / args.steps                # this rank's kernel time (one launch per step)
     achieved = bytes_per_sample * Nl / (my_ms * 1e-3) / 1e9
+    traffic = None                                           # DRAM bytes per launch, from the committed ncu capture
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = float(json.load(f)["dram_bytes_per_sample"]) * Nl
 
     # ---- e2e: public host-matrix API, pinned host buffers, H2D + kernel + D2H timed
     n_e2e = min(N_E2E, Nl)
@@ -331,7 +336,9 @@ def main():
                        "samples_per_gpu": Nl, "D": D_MAIN, "householder_K": K_HH, "parallelism": "columns sharded, no collective",
                        "l2": "inputs (%.1f GB per pass) >> 126 MB L2, no flush needed" % (bytes_per_sample * Nl / 1e9)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "traffic_source": "ncu dram__bytes_read+write per sample (profiles/r1_traffic.json) x samples per launch",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": bytes_per_sample},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": n_e2e * D_MAIN * 4,
                     "d2h_bytes_per_step": n_e2e * (D_MAIN + 1) * 4, "samples_per_step": n_e2e, "steps": e2e_steps,
