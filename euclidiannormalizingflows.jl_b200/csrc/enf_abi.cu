@@ -230,6 +230,7 @@ int derive_constants(enf_chain* ch) {
                     set(base + 2 * size_t(Dp), lm);
                     set(base + 3 * size_t(Dp), xi);
                     set(base + 4 * size_t(Dp), 1.0 / dl);
+                    set(base + 5 * size_t(Dp), 1.0 / lm);
                     if (r < D) ch->ladj_const_other += std::log(std::fabs(lm / dl));
                     break;
                 }
@@ -366,20 +367,20 @@ void finish(const enf_chain* ch, const double* sums, int64_t N, int flags, doubl
                 }
                 case OP_JO: {
                     const double r2 = row_sum(2, i), r3 = row_sum(3, i);
-                    const double dl = p[D + i], lm = p[3 * D + i];
+                    const double gm = p[i], dl = p[D + i], lm = p[3 * D + i];
                     g[i] = r0 / Nd;
-                    g[D + i] = (r1 + LB * Nd / dl) / Nd;
+                    g[D + i] = ((r1 - gm * r0) / dl + LB * Nd / dl) / Nd;     // sum G asinh z = sum G (y - gamma)/delta
                     g[2 * D + i] = (-r2 / lm) / Nd;
                     g[3 * D + i] = (-(r3 + LB * Nd) / lm) / Nd;
                     break;
                 }
                 case OP_JI: {
                     const double r2 = row_sum(2, i), r3 = row_sum(3, i);
-                    const double dl = p[D + i], lm = p[3 * D + i];
+                    const double dl = p[D + i], xi = p[2 * D + i], lm = p[3 * D + i];
                     g[i] = (-r0 / dl) / Nd;
                     g[D + i] = (-(r1 + LB * Nd) / dl) / Nd;
                     g[2 * D + i] = r2 / Nd;
-                    g[3 * D + i] = (r3 + LB * Nd / lm) / Nd;
+                    g[3 * D + i] = ((r3 - xi * r2) / lm + LB * Nd / lm) / Nd;  // sum G sinh s = sum G (y - xi)/lambda
                     break;
                 }
                 default: {  // OP_SS

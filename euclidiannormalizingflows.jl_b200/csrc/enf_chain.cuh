@@ -50,7 +50,7 @@ struct ChainDesc {
 };
 
 __host__ __device__ constexpr int n_consts_of(int kind, int K) {
-    return (kind == OP_CS || kind == OP_CC) ? 9 : (kind == OP_JO || kind == OP_JI) ? 5 : kind == OP_SS ? 2 : 2 * K;   // HH: V' and M = V' T^T
+    return (kind == OP_CS || kind == OP_CC) ? 9 : kind == OP_JO ? 5 : kind == OP_JI ? 6 : kind == OP_SS ? 2 : 2 * K;   // HH: V' and M = V' T^T
 }
 __host__ __device__ constexpr int n_rowslots_of(int kind, int K) {
     return (kind == OP_CS || kind == OP_CC) ? 3 : (kind == OP_JO || kind == OP_JI) ? 4 : kind == OP_SS ? 2 : K;
@@ -685,10 +685,11 @@ __global__ void __launch_bounds__(NT + 32 * ENF_PRODUCER_WARP, 2) chain_fwd_stat
                            });
 }
 
-// backward of one elementwise op on vector q of a tile: gt <- input cotangent,
-// ra[k][e] += m[u] * raw integrand k
+// backward of one elementwise op on vector q of a tile: xt = the op's input, yt = its output,
+// gt <- input cotangent, ra[k][e] += m[u] * raw integrand k
 template <class C, int KIND>
-__device__ __forceinline__ void bwd_elem(const Tile<C>& zt, Tile<C>& gt, int q, const typename C::T (&m)[C::SPT][C::LN],
+__device__ __forceinline__ void bwd_elem(const Tile<C>& xt, const Tile<C>& yt, Tile<C>& gt, int q,
+                                         const typename C::T (&m)[C::SPT][C::LN],
                                          const typename C::T (&c0)[C::VE], const typename C::T (&c1)[C::VE],
                                          const typename C::T (&c2)[C::VE], const typename C::T (&c3)[C::VE],
                                          const typename C::T (&c4)[C::VE], const typename C::T (&c5)[C::VE],
@@ -699,20 +700,20 @@ __device__ __forceinline__ void bwd_elem(const Tile<C>& zt, Tile<C>& gt, int q, 
 #pragma unroll
         for (int e = 0; e < C::VE; ++e) {
             T r[4] = {T(0), T(0), T(0), T(0)};
-            const T xin = zt.v[u][q][e], G = gt.v[u][q][e];
+            const T xin = xt.v[u][q][e], yout = yt.v[u][q][e], G = gt.v[u][q][e];
             T gx;
             if (KIND == OP_SS) {
                 r[0] = G * xin;
                 r[1] = G;
                 gx = G * c0[e];
             } else if (KIND == OP_CS) {
-                gx = cs_bwd<T>(xin, G, c0[e], c1[e], c2[e], c3[e], c4[e], c5[e], r);
+                gx = cs_bwd<T>(xin, yout, G, c0[e], c1[e], c2[e], c3[e], c4[e], c5[e], r);
             } else if (KIND == OP_CC) {
-                gx = cc_bwd<T>(xin, G, c0[e], c1[e], c2[e], c3[e], c4[e], c5[e], r);
+                gx = cc_bwd<T>(xin, yout, G, c0[e], c1[e], c2[e], c3[e], c4[e], c5[e], r);
             } else if (KIND == OP_JO) {
-                gx = jo_bwd<T>(xin, G, c0[e], c1[e], c3[e], c4[e], r);
+                gx = jo_bwd<T>(xin, yout, G, c0[e], c1[e], c4[e], r);
             } else {
-                gx = ji_bwd<T>(xin, G, c0[e], c1[e], c2[e], c4[e], r);
+                gx = ji_bwd<T>(xin, yout, G, c0[e], c1[e], c2[e], c3[e], c4[e], c5[e], r);
             }
             gt.v[u][q][e] = gx;
 #pragma unroll
@@ -885,13 +886,14 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
                 }
                 continue;
             }
-            // elementwise op: reload its input, differentiate
+            // elementwise op: zt holds its output; reload its input, differentiate
+            Tile<C> xt;
             {
                 const T* sv = s_save + (size_t(op.save) * TV * NT + tid) * VE;
 #pragma unroll
                 for (int u = 0; u < C::SPT; ++u)
 #pragma unroll
-                    for (int q = 0; q < C::CH; ++q) ld16_shared(sv + size_t(u * C::CH + q) * NT * VE, zt.v[u][q]);
+                    for (int q = 0; q < C::CH; ++q) ld16_shared(sv + size_t(u * C::CH + q) * NT * VE, xt.v[u][q]);
             }
 #pragma unroll
             for (int q = 0; q < C::CH; ++q) {
@@ -904,24 +906,25 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
                     ld16_shared(cb + 3 * Dp + co, c3);
                 }
                 if (op.kind != OP_SS) ld16_shared(cb + 4 * Dp + co, c4);
-                if (op.kind == OP_CS || op.kind == OP_CC) ld16_shared(cb + 5 * Dp + co, c5);
+                if (op.kind == OP_CS || op.kind == OP_CC || op.kind == OP_JI) ld16_shared(cb + 5 * Dp + co, c5);
                 T ra[4][VE];
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
                     for (int e = 0; e < VE; ++e) ra[k][e] = T(0);
                 switch (op.kind) {
-                    case OP_SS: bwd_elem<C, OP_SS>(zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                    case OP_CS: bwd_elem<C, OP_CS>(zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                    case OP_CC: bwd_elem<C, OP_CC>(zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                    case OP_JO: bwd_elem<C, OP_JO>(zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                    default: bwd_elem<C, OP_JI>(zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                    case OP_SS: bwd_elem<C, OP_SS>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                    case OP_CS: bwd_elem<C, OP_CS>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                    case OP_CC: bwd_elem<C, OP_CC>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                    case OP_JO: bwd_elem<C, OP_JO>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                    default: bwd_elem<C, OP_JI>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
                 }
                 const int nr = n_rowslots_of(op.kind, 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (k < nr) acc16_shared<T, VE>(s_acc + ((size_t(op.roff + k) * C::CH + q) * NT + tid) * VE, ra[k]);
             }
+            zt = xt;   // the input of this op is the output of the previous one
         }
     }
     // ---- CTA reduction in float64, fixed order

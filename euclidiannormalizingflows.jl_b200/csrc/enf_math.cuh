@@ -136,7 +136,7 @@ __device__ __forceinline__ T log_of_ratio(const T (&n)[N], const T (&d)[N], bool
 // constants (one value per row; K[k][e] = constant k of element e):
 //   CS / CC:  0 nb2 = -b log2(e)   1 A = e^{ba}   2 ib2 = LGU/b   3 c   4 a   5 b   6 A/2   7 2/A   8 (1+A^2)/A
 //   JO:       0 1/lambda   1 -xi/lambda   2 gamma   3 delta*LGU   4 delta
-//   JI:       0 U/delta    1 -gamma U/delta   2 lambda   3 xi   4 1/delta      (U = log2(e) for f32, 1 for f64)
+//   JI:       0 U/delta    1 -gamma U/delta   2 lambda   3 xi   4 1/delta   5 1/lambda   (U = log2(e) for f32, 1 for f64)
 
 // CenterStretch: src/center_stretch.jl:4-8 (value), :39-43 (ladj = -center_contract_ladj(y)).
 // With w = e^{-b|x|}, A = e^{ba}: e^{b(|u|-|x|)} = g = sqrt(m^2 + w) + m, m = (1-w)A/2 (the positive root of
@@ -227,102 +227,107 @@ __device__ __forceinline__ void ji_fwd_v(T* v, const T* k0, const T* k1, const T
 }
 
 // ---------------------------------------------------------------- backward
-// Every *_bwd takes the op's INPUT x and the output cotangent G, returns the
-// input cotangent and writes the raw-sum integrands r[...] (summed over samples
-// on the device, mapped to parameter gradients by enf_abi.cu: finish).
+// Every *_bwd takes the op's INPUT x, its OUTPUT y (both are at hand in the reverse sweep: y is the
+// input of the next op) and the output cotangent G; it returns the input cotangent and writes the
+// raw-sum integrands r[...] (summed over samples on the device, mapped to parameter gradients by
+// enf_abi.cu: finish).  Using y avoids recomputing the forward transcendental (log / asinh / sinh), and
+// the three reciprocals of the CenterContract sigmoids collapse into one:
+//   n1 = 1 + A w, n2 = A + w, n3 = n2 + w n1, R = 1/(n1 n2 n3):
+//   sigma_1 = 1/n1 = n2 n3 R,  sigma_2 = w/n2 = w n1 n3 R,  S = n3/(n1 n2) = n3^2 R,  1/S = (n1 n2)^2 R.
+
+template <typename T>
+struct CcParts { T S, iS, Su, Sa, Sb, ds; };   // ds = sigma_2 - sigma_1
+
+template <typename T>
+__device__ __forceinline__ CcParts<T> cc_parts(T au, T w, T A, T a, T b, T& s1au, T& s2au) {
+    using P = Prim<T>;
+    const T n1 = P::fma_(A, w, T(1));
+    const T n2 = A + w;
+    const T n3 = P::fma_(w, n1, n2);
+    const T p12 = n1 * n2;
+    const T R = P::rcp(p12 * n3);
+    const T t = n3 * R;
+    const T s1 = n2 * t;
+    const T s2 = w * n1 * t;
+    const T d1 = s1 * (T(1) - s1);
+    const T d2 = s2 * (T(1) - s2);
+    CcParts<T> o;
+    o.S = n3 * t;
+    o.iS = p12 * (p12 * R);
+    o.Su = b * (d1 - d2);
+    o.Sa = -b * (d1 + d2);
+    o.Sb = (au - a) * d1 - (au + a) * d2;
+    o.ds = s2 - s1;
+    s1au = s1 * (au - a);
+    s2au = s2 * (au + a);
+    return o;
+}
 
 // CenterContract.  raw: r0 -> -dc, r1 -> da, r2 -> db.
 template <typename T>
-__device__ __forceinline__ T cc_bwd(T x, T G, T nb2, T A, T ib2, T c, T a, T b, T* r) {
+__device__ __forceinline__ T cc_bwd(T x, T y, T G, T nb2, T A, T ib2, T c, T a, T b, T* r) {
     using P = Prim<T>;
     const T ib = ib2 * P::INV_LGU;
-    T u = x - c;
-    T au = P::abs_(u);
-    T sg = u < T(0) ? T(-1) : T(1);
-    T w = P::ex2(nb2 * au);
-    T n1 = P::fma_(A, w, T(1));
-    T n2 = A + w;
-    T s1 = P::rcp(n1);
-    T s2 = w * P::rcp(n2);
-    T S = s1 + s2;
-    T d1 = s1 * (T(1) - s1);
-    T d2 = s2 * (T(1) - s2);
-    T ya = P::fma_(P::lg(n1 * P::rcp(n2)), ib2, au);
-    T Su = b * (d1 - d2);
-    T Sa = -b * (d1 + d2);
-    T Sb = (au - a) * d1 - (au + a) * d2;
-    T ya_a = s2 - s1;
-    T ya_b = (s1 * (au - a) + s2 * (au + a) - ya) * ib;
-    T iS = P::rcp(S);
-    T Gx = G * S - sg * Su * iS;                // LB = -1
+    const T u = x - c;
+    const T au = P::abs_(u);
+    const T sg = u < T(0) ? T(-1) : T(1);
+    T s1au, s2au;
+    const CcParts<T> k = cc_parts<T>(au, P::ex2(nb2 * au), A, a, b, s1au, s2au);
+    const T ya_b = (s1au + s2au - P::abs_(y)) * ib;
+    const T Gx = G * k.S - sg * k.Su * k.iS;       // LB = -1
     r[0] = Gx;
-    r[1] = sg * G * ya_a - Sa * iS;
-    r[2] = sg * G * ya_b - Sb * iS;
+    r[1] = sg * G * k.ds - k.Sa * k.iS;
+    r[2] = sg * G * ya_b - k.Sb * k.iS;
     return Gx;
 }
 
-// CenterStretch (implicit inverse of CenterContract).  raw: r0 -> dc, r1 -> da, r2 -> db.
+// CenterStretch (implicit inverse of CenterContract: its output y plays the contract's input).
+// raw: r0 -> dc, r1 -> da, r2 -> db.
 template <typename T>
-__device__ __forceinline__ T cs_bwd(T x, T G, T nb2, T A, T ib2, T c, T a, T b, T* r) {
+__device__ __forceinline__ T cs_bwd(T x, T y, T G, T nb2, T A, T ib2, T c, T a, T b, T* r) {
     using P = Prim<T>;
     const T ib = ib2 * P::INV_LGU;
-    T ax = P::abs_(x);
-    T sg = x < T(0) ? T(-1) : T(1);
-    T w0 = P::ex2(nb2 * ax);
-    T m = P::fma_(-A, w0, A);
-    T g = T(0.5) * (P::sqrt_(P::fma_(m, m, T(4) * w0)) + m);
-    T au = P::fma_(P::lg(g), ib2, ax);
-    T wu = w0 * P::rcp(g);
-    T n1 = P::fma_(A, wu, T(1));
-    T n2 = A + wu;
-    T s1 = P::rcp(n1);
-    T s2 = wu * P::rcp(n2);
-    T S = s1 + s2;
-    T d1 = s1 * (T(1) - s1);
-    T d2 = s2 * (T(1) - s2);
-    T Su = b * (d1 - d2);
-    T Sa = -b * (d1 + d2);
-    T Sb = (au - a) * d1 - (au + a) * d2;
-    T Ca = s2 - s1;
-    T Cb = (s1 * (au - a) + s2 * (au + a) - ax) * ib;
-    T iS = P::rcp(S);
-    T Gy = G + sg * Su * iS;                    // G - LB*sg*Su/S
-    T Gx = Gy * iS;
+    const T u = y - c;
+    const T au = P::abs_(u);
+    const T sg = x < T(0) ? T(-1) : T(1);
+    T s1au, s2au;
+    const CcParts<T> k = cc_parts<T>(au, P::ex2(nb2 * au), A, a, b, s1au, s2au);
+    const T Cb = (s1au + s2au - P::abs_(x)) * ib;
+    const T Gy = G + sg * k.Su * k.iS;              // G - LB*sg*Su/S
+    const T Gx = Gy * k.iS;
     r[0] = G;
-    r[1] = -Gx * sg * Ca + Sa * iS;
-    r[2] = -Gx * sg * Cb + Sb * iS;
+    r[1] = -Gx * sg * k.ds + k.Sa * k.iS;
+    r[2] = -Gx * sg * Cb + k.Sb * k.iS;
     return Gx;
 }
 
-// JohnsonTrafo.  raw: r0 = G, r1 = G asinh z, r2 = gz, r3 = z gz.
+// JohnsonTrafo.  raw: r0 = G, r1 = G y, r2 = gz, r3 = z gz   (G asinh z = G (y - gamma)/delta: finished on the host)
 template <typename T>
-__device__ __forceinline__ T jo_bwd(T x, T G, T il, T c0, T delta2, T delta, T* r) {
+__device__ __forceinline__ T jo_bwd(T x, T y, T G, T il, T c0, T delta, T* r) {
     using P = Prim<T>;
-    T z = P::fma_(x, il, c0);
-    T s = P::fma_(z, z, T(1));
-    T rr = P::rsq(s);
-    T ash = P::asinh_lg(z, s, rr) * P::LGU;
-    T gz = P::fma_(G * delta, rr, z * rr * rr); // G delta r - LB z r^2
+    const T z = P::fma_(x, il, c0);
+    const T rr = P::rsq(P::fma_(z, z, T(1)));
+    const T gz = P::fma_(G * delta, rr, z * rr * rr); // G delta r - LB z r^2
     r[0] = G;
-    r[1] = G * ash;
+    r[1] = G * y;
     r[2] = gz;
     r[3] = z * gz;
     return gz * il;
 }
 
-// JohnsonTrafoInv.  raw: r0 = gs, r1 = s gs, r2 = G, r3 = G sinh s.
+// JohnsonTrafoInv.  raw: r0 = gs, r1 = s gs, r2 = G, r3 = G y   (sinh s = (y - xi)/lambda)
 template <typename T>
-__device__ __forceinline__ T ji_bwd(T x, T G, T k0, T k1, T lam, T idl, T* r) {
+__device__ __forceinline__ T ji_bwd(T x, T y, T G, T k0, T k1, T lam, T xi, T idl, T ilam, T* r) {
     using P = Prim<T>;
-    T sa = P::fma_(x, k0, k1);
-    T sh, ch;
-    P::sinhcosh(sa, sh, ch);
-    T s = (sizeof(T) == 4) ? sa * P::LGU : sa;      // argument in natural units
-    T gs = P::fma_(G * lam, ch, -sh * P::rcp(ch));  // G lam cosh + LB tanh
+    const T s = P::fma_(x, k0, k1) * P::LGU;          // argument in natural units
+    const T sh = (y - xi) * ilam;
+    const T q = P::fma_(sh, sh, T(1));
+    const T rq = P::rsq(q);                           // 1/cosh s
+    const T gs = P::fma_(G * lam, q * rq, -sh * rq);  // G lam cosh + LB tanh
     r[0] = gs;
     r[1] = s * gs;
     r[2] = G;
-    r[3] = G * sh;
+    r[3] = G * y;
     return gs * idl;
 }
 

@@ -97,33 +97,37 @@ def hh_fwd(x, V):
 
 # ---------------------------------------------------------------- backward
 # each returns (Gx, raw) ; finish_*() maps raw sums -> parameter gradients
-def _cc_parts(au, A, a, b):
-    w = np.exp2(-b * LOG2E * au)
+def _cc_parts(au, w, A, a, b):
+    """sigma_1 = 1/n1, sigma_2 = w/n2, S = sigma_1 + sigma_2 and 1/S from ONE reciprocal."""
     n1 = 1 + A * w
     n2 = A + w
-    s1 = 1 / n1
-    s2 = w / n2
-    S = s1 + s2
+    n3 = n2 + w * n1
+    p12 = n1 * n2
+    R = 1 / (p12 * n3)
+    t = n3 * R
+    s1 = n2 * t
+    s2 = w * n1 * t
     d1 = s1 * (1 - s1)
     d2 = s2 * (1 - s2)
-    ya = au + np.log(n1 / n2) / b
+    S = n3 * t
+    iS = p12 * (p12 * R)
     Su = b * (d1 - d2)                       # * sgn
     Sa = -b * (d1 + d2)
     Sb = (au - a) * d1 - (au + a) * d2
-    ya_a = s2 - s1                           # * sgn
-    ya_b = (s1 * (au - a) + s2 * (au + a) - ya) / b   # * sgn
-    return S, Su, Sa, Sb, ya_a, ya_b
+    return S, iS, Su, Sa, Sb, s2 - s1, s1 * (au - a) + s2 * (au + a)
 
 
-def cc_bwd(x, G, a, b, c):
+def cc_bwd(x, y, G, a, b, c):
+    """x: the op's input, y: its output (|y| replaces the recomputed forward value)."""
     a, b, c = a[:, None], b[:, None], c[:, None]
     A = np.exp(b * a)
     u = x - c
+    au = np.abs(u)
     sg = np.where(u < 0, -1.0, 1.0)
-    S, Su, Sa, Sb, ya_a, ya_b = _cc_parts(np.abs(u), A, a, b)
-    iS = 1 / S
+    S, iS, Su, Sa, Sb, ds, ssum = _cc_parts(au, np.exp2(-b * LOG2E * au), A, a, b)
+    ya_b = (ssum - np.abs(y)) / b
     Gx = G * S + LB * sg * Su * iS
-    ra = sg * G * ya_a + LB * Sa * iS
+    ra = sg * G * ds + LB * Sa * iS
     rb = sg * G * ya_b + LB * Sb * iS
     return Gx, (Gx.sum(1), ra.sum(1), rb.sum(1))
 
@@ -133,34 +137,17 @@ def cc_finish(raw, N, a, b, c):
     return {"a": R2, "b": R3, "c": -R1}
 
 
-def cs_bwd(x, G, a, b, c):
-    """x: the op's INPUT.  Recomputes u = y - c and differentiates implicitly."""
+def cs_bwd(x, y, G, a, b, c):
+    """Implicit differentiation of the inverse of CenterContract at u = y - c."""
     a, b, c = a[:, None], b[:, None], c[:, None]
     A = np.exp(b * a)
-    ax = np.abs(x)
+    au = np.abs(y - c)
     sg = np.where(x < 0, -1.0, 1.0)
-    w0 = np.exp2(-b * LOG2E * ax)
-    m = A - A * w0
-    g = 0.5 * (np.sqrt(m * m + 4 * w0) + m)
-    au = ax + np.log(g) / b
-    # contract partials at u (its output is x): pass ya = |x|
-    wu = w0 / g
-    n1 = 1 + A * wu
-    n2 = A + wu
-    s1 = 1 / n1
-    s2 = wu / n2
-    S = s1 + s2
-    d1 = s1 * (1 - s1)
-    d2 = s2 * (1 - s2)
-    Su = b * (d1 - d2)
-    Sa = -b * (d1 + d2)
-    Sb = (au - a) * d1 - (au + a) * d2
-    Ca = s2 - s1
-    Cb = (s1 * (au - a) + s2 * (au + a) - ax) / b
-    iS = 1 / S
+    S, iS, Su, Sa, Sb, ds, ssum = _cc_parts(au, np.exp2(-b * LOG2E * au), A, a, b)
+    Cb = (ssum - np.abs(x)) / b
     Gy = G - LB * sg * Su * iS               # total cotangent on y
     Gx = Gy * iS
-    ra = -Gx * sg * Ca - LB * Sa * iS
+    ra = -Gx * sg * ds - LB * Sa * iS
     rb = -Gx * sg * Cb - LB * Sb * iS
     return Gx, (G.sum(1), ra.sum(1), rb.sum(1))
 
@@ -170,37 +157,34 @@ def cs_finish(raw, N, a, b, c):
     return {"a": R2, "b": R3, "c": R1}
 
 
-def jo_bwd(x, G, gamma, delta, xi, lam):
+def jo_bwd(x, y, G, gamma, delta, xi, lam):
     gamma, delta, xi, lam = gamma[:, None], delta[:, None], xi[:, None], lam[:, None]
     il = 1 / lam
     z = x * il - xi * il
-    s = 1 + z * z
-    r = 1 / np.sqrt(s)
-    ash = np.copysign(np.log(np.abs(z) + s * r), z)
+    r = 1 / np.sqrt(1 + z * z)
     gz = G * delta * r - LB * z * r * r
-    return gz * il, (G.sum(1), (G * ash).sum(1), gz.sum(1), (z * gz).sum(1))
+    return gz * il, (G.sum(1), (G * y).sum(1), gz.sum(1), (z * gz).sum(1))
 
 
 def jo_finish(raw, N, gamma, delta, xi, lam):
     S1, S2, S3, S4 = raw
-    return {"gamma": S1, "delta": S2 + LB * N / delta, "xi": -S3 / lam, "lam": -(S4 + LB * N) / lam}
+    return {"gamma": S1, "delta": (S2 - gamma * S1) / delta + LB * N / delta, "xi": -S3 / lam, "lam": -(S4 + LB * N) / lam}
 
 
-def ji_bwd(x, G, gamma, delta, xi, lam):
+def ji_bwd(x, y, G, gamma, delta, xi, lam):
     gamma, delta, xi, lam = gamma[:, None], delta[:, None], xi[:, None], lam[:, None]
     idl = 1 / delta
     s = x * idl - gamma * idl
-    e = np.exp2(LOG2E * s)
-    ei = 1 / e
-    sh = 0.5 * (e - ei)
-    ch = 0.5 * (e + ei)
-    gs = G * lam * ch + LB * sh / ch
-    return gs * idl, (gs.sum(1), (s * gs).sum(1), G.sum(1), (G * sh).sum(1))
+    sh = (y - xi) / lam
+    q = 1 + sh * sh
+    rq = 1 / np.sqrt(q)
+    gs = G * lam * q * rq + LB * sh * rq
+    return gs * idl, (gs.sum(1), (s * gs).sum(1), G.sum(1), (G * y).sum(1))
 
 
 def ji_finish(raw, N, gamma, delta, xi, lam):
     S1, S2, S3, S4 = raw
-    return {"gamma": -S1 / delta, "delta": -(S2 + LB * N) / delta, "xi": S3, "lam": S4 + LB * N / lam}
+    return {"gamma": -S1 / delta, "delta": -(S2 + LB * N) / delta, "xi": S3, "lam": (S4 - xi * S3) / lam + LB * N / lam}
 
 
 def ss_bwd(x, G, a, b):

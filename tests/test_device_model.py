@@ -60,10 +60,10 @@ def test_forward_and_gradient_algebra(seed):
     for i in reversed(range(len(ops))):
         k, o = ops[i]
         xin, xout = xs[i], xs[i + 1]
-        if k == "cc": G, raw = M.cc_bwd(xin, G, o.a, o.b, o.c); g = M.cc_finish(raw, N, o.a, o.b, o.c)
-        elif k == "cs": G, raw = M.cs_bwd(xin, G, o.a, o.b, o.c); g = M.cs_finish(raw, N, o.a, o.b, o.c)
-        elif k == "jo": G, raw = M.jo_bwd(xin, G, o.gamma, o.delta, o.xi, o.lam); g = M.jo_finish(raw, N, o.gamma, o.delta, o.xi, o.lam)
-        elif k == "ji": G, raw = M.ji_bwd(xin, G, o.gamma, o.delta, o.xi, o.lam); g = M.ji_finish(raw, N, o.gamma, o.delta, o.xi, o.lam)
+        if k == "cc": G, raw = M.cc_bwd(xin, xout, G, o.a, o.b, o.c); g = M.cc_finish(raw, N, o.a, o.b, o.c)
+        elif k == "cs": G, raw = M.cs_bwd(xin, xout, G, o.a, o.b, o.c); g = M.cs_finish(raw, N, o.a, o.b, o.c)
+        elif k == "jo": G, raw = M.jo_bwd(xin, xout, G, o.gamma, o.delta, o.xi, o.lam); g = M.jo_finish(raw, N, o.gamma, o.delta, o.xi, o.lam)
+        elif k == "ji": G, raw = M.ji_bwd(xin, xout, G, o.gamma, o.delta, o.xi, o.lam); g = M.ji_finish(raw, N, o.gamma, o.delta, o.xi, o.lam)
         elif k == "ss": G, raw = M.ss_bwd(xin, G, o.a, o.b); g = M.ss_finish(raw, N, o.a, o.b)
         else:
             G, raw, z = M.hh_bwd(xout, G, o.V)
