@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -99,6 +100,20 @@ __device__ __forceinline__ uint64_t make_desc_sw128(const void* smem_ptr) {
     return d;
 }
 
+// K-major descriptor for rows of KC floats: KC = 32 -> SWIZZLE_128B, KC = 16 -> SWIZZLE_64B (8-row groups KC*32 bytes apart)
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc_kmajor(const void* smem_ptr) {
+    static_assert(KC == 32 || KC == 16, "one swizzle atom per row");
+    const uint32_t addr = smem_u32(smem_ptr);
+    uint64_t d = 0;
+    d |= uint64_t((addr & 0x3FFFF) >> 4);
+    d |= uint64_t(1) << 16;
+    d |= uint64_t((8 * KC * 4) >> 4) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(KC == 32 ? 2 : 4) << 61;
+    return d;
+}
+
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4)                 // c_format = F32
@@ -111,11 +126,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 // round-to-nearest tf32 (10-bit mantissa) / remainder
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
-template <int ND>
+template <int ND, int KC>
 struct AffineSmem {
-    static constexpr int STAGES = ND >= 256 ? 2 : 3;
-    static constexpr int X_BYTES = AF_TILE_M * AF_KC * 4;   // 16 KB
-    static constexpr int W_BYTES = ND * AF_KC * 4;          // 32 KB at ND = 256
+    static constexpr int X_BYTES = AF_TILE_M * KC * 4;      // 16 KB at KC = 32
+    static constexpr int W_BYTES = ND * KC * 4;             // 32 KB at ND = 256, KC = 32
+    static constexpr int STAGES = (192 * 1024) / (2 * X_BYTES + 2 * W_BYTES) > 6 ? 6 : (192 * 1024) / (2 * X_BYTES + 2 * W_BYTES);
     static constexpr int STAGE_BYTES = 2 * X_BYTES + 2 * W_BYTES;
     static constexpr int OUT_BYTES = 32 * AF_KC * 4;        // one epilogue staging box: 32 rows x 32 cols
     static constexpr int OUT_OFF = STAGES * STAGE_BYTES;    // [epilogue warp][2] staging boxes
@@ -126,13 +141,13 @@ struct AffineSmem {
 };
 
 // One CTA per SM, persistent over 128-sample tiles.
-template <int ND>
+template <int ND, int KC>
 __global__ void __launch_bounds__(AF_THREADS, 1)
 affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
                    const __grid_constant__ CUtensorMap map_wl, const __grid_constant__ CUtensorMap map_y,
                    const float* __restrict__ bias, float* __restrict__ ladj, float ladj_const, int64_t N) {
-    using S = AffineSmem<ND>;
-    constexpr int NKC = ND / AF_KC;                     // K chunks per tile (K = D = ND)
+    using S = AffineSmem<ND, KC>;
+    constexpr int NKC = ND / KC;                        // K chunks per tile (K = D = ND)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // TMA landed             (count 1 + tx)
@@ -174,9 +189,9 @@ affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     if (it >= uint32_t(S::STAGES)) mbar_wait(&empty[s], ((it / S::STAGES) - 1) & 1);
                     unsigned char* st = smem + size_t(s) * S::STAGE_BYTES;
                     mbar_expect_tx(&full[s], S::X_BYTES + 2 * S::W_BYTES);
-                    tma_load_2d(st, &map_x, kc * AF_KC, int(tile * AF_TILE_M), &full[s]);             // x chunk  [128 x 32]
-                    tma_load_2d(st + 2 * S::X_BYTES, &map_wh, kc * AF_KC, 0, &full[s]);               // Wh chunk [ND x 32]
-                    tma_load_2d(st + 2 * S::X_BYTES + S::W_BYTES, &map_wl, kc * AF_KC, 0, &full[s]);  // Wl chunk
+                    tma_load_2d(st, &map_x, kc * KC, int(tile * AF_TILE_M), &full[s]);             // x chunk  [128 x 32]
+                    tma_load_2d(st + 2 * S::X_BYTES, &map_wh, kc * KC, 0, &full[s]);               // Wh chunk [ND x 32]
+                    tma_load_2d(st + 2 * S::X_BYTES + S::W_BYTES, &map_wl, kc * KC, 0, &full[s]);  // Wl chunk
                 }
             }
         }
@@ -197,11 +212,11 @@ affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     unsigned char* st = smem + size_t(s) * S::STAGE_BYTES;
-                    const uint64_t dxh = make_desc_sw128(st), dxl = make_desc_sw128(st + S::X_BYTES);
-                    const uint64_t dwh = make_desc_sw128(st + 2 * S::X_BYTES);
-                    const uint64_t dwl = make_desc_sw128(st + 2 * S::X_BYTES + S::W_BYTES);
+                    const uint64_t dxh = make_desc_kmajor<KC>(st), dxl = make_desc_kmajor<KC>(st + S::X_BYTES);
+                    const uint64_t dwh = make_desc_kmajor<KC>(st + 2 * S::X_BYTES);
+                    const uint64_t dwl = make_desc_kmajor<KC>(st + 2 * S::X_BYTES + S::W_BYTES);
 #pragma unroll
-                    for (int j = 0; j < AF_KC / 8; ++j) {          // UMMA K = 8 tf32 = 32 bytes inside the swizzle atom
+                    for (int j = 0; j < KC / 8; ++j) {             // UMMA K = 8 tf32 = 32 bytes inside the swizzle atom
                         const uint64_t adv = uint64_t((j * 32) >> 4);
                         umma_tf32(acc, dxh + adv, dwh + adv, idesc, (kc | j) != 0);
                         umma_tf32(acc, dxl + adv, dwh + adv, idesc, 1);
@@ -281,6 +296,232 @@ affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
+// ======================================================================================
+// 2-SM variant (cta_group::2): a CTA pair (cluster of 2) computes a 256-sample tile with
+// ONE tcgen05.mma.cta_group::2 per K step (M = 256).  Each CTA holds its own 128 sample
+// rows (A) and only HALF of the W chunk (B: N/2 rows), so the per-CTA L2->SM traffic for W
+// and its shared-memory footprint are halved -> three pipeline stages fit instead of two.
+// Barriers: x_full / empty / acc_full are per CTA (empty and acc_full are signalled in both
+// CTAs by a multicast tcgen05.commit); w_full, split_done and acc_empty live in the leader
+// CTA (rank 0) and are signalled remotely by the peer.
+// ======================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t ncluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address of a CTA pair -> rank 0
+__device__ __forceinline__ void tma_load_2d_to_leader_bar(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    // data lands in THIS CTA's shared memory, the transaction bytes are counted on the LEADER CTA's mbarrier
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(uint16_t(3))
+                 : "memory");
+}
+
+template <int ND>
+struct Affine2Smem {
+    static constexpr int STAGES = 3;
+    static constexpr int X_BYTES = AF_TILE_M * AF_KC * 4;        // 16 KB (this CTA's 128 rows)
+    static constexpr int W_BYTES = (ND / 2) * AF_KC * 4;         // this CTA's half of the W chunk (16 KB at ND = 256)
+    static constexpr int STAGE_BYTES = 2 * X_BYTES + 2 * W_BYTES;
+    static constexpr int OUT_BYTES = 32 * AF_KC * 4;
+    static constexpr int OUT_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = OUT_OFF + AF_EPI_WARPS * 2 * OUT_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr uint32_t ACC_COLS = ND;
+    static constexpr uint32_t TMEM_COLS = 2 * ND < 32 ? 32 : 2 * ND;
+};
+
+template <int ND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AF_THREADS, 1)
+affine2_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
+                    const __grid_constant__ CUtensorMap map_wl, const __grid_constant__ CUtensorMap map_y,
+                    const float* __restrict__ bias, float* __restrict__ ladj, float ladj_const, int64_t N) {
+    using S = Affine2Smem<ND>;
+    constexpr int NKC = ND / AF_KC;
+    constexpr int NH = ND / 2;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);  // local : this CTA's x chunk landed
+    uint64_t* w_full = x_full + S::STAGES;                              // leader: both W halves landed
+    uint64_t* split = w_full + S::STAGES;                               // leader: xh/xl written in both CTAs (4 warps)
+    uint64_t* empty = split + S::STAGES;                                // local : stage consumed (multicast commit)
+    uint64_t* acc_full = empty + S::STAGES;                             // local [2]: tile accumulated (multicast commit)
+    uint64_t* acc_empty = acc_full + 2;                                 // leader [2]: both epilogues drained (8 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int64_t n_ptiles = (N + 2 * AF_TILE_M - 1) / (2 * AF_TILE_M);   // 256-sample pair tiles
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S::STAGES; ++s) {
+            mbar_init(&x_full[s], 1);
+            mbar_init(&w_full[s], 1);
+            mbar_init(&split[s], 2 * AF_SPLITTERS / 32);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 2 * AF_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, S::TMEM_COLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();          // the peer's barriers exist before anything remote is signalled
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t pt = cluster_id_x(); pt < n_ptiles; pt += ncluster_id_x()) {
+                const int row0 = int(pt * 2 * AF_TILE_M + rank * AF_TILE_M);
+                for (int kc = 0; kc < NKC; ++kc, ++it) {
+                    const int s = it % S::STAGES;
+                    if (it >= uint32_t(S::STAGES)) mbar_wait(&empty[s], ((it / S::STAGES) - 1) & 1);
+                    unsigned char* st = smem + size_t(s) * S::STAGE_BYTES;
+                    mbar_expect_tx(&x_full[s], S::X_BYTES);
+                    tma_load_2d(st, &map_x, kc * AF_KC, row0, &x_full[s]);
+                    if (rank == 0) mbar_expect_tx(&w_full[s], 4 * S::W_BYTES);     // Wh + Wl halves of both CTAs
+                    tma_load_2d_to_leader_bar(st + 2 * S::X_BYTES, &map_wh, kc * AF_KC, int(rank) * NH, &w_full[s]);
+                    tma_load_2d_to_leader_bar(st + 2 * S::X_BYTES + S::W_BYTES, &map_wl, kc * AF_KC, int(rank) * NH, &w_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only; one lane issues for the pair) =====
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(2 * AF_TILE_M, ND);
+            uint32_t it = 0, tcount = 0;
+            for (int64_t pt = cluster_id_x(); pt < n_ptiles; pt += ncluster_id_x(), ++tcount) {
+                const uint32_t buf = tcount & 1;
+                if (tcount >= 2) mbar_wait(&acc_empty[buf], ((tcount >> 1) - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + buf * S::ACC_COLS;
+                for (int kc = 0; kc < NKC; ++kc, ++it) {
+                    const int s = it % S::STAGES;
+                    const uint32_t ph = (it / S::STAGES) & 1;
+                    mbar_wait(&w_full[s], ph);
+                    mbar_wait(&split[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        unsigned char* st = smem + size_t(s) * S::STAGE_BYTES;
+                        const uint64_t dxh = make_desc_sw128(st), dxl = make_desc_sw128(st + S::X_BYTES);
+                        const uint64_t dwh = make_desc_sw128(st + 2 * S::X_BYTES);
+                        const uint64_t dwl = make_desc_sw128(st + 2 * S::X_BYTES + S::W_BYTES);
+#pragma unroll
+                        for (int j = 0; j < AF_KC / 8; ++j) {
+                            const uint64_t adv = uint64_t((j * 32) >> 4);
+                            umma2_tf32(acc, dxh + adv, dwh + adv, idesc, (kc | j) != 0);
+                            umma2_tf32(acc, dxl + adv, dwh + adv, idesc, 1);
+                            umma2_tf32(acc, dxh + adv, dwl + adv, idesc, 1);
+                        }
+                        umma2_commit_both(&empty[s]);
+                        if (kc == NKC - 1) umma2_commit_both(&acc_full[buf]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp < 4) {
+        // ===== splitters (both CTAs): local x chunk -> xh (in place) and xl; signal the leader =====
+        const int wt = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int64_t pt = cluster_id_x(); pt < n_ptiles; pt += ncluster_id_x()) {
+            for (int kc = 0; kc < NKC; ++kc, ++it) {
+                const int s = it % S::STAGES;
+                mbar_wait(&x_full[s], (it / S::STAGES) & 1);
+                float4* xs = reinterpret_cast<float4*>(smem + size_t(s) * S::STAGE_BYTES);
+                float4* xl = reinterpret_cast<float4*>(smem + size_t(s) * S::STAGE_BYTES + S::X_BYTES);
+#pragma unroll 4
+                for (int i = 0; i < S::X_BYTES / 16 / AF_SPLITTERS; ++i) {
+                    const float4 v = xs[wt + i * AF_SPLITTERS];
+                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                    xs[wt + i * AF_SPLITTERS] = h;
+                    xl[wt + i * AF_SPLITTERS] = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&split[s], 0);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): own 128 rows of the accumulator =====
+        const int quarter = warp & 3;
+        unsigned char* stage_out = smem + S::OUT_OFF + size_t(warp - 4) * 2 * S::OUT_BYTES;
+        uint32_t tcount = 0, nbox = 0;
+        for (int64_t pt = cluster_id_x(); pt < n_ptiles; pt += ncluster_id_x(), ++tcount) {
+            const uint32_t buf = tcount & 1;
+            mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t row0 = pt * 2 * AF_TILE_M + rank * AF_TILE_M + quarter * 32;
+            const uint32_t taddr = tmem_base + buf * S::ACC_COLS + (uint32_t(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < ND / 32; ++c, ++nbox) {
+                float v[32];
+                tmem_ld32(taddr + uint32_t(c * 32), v);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                float4* box = reinterpret_cast<float4*>(stage_out + (nbox & 1) * S::OUT_BYTES);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + j * 4);
+                    box[lane * 8 + (j ^ (lane & 7))] =
+                        make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (row0 < N) tma_store_2d(&map_y, box, c * 32, int(row0));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            if (ladj != nullptr && row0 + lane < N) __stcs(ladj + row0 + lane, ladj_const);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&acc_empty[buf], 0);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();          // nobody leaves while the peer may still signal or read this CTA
+    if (warp == 1) tmem_dealloc2(tmem_base, S::TMEM_COLS);
+}
+
 // ---- host side ------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -299,15 +540,16 @@ EncodeTiledFn get_encode() {
 }
 
 // row-major [rows][cols] float32 matrix, box [box_rows][32 cols], 128-byte swizzle
-bool make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+bool make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols = AF_KC) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     const cuuint64_t dims[2] = {cols, rows};
     const cuuint64_t strides[1] = {cols * sizeof(float)};
-    const cuuint32_t box[2] = {AF_KC, box_rows};
+    const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -379,9 +621,15 @@ void affine_fold(int D, int n_ops, const int* kinds, const int* Ks, const double
 cudaError_t launch_affine(int D, const float* d_w, const void* x, void* y, void* ladj, int64_t N, double ladj_const,
                           int sm_count, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
+    // cta_group::2 pairs measured slower than independent CTAs in round 1 (profiles/README.md): opt-in
+    static const bool two_sm = getenv("ENF_AFFINE_2SM") != nullptr;
+    static const int kc_env = getenv("ENF_AFFINE_KC") ? atoi(getenv("ENF_AFFINE_KC")) : 0;
+    const bool use2 = two_sm && D >= 128;
+    const uint32_t kc = use2 ? 32u : (kc_env == 16 || kc_env == 32) ? uint32_t(kc_env) : 32u;
     CUtensorMap mx, mh, ml, my;
-    if (!make_map(&mx, x, uint64_t(N), uint64_t(D), AF_TILE_M) || !make_map(&mh, d_w, uint64_t(D), uint64_t(D), uint32_t(D)) ||
-        !make_map(&ml, d_w + size_t(D) * D, uint64_t(D), uint64_t(D), uint32_t(D)) ||
+    const uint32_t wbox = use2 ? uint32_t(D / 2) : uint32_t(D);
+    if (!make_map(&mx, x, uint64_t(N), uint64_t(D), AF_TILE_M, kc) || !make_map(&mh, d_w, uint64_t(D), uint64_t(D), wbox, kc) ||
+        !make_map(&ml, d_w + size_t(D) * D, uint64_t(D), uint64_t(D), wbox, kc) ||
         !make_map(&my, y, uint64_t(N), uint64_t(D), 32))
         return cudaErrorInvalidValue;
     const float* bias = d_w + 2 * size_t(D) * D;
@@ -390,24 +638,51 @@ cudaError_t launch_affine(int D, const float* d_w, const void* x, void* y, void*
     const int64_t tiles = (N + AF_TILE_M - 1) / AF_TILE_M;
     const unsigned grid = unsigned(tiles < sm_count ? tiles : sm_count);
     cudaError_t e = cudaSuccess;
-#define ENF_AFFINE_LAUNCH(ND)                                                                                          \
+#define ENF_AFFINE_LAUNCH_KC(ND, KC)                                                                                   \
     {                                                                                                                  \
-        const int smem = AffineSmem<ND>::TOTAL;                                                                        \
+        const int smem = AffineSmem<ND, KC>::TOTAL;                                                                    \
         static bool set[64] = {};                                                                                      \
         int dev = 0;                                                                                                   \
         cudaGetDevice(&dev);                                                                                           \
         if (!set[dev & 63]) {                                                                                          \
-            e = cudaFuncSetAttribute(affine_gemm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
+            e = cudaFuncSetAttribute(affine_gemm_kernel<ND, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   \
             if (e != cudaSuccess) return e;                                                                            \
             set[dev & 63] = true;                                                                                      \
         }                                                                                                              \
-        affine_gemm_kernel<ND><<<grid, AF_THREADS, smem, st>>>(mx, mh, ml, my, bias, lf, lc, N);                       \
+        affine_gemm_kernel<ND, KC><<<grid, AF_THREADS, smem, st>>>(mx, mh, ml, my, bias, lf, lc, N);                   \
+    }
+#define ENF_AFFINE_LAUNCH(ND)                                                                                          \
+    {                                                                                                                  \
+        if (kc == 16) ENF_AFFINE_LAUNCH_KC(ND, 16) else ENF_AFFINE_LAUNCH_KC(ND, 32)                                   \
+    }
+    if (use2) {
+        const int64_t ptiles = (N + 2 * AF_TILE_M - 1) / (2 * AF_TILE_M);
+        const int max_pairs = sm_count / 2;
+        const unsigned grid2 = 2u * unsigned(ptiles < max_pairs ? ptiles : max_pairs);
+#define ENF_AFFINE2_LAUNCH(ND)                                                                                         \
+    {                                                                                                                  \
+        const int smem = Affine2Smem<ND>::TOTAL;                                                                       \
+        static bool set[64] = {};                                                                                      \
+        int dev = 0;                                                                                                   \
+        cudaGetDevice(&dev);                                                                                           \
+        if (!set[dev & 63]) {                                                                                          \
+            e = cudaFuncSetAttribute(affine2_gemm_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      \
+            if (e != cudaSuccess) return e;                                                                            \
+            set[dev & 63] = true;                                                                                      \
+        }                                                                                                              \
+        affine2_gemm_kernel<ND><<<grid2, AF_THREADS, smem, st>>>(mx, mh, ml, my, bias, lf, lc, N);                     \
+    }
+        if (D == 256) ENF_AFFINE2_LAUNCH(256)
+        else ENF_AFFINE2_LAUNCH(128)
+#undef ENF_AFFINE2_LAUNCH
+        return cudaGetLastError();
     }
     if (D == 256) ENF_AFFINE_LAUNCH(256)
     else if (D == 128) ENF_AFFINE_LAUNCH(128)
     else if (D == 64) ENF_AFFINE_LAUNCH(64)
     else return cudaErrorInvalidValue;
 #undef ENF_AFFINE_LAUNCH
+#undef ENF_AFFINE_LAUNCH_KC
     return cudaGetLastError();
 }
 
