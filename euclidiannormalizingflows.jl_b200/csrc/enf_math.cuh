@@ -117,7 +117,7 @@ __device__ __forceinline__ T log_of_ratio(const T (&n)[N], const T (&d)[N], bool
     if (SAFE) {
         T L = T(0);
 #pragma unroll
-        for (int i = 0; i < N; ++i) L += P::lg(n[i]) - P::lg(d[i]);
+        for (int i = 0; i < N; ++i) L += P::lg(n[i] * P::rcp(d[i]));   // log of the ratio: no cancellation of two large logs
         return L;
     }
     T pn = n[0], pd = d[0];

@@ -289,3 +289,40 @@ def test_affine_chains_on_tensor_cores(ctx, spec, D, N):
     X2, L2 = E.with_logabsdet_jacobian(E.inverse(fe), Y)
     assert_close(X2.to_host(), X, dtype, "affine roundtrip", factor=4)
     assert_close(Y.cols(0, 7).to_host(), y_ref[:, :7], dtype, "view")
+
+
+@pytest.mark.parametrize("code", ["ji", "cs", "cc", "jo"])
+def test_range_guard_redo_path(ctx, code):
+    """The Float32 kernels take ONE log of the product of a lane's Jacobian factors; when that product leaves
+    the float range the warp redoes the tile with per-element logs.  Parameters / inputs chosen so that the
+    products overflow or underflow while every per-element quantity (and the reference) stays finite."""
+    import enf_b200 as E
+    D, N = 16, 4096
+    rng = np.random.default_rng(77)
+    one = np.ones(D, dtype=np.float32)
+    if code == "ji":      # cosh(s) ~ 1e13 per element -> product of 4 overflows
+        fo = O.JohnsonTrafoInv(0 * one, one, 0 * one, one)
+        fe = E.JohnsonTrafoInv(0 * one, one, 0 * one, one)
+        X = (rng.choice([-1.0, 1.0], (D, N)) * rng.uniform(28, 32, (D, N))).astype(np.float32)
+    elif code == "jo":    # z ~ 1e12 -> r = 1/sqrt(1+z^2) ~ 1e-12, product of 4 underflows
+        fo = O.JohnsonTrafo(0 * one, one, 0 * one, 1e-9 * one)
+        fe = E.JohnsonTrafo(0 * one, one, 0 * one, 1e-9 * one)
+        X = (rng.standard_normal((D, N)) * 1e3).astype(np.float32)
+    else:                 # e^{ba} = e^{20}: the sigmoid-sum numerators/denominators ~ A^2..A^3 per element
+        a, b, c = 10 * one, 2 * one, 0 * one
+        fo = (O.CenterStretch if code == "cs" else O.CenterContract)(a, b, c)
+        fe = (E.CenterStretch if code == "cs" else E.CenterContract)(a, b, c)
+        X = (rng.standard_normal((D, N)) * (3 if code == "cs" else 12)).astype(np.float32)
+    Y, L = E.with_logabsdet_jacobian(fe, E.B200Matrix.from_host(X, ctx))
+    y_ref, l_ref = O.with_logabsdet_jacobian(fo, X.astype(np.float64))
+    assert np.isfinite(y_ref).all() and np.isfinite(l_ref).all()
+    y, l = Y.to_host(), L.to_host()[0]
+    assert np.isfinite(y).all() and np.isfinite(l).all()
+    assert_close(y, y_ref, np.float32, f"redo y {code}", factor=2)
+    # CenterStretch at e^{ba} = 5e8: S -> 1 - e^{-b|x|}, so ladj = -log S is conditioned like log(1 + delta) with delta
+    # formed in Float32 -- for this kernel and for the reference's Float32 formula alike (src/center_stretch.jl:20-21)
+    assert_close(l, l_ref, np.float32, f"redo ladj {code}", factor=8 if code == "cs" else 2)
+    if code in ("ji", "cc"):     # and through the loss / gradient kernel's forward pass
+        v = E.mvnormal_negll_trafo(fe, E.B200Matrix.from_host(X, ctx))
+        v_ref = float(O.mvnormal_negll_trafo(fo, X.astype(np.float64)))
+        assert np.isfinite(v) and abs(v - v_ref) <= 1e-5 * (abs(v_ref) + 1)
