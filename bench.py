@@ -315,6 +315,24 @@ def main():
                                         "tf32_tflops_issued": flops * n4 / (c4_ms * 1e-3) / 1e12,
                                         "path": "tcgen05.mma kind::tf32, 3xTF32 split, y = W x + c folded on the host"}
 
+        # C2: 1-D JohnsonTrafo + ScaleShiftTrafo whitening fit, 1e7 samples, nbatches=100 (examples/nf_example_1d.jl shape):
+        # time per gradient step of the host loop (one fused kernel + host optimizer per step) and of the device loop
+        n2 = min(10_000_000, Nl * D_MAIN)
+        one = np.ones(1, dtype=np.float32)
+        f2 = E.compose(E.JohnsonTrafo(0 * one, 5 * one, 0 * one, 5 * one), E.ScaleShiftTrafo(one.copy(), 0 * one))
+        X2 = E.B200Matrix(ctx, 1, n2, np.float32, _ptr=X.ptr, _owner=X)
+        E.optimize_whitening(X2, f2, E.ADAGrad(), nbatches=100, nepochs=1, device_loop=True, group=world > 1)
+        ctx.sync(); barrier()
+        t0 = time.perf_counter()
+        rr = E.optimize_whitening(X2, f2, E.ADAGrad(), nbatches=100, nepochs=20, device_loop=True, group=world > 1)
+        dev_s = max_over_ranks(time.perf_counter() - t0) / len(rr["negll_history"])
+        t0 = time.perf_counter()
+        rr = E.optimize_whitening(X2, f2, E.ADAGrad(), nbatches=100, nepochs=2, group=world > 1)
+        host_s = max_over_ranks(time.perf_counter() - t0) / len(rr["negll_history"])
+        extras["fit_c2_d1"] = {"batch_per_gpu": n2 // 100, "us_per_step_device_loop": dev_s * 1e6, "us_per_step_host_loop": host_s * 1e6,
+                               "samples_per_s_device_loop": (n2 // 100) * world / dev_s,
+                               "note": "optimize_whitening steps; device loop = enf_optimize_whitening (2 launches/step, CUDA graph per epoch)"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1

@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -923,4 +924,156 @@ extern "C" int enf_negll_grad_group(enf_chain* ch, const void* x, int64_t N_loca
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     const int64_t N_global = int64_t(std::llround(ch->h_sums[ch->n_raw]));
     return enf_negll_grad_finish(ch, ch->h_sums, N_global, flags, negll, grads_host);
+}
+
+// ------------------------------------------------------------------ device-side fit loop
+extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, int64_t nbatches, int64_t nepochs,
+                                      double eta, double epsilon, int flags, int use_group, int fresh_state,
+                                      double* state_inout, void* params_out, double* history_out, int64_t* n_steps_out) {
+    if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
+    enf_ctx* ctx = ch->ctx;
+    if (!x || !state_inout || !params_out || !history_out) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    if (N < 1 || nbatches < 1 || nepochs < 0) return fail(ctx, ENF_ERR_INVALID, "bad N / nbatches / nepochs");
+    if (use_group && !ctx->comm) return fail(ctx, ENF_ERR_INVALID, "enf_group_init has not been called on this context");
+    CU(ctx, cudaSetDevice(ctx->device));
+    // src/optimize_whitening.jl:31: batchsize = round(Int, length(smpls) / nbatches)  (ties to even)
+    const int64_t batchsize = int64_t(std::nearbyint(double(N) / double(nbatches)));
+    if (batchsize < 1) return fail(ctx, ENF_ERR_INVALID, "nbatches exceeds the number of samples");
+    const int64_t nb = (N + batchsize - 1) / batchsize;
+    const int64_t n_steps = nb * nepochs;
+    if (n_steps_out) *n_steps_out = n_steps;
+    const size_t P = ch->n_params;
+    const size_t es = elem_size(ch->dtype);
+
+    FitDesc fd;
+    std::memset(&fd, 0, sizeof fd);
+    fd.n_ops = int(ch->ops.size());
+    fd.D = ch->D;
+    fd.Dp = ch->desc.Dp;
+    fd.packed = ch->plan.packed ? 1 : 0;
+    fd.n_rowslots = ch->desc.n_rowslots;
+    fd.n_raw = ch->n_raw;
+    for (int o = 0; o < fd.n_ops; ++o) {
+        fd.ops[o].kind = ch->ops[o].kind;
+        fd.ops[o].K = ch->ops[o].K;
+        fd.ops[o].poff = int(ch->ops[o].poff);
+        fd.ops[o].coff = ch->desc.ops[o].coff;
+        fd.ops[o].roff = ch->desc.ops[o].roff;
+        fd.ops[o].soff = ch->desc.ops[o].soff;
+    }
+    KernelSet ks_probe;
+    if (!select_kernels(ch->dtype, ch->plan, ch->plan.packed ? MODE_PACKU : MODE_SCALAR, ks_probe))
+        return fail(ctx, ENF_ERR_INVALID, "no kernel variant for dtype=%d D=%d", ch->dtype, ch->D);
+    if (grad_smem_bytes(ch->dtype, ch->desc, ks_probe, true) > 227 * 1024)
+        return fail(ctx, ENF_ERR_INVALID, "chain too large for the fused gradient kernel");
+
+    double *d_params = nullptr, *d_state = nullptr, *d_lconst = nullptr, *d_hist = nullptr, *d_counts = nullptr;
+    long long* d_step = nullptr;
+    std::vector<double> counts(static_cast<size_t>(nb), 0.0);
+    std::vector<double> st0(P, 0.0);
+    for (int64_t b = 0; b < nb; ++b) counts[size_t(b)] = double(std::min(batchsize, N - b * batchsize));
+    for (size_t i = 0; i < P; ++i) st0[i] = fresh_state ? epsilon : state_inout[i];
+    auto cleanup = [&]() {
+        if (d_params) cudaFree(d_params);
+        if (d_state) cudaFree(d_state);
+        if (d_lconst) cudaFree(d_lconst);
+        if (d_hist) cudaFree(d_hist);
+        if (d_counts) cudaFree(d_counts);
+        if (d_step) cudaFree(d_step);
+    };
+#define CUF(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            cleanup();                                                                                   \
+            return fail(ctx, ENF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                \
+    } while (0)
+    CUF(cudaMalloc(reinterpret_cast<void**>(&d_params), P * sizeof(double)));
+    CUF(cudaMalloc(reinterpret_cast<void**>(&d_state), P * sizeof(double)));
+    CUF(cudaMalloc(reinterpret_cast<void**>(&d_lconst), 2 * sizeof(double)));
+    CUF(cudaMalloc(reinterpret_cast<void**>(&d_hist), size_t(n_steps ? n_steps : 1) * sizeof(double)));
+    CUF(cudaMalloc(reinterpret_cast<void**>(&d_counts), size_t(nb) * sizeof(double)));
+    CUF(cudaMalloc(reinterpret_cast<void**>(&d_step), sizeof(long long)));
+    CUF(cudaMemcpyAsync(d_params, ch->params.data(), P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUF(cudaMemcpyAsync(d_state, st0.data(), P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUF(cudaMemcpyAsync(d_counts, counts.data(), size_t(nb) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUF(cudaStreamSynchronize(ctx->stream));   // the pageable sources above may now go away / be reused
+    if (ch->consts_pending) {
+        CUF(cudaEventSynchronize(ch->consts_copied));
+        ch->consts_pending = false;
+    }
+    CUF(cudaMemsetAsync(d_step, 0, sizeof(long long), ctx->stream));
+    CUF(launch_fit_derive(ch->dtype, fd, d_params, ch->d_consts, d_lconst, ctx->stream));   // constants + ladj row constants of step 0
+    // one epoch = nb steps of (derive, grad, reduce, count, [all-reduce], update); identical every epoch
+    auto enqueue_epoch = [&]() -> int {
+        for (int64_t b = 0; b < nb; ++b) {
+            const int64_t start = b * batchsize, nbt = std::min(batchsize, N - start);
+            const char* xb = static_cast<const char*>(x) + size_t(start) * size_t(ch->D) * es;
+            KernelSet ks;
+            select_kernels(ch->dtype, ch->plan, pick_mode(ch, xb, nullptr), ks);
+            int blocks = 0;
+            CUF(launch_grad(ch->dtype, ks, ch->desc, ch->d_consts, xb, nbt, true, ch->d_partials, ch->max_blocks, &blocks,
+                            ctx->sm_count, ctx->stream));
+            if (use_group) {
+                CUF(launch_reduce(ch->d_partials, blocks, ch->n_raw, ch->d_sums, false, ctx->stream));
+                CUF(cudaMemcpyAsync(ch->d_sums + ch->n_raw, d_counts + b, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+                ncclResult_t r = g_nccl.AllReduce(ch->d_sums, ch->d_sums, size_t(ch->n_raw + 1), ncclDouble, ncclSum, ctx->comm, ctx->stream);
+                if (r != ncclSuccess) {
+                    cleanup();
+                    return fail(ctx, ENF_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+                }
+                CUF(launch_fit_update(ch->dtype, fd, ch->d_sums, nullptr, 0, 0.0, d_lconst, d_params, d_state, eta, epsilon, flags,
+                                      d_hist, d_step, ch->d_consts, ctx->stream));
+                ctx->launches += 3;
+            } else {
+                CUF(launch_fit_update(ch->dtype, fd, ch->d_sums, ch->d_partials, blocks, double(nbt), d_lconst, d_params, d_state,
+                                      eta, epsilon, flags, d_hist, d_step, ch->d_consts, ctx->stream));
+                ctx->launches += 2;
+            }
+        }
+        return ENF_OK;
+    };
+    int64_t ep = 0;
+    if (nepochs >= 1) {          // first epoch directly: it also sets the kernels' shared-memory attributes (not capturable)
+        int rc = enqueue_epoch();
+        if (rc != ENF_OK) return rc;
+        ep = 1;
+    }
+    static const bool no_graph = getenv("ENF_NO_GRAPH") != nullptr;
+    if (nepochs - ep >= 2 && !no_graph && nb <= 4096) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            int rc = enqueue_epoch();
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc != ENF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            ok = ce == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        }
+        if (ok) {
+            for (; ep < nepochs; ++ep) {
+                cudaError_t le = cudaGraphLaunch(exec, ctx->stream);
+                if (le != cudaSuccess) { ok = false; break; }
+            }
+        } else {
+            cudaGetLastError();   // capture unsupported here: fall through to direct launches
+        }
+        if (exec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(exec); }
+        if (graph) cudaGraphDestroy(graph);
+    }
+    for (; ep < nepochs; ++ep) {
+        int rc = enqueue_epoch();
+        if (rc != ENF_OK) return rc;
+    }
+    std::vector<double> pfin(P);
+    CUF(cudaMemcpyAsync(pfin.data(), d_params, P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUF(cudaMemcpyAsync(state_inout, d_state, P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_steps) CUF(cudaMemcpyAsync(history_out, d_hist, size_t(n_steps) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUF(cudaStreamSynchronize(ctx->stream));
+#undef CUF
+    cleanup();
+    ch->params = pfin;
+    export_grads(ch, pfin, params_out);        // same packed layout / dtype conversion as gradients
+    return derive_constants(ch);               // host derivation restores everything (incl. the compact-WY factors)
 }

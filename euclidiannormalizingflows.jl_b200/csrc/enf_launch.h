@@ -64,6 +64,25 @@ bool affine_supported(int dtype, int D, const ChainDesc& d);
 cudaError_t launch_affine(int D, const float* d_w, const void* x, void* y, void* ladj, int64_t N, double ladj_const,
                           int sm_count, cudaStream_t st);
 
+// device-side optimize_whitening loop (enf_fit.cu)
+struct FitOp {
+    int kind, K;
+    int poff;   // offset of the op's parameters in the packed parameter vector
+    int coff;   // offset of its constants in the constants block
+    int roff;   // first per-row raw-sum slot
+    int soff;   // first scalar raw-sum slot
+};
+struct FitDesc {
+    int n_ops, D, Dp, packed;
+    int n_rowslots, n_raw;
+    FitOp ops[24];
+};
+cudaError_t launch_fit_derive(int dtype, const FitDesc& fd, const double* params, void* consts, double* lconst,
+                              cudaStream_t st);
+cudaError_t launch_fit_update(int dtype, const FitDesc& fd, double* sums, const double* partials, int n_blocks, double count,
+                              double* lconst, double* params, double* state, double eta, double eps, int flags,
+                              double* history, long long* step_ctr, void* consts, cudaStream_t st);
+
 // synthetic data (enf_fill.cu)
 cudaError_t launch_fill_normal(int dtype, void* x, int D, int64_t N, int64_t col0, uint64_t seed, cudaStream_t st);
 

@@ -16,7 +16,7 @@ from typing import Any, Dict, List, Optional, Tuple
 import numpy as np
 
 from .device import B200Matrix, Context, default_context
-from .trafos import (ComposedFunction, HouseholderTrafo, Trafo, mvnormal_negll_trafograd, result_dtype)
+from .trafos import (ComposedFunction, HouseholderTrafo, Trafo, flatten, mvnormal_negll_trafograd, result_dtype)
 
 
 @dataclass
@@ -70,17 +70,89 @@ def batch_ranges(nsamples: int, nbatches: int) -> List[Tuple[int, int]]:
     return [(s, min(s + batchsize, nsamples)) for s in range(0, nsamples, batchsize)]
 
 
+def _pack_tree(trafo, tree, D):
+    """nested per-field structure (optimizer state) -> packed float64 vector in parameter order."""
+    out = []
+    for lf, st in zip(flatten(trafo), _leaves_of(trafo, tree)):
+        for n in lf.fields:
+            a = np.asarray(st[n], dtype=np.float64)
+            if a.ndim == 0:
+                raise TypeError("the device loop needs vector-valued parameters (expand scalar fields first)")
+            out.append(np.asfortranarray(a.reshape(D, -1)).ravel(order="F"))
+    return np.ascontiguousarray(np.concatenate(out))
+
+
+def _leaves_of(trafo, tree):
+    if isinstance(trafo, ComposedFunction):
+        return _leaves_of(trafo.inner, tree["inner"]) + _leaves_of(trafo.outer, tree["outer"])
+    return [tree]
+
+
+def _unpack_tree(trafo, flat, D):
+    pos = [0]
+
+    def rec(f):
+        if isinstance(f, ComposedFunction):
+            inner = rec(f.inner)
+            outer = rec(f.outer)
+            return {"outer": outer, "inner": inner}
+        out = {}
+        for n in f.fields:
+            shape = np.shape(getattr(f, n))
+            k = int(np.prod(shape))
+            out[n] = flat[pos[0]:pos[0] + k].reshape(shape, order="F").copy()
+            pos[0] += k
+        return out
+
+    return rec(trafo)
+
+
+def _rebuild(trafo, tree):
+    if isinstance(trafo, ComposedFunction):
+        return ComposedFunction(_rebuild(trafo.outer, tree["outer"]), _rebuild(trafo.inner, tree["inner"]))
+    return type(trafo)(**{n: tree[n] for n in trafo.fields})
+
+
+def _optimize_whitening_device(smpls, trafo, optimizer, nbatches, nepochs, optstate, group):
+    """enf_optimize_whitening: the whole loop on the device."""
+    import ctypes as C
+    from . import _lib as L
+    from .trafos import get_chain
+    ctx = smpls.ctx
+    ch = get_chain(trafo, smpls.D, smpls.dtype, ctx)
+    P = ch.nparams
+    state = _pack_tree(trafo, optstate, smpls.D) if optstate is not None else np.empty(P, dtype=np.float64)
+    nb = len(batch_ranges(smpls.N, nbatches))
+    hist = np.empty(max(nb * nepochs, 1), dtype=np.float64)
+    params = np.empty(P, dtype=smpls.dtype)
+    n_steps = C.c_int64()
+    L.check(ctx._lib.enf_optimize_whitening(
+        ch.handle, C.c_void_p(smpls.ptr), smpls.N, int(nbatches), int(nepochs), float(optimizer.eta), float(optimizer.epsilon),
+        L.ENF_NEGLL_ZYGOTE_PRIMAL, 1 if group else 0, 0 if optstate is not None else 1,
+        state.ctypes.data_as(C.c_void_p), params.ctypes.data_as(C.c_void_p), hist.ctypes.data_as(C.c_void_p),
+        C.byref(n_steps)), ctx.handle)
+    ch.last = params.copy()
+    result = _rebuild(trafo, _unpack_tree(trafo, params, smpls.D))
+    return result, _unpack_tree(trafo, state, smpls.D), [float(v) for v in hist[:n_steps.value]]
+
+
 def optimize_whitening(smpls, initial_trafo, optimizer: ADAGrad, *, nbatches: int = 100, nepochs: int = 100,
-                       optstate=None, negll_history=None, group: bool = False, ctx: Optional[Context] = None):
+                       optstate=None, negll_history=None, group: bool = False, ctx: Optional[Context] = None,
+                       device_loop: bool = False):
     """Returns {'result', 'optimizer_state', 'negll_history'} like the
     reference's NamedTuple.  `smpls`: D x N samples (B200Matrix, or a host array
     that is uploaded once).  group=True: `smpls` holds this rank's column block
     of every global batch (see dist.shard_batches); all ranks apply the
-    identical update from all-reduced sums."""
+    identical update from all-reduced sums.  device_loop=True: the whole loop runs on the device
+    (enf_optimize_whitening: four kernel launches per step, no host round trip)."""
     if not isinstance(smpls, B200Matrix):
         X = np.asarray(smpls)
         dt = result_dtype(initial_trafo, X.dtype if X.dtype.kind == "f" else np.float64)
         smpls = B200Matrix.from_host(np.asarray(X, dtype=dt), ctx or default_context())
+    if device_loop:
+        result, state, hist = _optimize_whitening_device(smpls, copy.deepcopy(initial_trafo), optimizer, nbatches, nepochs,
+                                                         optstate, group)
+        return {"result": result, "optimizer_state": state, "negll_history": list(negll_history or []) + hist}
     trafo = copy.deepcopy(initial_trafo)
     state = copy.deepcopy(optstate) if optstate is not None else setup(optimizer, trafo)
     hist: List[float] = []

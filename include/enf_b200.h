@@ -156,6 +156,25 @@ int enf_group_destroy(enf_ctx* ctx);
 int enf_negll_grad_group(enf_chain* chain, const void* x_dev, int64_t N_local, int flags,
                          double* negll_host, void* grads_host);
 
+/* ---- optimize_whitening on the device -----------------------------
+ * The whole loop of src/optimize_whitening.jl:36-43 -- for epoch, for batch: (negll, grad) ->
+ * Optimisers.update -> push!(negll_hist) -- with parameters, optimizer state and loss history kept
+ * on the device: two kernel launches per step (captured per epoch into a CUDA graph), no host round trip.  Batches are the contiguous
+ * column ranges of src/optimize_whitening.jl:31-32 (batchsize = round(Int, N / nbatches)).
+ * Optimizer: ADAGrad with the Optimisers.jl 0.2 rule (eta, epsilon; state starts at epsilon);
+ * HouseholderTrafo columns are re-normalised after every update (src/householder_trafo.jl:134-146).
+ *   state_inout : packed like the parameters, float64; on entry the accumulated state to continue from
+ *                 (ignored when fresh_state != 0), on exit the final state.  May not be NULL.
+ *   params_out  : final parameters, packed, chain dtype.  The chain itself is left holding them.
+ *   history_out : one loss per step (nepochs * number of batches values; the Zygote-primal value when
+ *                 flags has ENF_NEGLL_ZYGOTE_PRIMAL, like negll_history of the reference).
+ *   use_group   : != 0: x holds this rank's columns of every batch; sums are all-reduced over the
+ *                 context's NCCL group each step (enf_group_init), every rank applies the same update.
+ * Blocking. */
+int enf_optimize_whitening(enf_chain* chain, const void* x_dev, int64_t N, int64_t nbatches, int64_t nepochs,
+                           double eta, double epsilon, int flags, int use_group, int fresh_state,
+                           double* state_inout, void* params_out, double* history_out, int64_t* n_steps_out);
+
 /* ---- timing on the context stream ---------------------------------------------
  * The library launches on its own stream, which events of other libraries do
  * not see.  ENF_N_EVENTS CUDA events per context: record one, later read the

@@ -179,6 +179,23 @@ function mvnormal_negll_trafograd(f::Trafo, x::B200Matrix{T}) where {T}
     T(out[]), unpack(f, g, size(x, 1), Ref(0))
 end
 
+# The whole fit loop on the device (enf_optimize_whitening, SURVEY §8f n1): same arguments and result as
+# optimize_whitening (src/optimize_whitening.jl:25-45) for an ADAGrad optimizer; two kernel launches per step.
+function optimize_whitening_device(smpls::B200Matrix{T}, initial_trafo::Trafo; eta = 0.1f0, epsilon = eps(Float32),
+                                   nbatches::Integer = 100, nepochs::Integer = 100) where {T}
+    ch, _ = chain(smpls.ctx, initial_trafo, size(smpls, 1), T)
+    np = Ref{Int64}(0)
+    check(ccall((:enf_chain_num_params, libenf), Cint, (Ptr{Cvoid}, Ref{Int64}), ch, np), smpls.ctx.handle)
+    nb = cld(size(smpls, 2), round(Int, size(smpls, 2) / nbatches))
+    state = Vector{Float64}(undef, np[]); params = Vector{T}(undef, np[]); hist = Vector{Float64}(undef, nb * nepochs)
+    nsteps = Ref{Int64}(0)
+    GC.@preserve state params hist check(ccall((:enf_optimize_whitening, libenf), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Float64, Float64, Cint, Cint, Cint, Ptr{Float64}, Ptr{T}, Ptr{Float64}, Ref{Int64}),
+        ch, smpls.ptr, size(smpls, 2), nbatches, nepochs, eta, epsilon, ENF_NEGLL_ZYGOTE_PRIMAL, 0, 1, state, params, hist, nsteps),
+        smpls.ctx.handle)
+    (params = params, optimizer_state = state, negll_history = hist[1:nsteps[]])   # packed like the C ABI; unpack() rebuilds the tree
+end
+
 # optimize_whitening itself (src/optimize_whitening.jl:25-45) needs one extra method so that
 # `flatview(batch)` of a device matrix is a column view; everything else is the reference's loop:
 #   smpls = B200Matrix(X); optimize_whitening(nestedview(smpls), initial_trafo, ADAGrad(); ...)

@@ -35,6 +35,17 @@ WORKER = textwrap.dedent("""
     for (k, x), (_, y) in zip(flat_grads(g, fe), flat_grads(g_ref, fo)):
         y = y.reshape(x.shape)
         assert np.max(np.abs(x - y) / (np.abs(y) + np.sqrt(np.mean(y * y)) + 1e-30)) < 1e-10, k
+    # the device-side fit loop over a sharded data set: every rank ends with the parameters of the single-process fit
+    from enf_b200.dist import shard_batches
+    Xs = np.random.default_rng(5).standard_normal((D, 4000)) * 1.3
+    ranges = E.batch_ranges(4000, 5)
+    mine = shard_batches(ranges, rank, world)
+    Xl = np.concatenate([Xs[:, a:b] for a, b in mine], axis=1)          # this rank's columns of every batch, in batch order
+    assert len({b - a for a, b in mine}) == 1                            # equal local batches -> local partition == global batches
+    r = E.optimize_whitening(E.B200Matrix.from_host(Xl, ctx), fe, E.ADAGrad(), nbatches=5, nepochs=2, group=True, device_loop=True)
+    r_ref = O.optimize_whitening(Xs, fo, O.ADAGrad(), nbatches=5, nepochs=2)
+    h, h_ref = np.array(r["negll_history"]), np.array(r_ref["negll_history"])
+    assert h.shape == h_ref.shape and np.max(np.abs(h - h_ref) / (np.abs(h_ref) + 1)) < 1e-9, (h, h_ref)
     dist.barrier(); dist.destroy_process_group()
     print("rank", rank, "ok")
 """) % (ROOT, ROOT)

@@ -326,3 +326,49 @@ def test_range_guard_redo_path(ctx, code):
         v = E.mvnormal_negll_trafo(fe, E.B200Matrix.from_host(X, ctx))
         v_ref = float(O.mvnormal_negll_trafo(fo, X.astype(np.float64)))
         assert np.isfinite(v) and abs(v - v_ref) <= 1e-5 * (abs(v_ref) + 1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_device_side_fit_loop_matches_host_loop(ctx, dtype):
+    """enf_optimize_whitening (the loop of src/optimize_whitening.jl:36-43 kept on the device: derive constants,
+    fused loss+gradient, ADAGrad update, Householder re-normalisation, history) against the host loop and the
+    oracle's restatement, including continuation from a returned optimizer state."""
+    import enf_b200 as E
+    rng = np.random.default_rng(3)
+    D, N = 4, 3011
+    X = (rng.standard_normal((D, N)) * np.array([[1.5], [0.4], [2.0], [1.0]]) + 0.3).astype(dtype)
+
+    def init(ns):
+        r = np.random.default_rng(9)
+        one = np.ones(D, dtype=dtype)
+        return ns.compose(ns.ScaleShiftTrafo(one.copy(), 0 * one),
+                          ns.HouseholderTrafo(r.standard_normal((D, 2)).astype(dtype)),
+                          ns.JohnsonTrafo(0 * one, 5 * one, 0 * one, 5 * one),
+                          ns.CenterContract(0.5 * one, one.copy(), 0 * one))
+
+    Xd = E.B200Matrix.from_host(X, ctx)
+    r_dev = E.optimize_whitening(Xd, init(E), E.ADAGrad(), nbatches=7, nepochs=3, device_loop=True)
+    r_host = E.optimize_whitening(Xd, init(E), E.ADAGrad(), nbatches=7, nepochs=3)
+    r_ref = O.optimize_whitening(X.astype(np.float64), init(O), O.ADAGrad(), nbatches=7, nepochs=3)
+    nb = len(E.batch_ranges(N, 7))
+    hd, hh, hr = (np.array(r["negll_history"]) for r in (r_dev, r_host, r_ref))
+    assert hd.shape == hh.shape == hr.shape == (3 * nb,)
+    tol = 2e-4 if dtype == np.float32 else 1e-9        # 3 epochs of updates amplify Float32 rounding
+    assert np.max(np.abs(hd - hr) / (np.abs(hr) + 1)) < tol
+    assert np.max(np.abs(hd - hh) / (np.abs(hh) + 1)) < tol
+    for a, b in zip(E.flatten(r_dev["result"]), O.flatten(r_ref["result"])):
+        for n in a.fields:
+            pa, pb = np.asarray(getattr(a, n), dtype=np.float64), np.asarray(getattr(b, n), dtype=np.float64)
+            assert np.max(np.abs(pa - pb)) < (5e-3 if dtype == np.float32 else 1e-8), n
+    V = E.flatten(r_dev["result"])[2].V
+    np.testing.assert_allclose((np.asarray(V, dtype=np.float64) ** 2).sum(0), 1.0, rtol=1e-5)
+    # continue from the returned state: same as one longer run
+    r_a = E.optimize_whitening(Xd, init(E), E.ADAGrad(), nbatches=7, nepochs=1, device_loop=True)
+    r_b = E.optimize_whitening(Xd, r_a["result"], E.ADAGrad(), nbatches=7, nepochs=2, device_loop=True,
+                               optstate=r_a["optimizer_state"], negll_history=r_a["negll_history"])
+    hb = np.array(r_b["negll_history"])
+    assert hb.shape == hd.shape and np.max(np.abs(hb - hd) / (np.abs(hd) + 1)) < tol
+    # the chain is left consistent with the final parameters
+    v = E.mvnormal_negll_trafo(r_dev["result"], Xd)
+    v_ref = float(O.mvnormal_negll_trafo(r_ref["result"], X.astype(np.float64)))
+    assert abs(v - v_ref) < (5e-3 if dtype == np.float32 else 1e-8) * (abs(v_ref) + 1)
