@@ -333,6 +333,23 @@ def main():
                                "samples_per_s_device_loop": (n2 // 100) * world / dev_s,
                                "note": "optimize_whitening steps; device loop = enf_optimize_whitening (2 launches/step, CUDA graph per epoch)"}
 
+        # C1: examples/nf_example_2d.jl chain (ScaleShift ∘ Householder([1,0.3]) ∘ CenterStretch), 1e5 Float64 samples:
+        # 4 MB working set, L2-resident and launch-latency-bound -> report microseconds per pass
+        f1 = E.compose(E.ScaleShiftTrafo(np.array([1.3, 0.4]), np.array([2.5, -1.2])), E.HouseholderTrafo(np.array([1.0, 0.3])),
+                       E.CenterStretch(np.array([4.0, 4.1]), np.array([2.0, 2.1]), np.array([3.0, 3.1])))
+        f1i = E.inverse(f1)
+        X1 = E.B200Matrix.randn(2, 100_000, np.float64, seed=SEED, ctx=ctx)
+        Y1, L1, Z1 = X1.empty_like(), E.B200Matrix(ctx, 1, 100_000, np.float64), X1.empty_like()
+        for _ in range(5):
+            E.with_logabsdet_jacobian(f1, X1, out=(Y1, L1)); E.with_logabsdet_jacobian(f1i, Y1, out=(Z1, L1))
+        ctx.record(6)
+        for _ in range(50):
+            E.with_logabsdet_jacobian(f1, X1, out=(Y1, L1)); E.with_logabsdet_jacobian(f1i, Y1, out=(Z1, L1))
+        ctx.record(7)
+        c1_us = max_over_ranks(ctx.elapsed_ms(6, 7) / 50) * 1e3
+        extras["c1_2d_f64"] = {"us_forward_plus_inverse_with_ladj": c1_us, "samples": 100_000,
+                               "samples_per_s": 2 * 100_000 * world / (c1_us * 1e-6), "note": "L2-resident, launch-latency-bound"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
