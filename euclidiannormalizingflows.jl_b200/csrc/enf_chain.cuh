@@ -24,7 +24,10 @@
 namespace enf {
 
 constexpr int MAX_OPS = 24;
-constexpr int NT = 256;  // threads per CTA of the chain kernels
+#ifndef ENF_NT
+#define ENF_NT 256
+#endif
+constexpr int NT = ENF_NT;  // threads per CTA of the chain kernels
 
 enum : int { OP_CS = 0, OP_CC = 1, OP_JO = 2, OP_JI = 3, OP_SS = 4, OP_HH = 5 };
 enum : int { MODE_VEC = 0, MODE_SCALAR = 1, MODE_PACK = 2, MODE_PACKU = 3 };  // PACKU: pack layout, unaligned pointers
@@ -88,6 +91,14 @@ __device__ __forceinline__ void st16_shared(float* p, const float (&o)[4]) {
 }
 __device__ __forceinline__ void st16_shared(double* p, const double (&o)[2]) {
     *reinterpret_cast<double2*>(p) = make_double2(o[0], o[1]);
+}
+// 16-byte load from a 32-bit shared-window address (keeps the ring reads LDS.128 with immediate offsets;
+// through a generic pointer the compiler emits 64-bit generic LD.E.128)
+__device__ __forceinline__ void lds16(uint32_t a, float (&o)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(a));
+}
+__device__ __forceinline__ void lds16(uint32_t a, double (&o)[2]) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(a));
 }
 // 16-byte read-modify-write of a per-thread accumulator vector in shared memory
 template <typename T, int VE>
@@ -224,6 +235,11 @@ __host__ __device__ constexpr int fwd_const_slot(int kind, int j) {
 }
 constexpr int MAX_FWD_CONSTS = 6;
 
+#ifndef ENF_HH_UNROLL
+#define ENF_HH_UNROLL 1
+#endif
+constexpr int HH_UNROLL = ENF_HH_UNROLL;   // unroll factor of the reflection loop of the interpretive kernel
+
 // one Householder reflection y = x - (v'.x) v' with the pre-scaled v' = v sqrt(2/v.v)
 // (src/householder_trafo.jl:4-11): partial dot products per lane, xor-shuffles inside the group
 template <class C>
@@ -263,10 +279,12 @@ __device__ __forceinline__ void hh_reflect(Tile<C>& t, const typename C::T (&vk)
     }
 }
 
-// elementwise trafo KIND on vector q of every sample of the tile; k[j] = j-th forward constant of the lane's rows
-template <class C, int KIND, bool LADJ, bool SAFE>
+// elementwise trafo KIND on vector q of every sample of the tile; k[j] = j-th forward constant of the lane's rows.
+// DEFER: Jacobian factors are multiplied into pn/pd (one pair per sample) instead of being logged per vector.
+template <class C, int KIND, bool LADJ, bool SAFE, bool DEFER>
 __device__ __forceinline__ void elem_fwd_q(Tile<C>& t, int q, const typename C::T (&k)[MAX_FWD_CONSTS][C::VE],
-                                           typename C::T (&l)[C::SPT][C::LN], bool& bad) {
+                                           typename C::T (&l)[C::SPT][C::LN], bool& bad, typename C::T (&pn)[C::SPT],
+                                           typename C::T (&pd)[C::SPT]) {
     using T = typename C::T;
     constexpr int VE = C::VE;
     constexpr int GR = C::PACKED ? C::PDD : VE;   // consecutive elements that belong to one sample
@@ -281,10 +299,11 @@ __device__ __forceinline__ void elem_fwd_q(Tile<C>& t, int q, const typename C::
                 T* v = &t.v[u][q][p * GR];
                 T& ll = l[u][C::slot(p * GR)];
                 const int o = p * GR;
-                if (KIND == OP_CS) cs_fwd_v<T, GR, LADJ, SAFE>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, k[4] + o, k[5] + o, ll, bad);
-                else if (KIND == OP_CC) cc_fwd_v<T, GR, LADJ, SAFE>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, ll, bad);
-                else if (KIND == OP_JO) jo_fwd_v<T, GR, LADJ, SAFE>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, ll, bad);
-                else ji_fwd_v<T, GR, LADJ, SAFE>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, ll, bad);
+                if (KIND == OP_CS)
+                    cs_fwd_v<T, GR, LADJ, SAFE, DEFER>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, k[4] + o, k[5] + o, ll, bad, &pn[u], &pd[u]);
+                else if (KIND == OP_CC) cc_fwd_v<T, GR, LADJ, SAFE, DEFER>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, ll, bad, &pn[u]);
+                else if (KIND == OP_JO) jo_fwd_v<T, GR, LADJ, SAFE, DEFER>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, ll, bad, &pn[u]);
+                else ji_fwd_v<T, GR, LADJ, SAFE, DEFER>(v, k[0] + o, k[1] + o, k[2] + o, k[3] + o, ll, bad, &pn[u]);
             }
         }
     }
@@ -294,12 +313,26 @@ template <class C, int KIND, bool LADJ, bool SAFE>
 __device__ __forceinline__ void elem_fwd_from(const typename C::T* cb, Tile<C>& t, typename C::T (&l)[C::SPT][C::LN],
                                               bool& bad) {
     using T = typename C::T;
+    using P = Prim<T>;
+    // one log per op and lane-sample (product over all CH vectors of the lane) on the fast path
+    constexpr bool DEFER = LADJ && !SAFE && !C::PACKED && C::CH > 1 && KIND != OP_SS;
+    T pn[C::SPT], pd[C::SPT];
+#pragma unroll
+    for (int u = 0; u < C::SPT; ++u) pn[u] = pd[u] = T(1);
 #pragma unroll
     for (int q = 0; q < C::CH; ++q) {
         T k[MAX_FWD_CONSTS][C::VE];
 #pragma unroll
         for (int j = 0; j < n_fwd_consts(KIND); ++j) ld16_shared(cb + fwd_const_slot(KIND, j) * C::DP + const_off<C>(q), k[j]);
-        elem_fwd_q<C, KIND, LADJ, SAFE>(t, q, k, l, bad);
+        elem_fwd_q<C, KIND, LADJ, SAFE, DEFER>(t, q, k, l, bad, pn, pd);
+    }
+    if (DEFER) {
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u) {
+            const T L = P::lg(KIND == OP_CS ? pn[u] * P::rcp(pd[u]) : pn[u]);
+            bad = bad || !(P::abs_(L) < P::LG_SAFE);
+            l[u][0] += (KIND == OP_JO && sizeof(T) == 8) ? T(-0.5) * L : L;
+        }
     }
 }
 
@@ -357,6 +390,7 @@ __device__ __forceinline__ void apply_op_fwd(const DevOp& op, const typename C::
         case OP_HH:
             // (the rank-K block update hh_block<> measured 2-5 % slower here than K sequential reflections: the
             // extra live dot products cost more registers than the overlapped reductions save; profiles/README.md)
+#pragma unroll HH_UNROLL
             for (int k = 0; k < op.K; ++k) {
                 T vk[C::CH][C::VE];
 #pragma unroll
@@ -463,7 +497,10 @@ __device__ __forceinline__ void store_ladj(typename C::T* ladj, int64_t tile, ty
 // tiles ahead of the math.  Every thread then picks its own 16-byte vectors out of
 // the staged tile with LDS.128, so no warp ever waits on HBM latency and no
 // registers are tied up by loads in flight.
-constexpr int RING = 3;
+#ifndef ENF_RING
+#define ENF_RING 2   // 2 x 32 KB stages per CTA (8 vectors per thread), 3 CTAs per SM
+#endif
+constexpr int RING = ENF_RING;
 #ifndef ENF_PRODUCER_WARP
 #define ENF_PRODUCER_WARP 0   // 1: dedicated TMA producer warp (+32 threads per CTA); 0: thread 0 also feeds the ring
 #endif
@@ -542,6 +579,54 @@ __device__ __forceinline__ void ring_read(const unsigned char* stage, int64_t N,
     }
 }
 
+// Fast paths for a tile whose samples all exist (every tile but the last): no per-sample predicates, one
+// base address per tile, immediate offsets per vector.
+template <class C>
+__device__ __forceinline__ void ring_read_full(uint32_t stage, int D, Tile<C>& t) {
+    using T = typename C::T;
+    const int g = threadIdx.x & (C::G - 1);
+    const int s_in = threadIdx.x >> C::LG;
+    const uint32_t base = stage + uint32_t((s_in * D + g * C::VE) * int(sizeof(T)));
+    const uint32_t ustride = uint32_t(C::SB * D * int(sizeof(T)));
+#pragma unroll
+    for (int u = 0; u < C::SPT; ++u) {
+#pragma unroll
+        for (int q = 0; q < C::CH; ++q) {
+            if ((q * C::G + g) * C::VE < D) lds16(base + u * ustride + uint32_t(q * C::G * C::VE * int(sizeof(T))), t.v[u][q]);
+            else {
+#pragma unroll
+                for (int e = 0; e < C::VE; ++e) t.v[u][q][e] = T(0);
+            }
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void store_tile_full(typename C::T* y, int D, int64_t tile, const Tile<C>& t) {
+    using T = typename C::T;
+    const int g = threadIdx.x & (C::G - 1);
+    T* yb = y + tile_item<C>(tile, 0) * D + g * C::VE;
+    const int ustride = C::SB * D;
+#pragma unroll
+    for (int u = 0; u < C::SPT; ++u) {
+#pragma unroll
+        for (int q = 0; q < C::CH; ++q)
+            if ((q * C::G + g) * C::VE < D) st16_stream(yb + u * ustride + q * C::G * C::VE, t.v[u][q]);
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void store_ladj_full(typename C::T* ladj, int64_t tile, typename C::T (&l)[C::SPT][C::LN],
+                                                typename C::T ladj_const) {
+    using T = typename C::T;
+    T* lb = ladj + tile_item<C>(tile, 0);
+#pragma unroll
+    for (int u = 0; u < C::SPT; ++u) {
+        const T tot = group_sum<C>(l[u][0]);
+        if ((threadIdx.x & (C::G - 1)) == 0) __stcs(lb + u * C::SB, Prim<T>::fma_(tot, Prim<T>::LGU, ladj_const));
+    }
+}
+
 // ------------------------------------------------------------------ forward (+ ladj) kernels
 // Grid-stride loop over tiles shared by the interpretive and the static kernel;
 // `apply(t, l)` runs the chain on one register tile.  `ring_smem` is 128-byte
@@ -552,6 +637,7 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
     using T = typename C::T;
     const int64_t nt = num_tiles<C>(N);
     unsigned char* stage0 = ring_smem;
+    const uint32_t stage0_u32 = smem_u32(ring_smem);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring_smem + RING * Ring<C>::STAGE_BYTES);   // TMA landed
     uint64_t* empty = full + RING;                                                            // all warps have read
     if (Ring<C>::ON) {
@@ -597,6 +683,8 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
         Tile<C> t;
         int nv[C::SPT];
         T l[C::SPT][C::LN];
+        // MODE_VEC: every tile but the last is complete -> predicate-free loads and stores
+        const bool full_tile = Ring<C>::ON && (tile + 1) * Ring<C>::TILE_SAMPLES <= N;
         if (Ring<C>::ON) {
             const int slot = k % RING;
             const uint32_t parity = uint32_t(k / RING) & 1u;
@@ -613,7 +701,13 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
             }
 #endif
             while (!mbar_try_wait(&full[slot], parity)) {}
-            ring_read<C>(stage0 + size_t(slot) * Ring<C>::STAGE_BYTES, N, D, tile, t, nv);
+            if (full_tile) {
+                ring_read_full<C>(stage0_u32 + uint32_t(slot) * uint32_t(Ring<C>::STAGE_BYTES), D, t);
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u) nv[u] = 1;
+            } else {
+                ring_read<C>(stage0 + size_t(slot) * Ring<C>::STAGE_BYTES, N, D, tile, t, nv);
+            }
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);
         } else {
@@ -635,8 +729,13 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
                 for (int p = 0; p < C::LN; ++p) l[u][p] = T(0);
             apply(std::true_type{}, t, l, bad);
         }
-        store_tile<C>(y, D, tile, t, nv);
-        if (LADJ) store_ladj<C>(ladj, tile, l, nv, ladj_const);
+        if (full_tile) {
+            store_tile_full<C>(y, D, tile, t);
+            if (LADJ) store_ladj_full<C>(ladj, tile, l, ladj_const);
+        } else {
+            store_tile<C>(y, D, tile, t, nv);
+            if (LADJ) store_ladj<C>(ladj, tile, l, nv, ladj_const);
+        }
     }
 }
 

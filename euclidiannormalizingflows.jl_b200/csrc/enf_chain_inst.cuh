@@ -8,7 +8,7 @@ namespace enf {
 namespace {
 
 #ifndef ENF_FWD_VECS
-#define ENF_FWD_VECS 4   // 16-byte vectors per thread per tile in the forward kernels
+#define ENF_FWD_VECS 8   // 16-byte vectors per thread per tile in the forward kernels
 #endif
 
 template <typename T, int LG, int CH, int MODE, int PD>

@@ -128,6 +128,16 @@ __device__ __forceinline__ T log_of_ratio(const T (&n)[N], const T (&d)[N], bool
     return L;
 }
 
+// product of the N values (deferred logs: the caller multiplies the Jacobian factors of ALL vectors a lane
+// owns of one sample and takes a single log per op, see elem_fwd_from)
+template <typename T, int N>
+__device__ __forceinline__ T product_of(const T (&p)[N]) {
+    T prod = p[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) prod *= p[i];
+    return prod;
+}
+
 // ---------------------------------------------------------------- forward
 // Each *_fwd_v transforms GR consecutive elements that belong to ONE sample and
 // adds their ladj contribution, in lg units, to `l` (row constants such as
@@ -143,9 +153,10 @@ __device__ __forceinline__ T log_of_ratio(const T (&n)[N], const T (&d)[N], bool
 // the reference's quadratic, divided through by e^{b|x|} so nothing overflows), u = y - c.
 // -ladj = log S(u), S = sigma(b(u-a)) + sigma(-b(u+a)) = [P + (2/A) w g] / [P + ((1+A^2)/A) w g], P = g^2 + w^2
 // (numerator and denominator scaled by g^2 A, which cancels in the ratio: no division by g is needed).
-template <typename T, int GR, bool LADJ, bool SAFE>
+// DEFER: do not take the log here; multiply the factors into pn (and pd) instead.
+template <typename T, int GR, bool LADJ, bool SAFE, bool DEFER = false>
 __device__ __forceinline__ void cs_fwd_v(T* v, const T* nb2, const T* Ah, const T* ib2, const T* c, const T* k1,
-                                         const T* k2, T& l, bool& bad) {
+                                         const T* k2, T& l, bool& bad, T* pn = nullptr, T* pd = nullptr) {
     using P = Prim<T>;
     T nn[GR], nd[GR];
 #pragma unroll
@@ -163,12 +174,20 @@ __device__ __forceinline__ void cs_fwd_v(T* v, const T* nb2, const T* Ah, const 
             nn[e] = P::fma_(k2[e], wg, p2);
         }
     }
-    if (LADJ) l += log_of_ratio<T, GR, SAFE>(nn, nd, bad);                   // -log S
+    if (LADJ) {
+        if (DEFER) {
+            *pn *= product_of<T, GR>(nn);
+            *pd *= product_of<T, GR>(nd);
+        } else {
+            l += log_of_ratio<T, GR, SAFE>(nn, nd, bad);                      // -log S
+        }
+    }
 }
 
 // CenterContract: src/center_stretch.jl:11-15 (value), :17-22,63-67 (ladj).
-template <typename T, int GR, bool LADJ, bool SAFE>
-__device__ __forceinline__ void cc_fwd_v(T* v, const T* nb2, const T* A, const T* ib2, const T* c, T& l, bool& bad) {
+template <typename T, int GR, bool LADJ, bool SAFE, bool DEFER = false>
+__device__ __forceinline__ void cc_fwd_v(T* v, const T* nb2, const T* A, const T* ib2, const T* c, T& l, bool& bad,
+                                         T* pn = nullptr) {
     using P = Prim<T>;
     T n3[GR];
     T ls = T(0);
@@ -186,13 +205,20 @@ __device__ __forceinline__ void cc_fwd_v(T* v, const T* nb2, const T* A, const T
             ls -= L1 + L2;
         }
     }
-    if (LADJ) l += ls + log_of_product<T, GR, SAFE>(n3, bad);                // log S
+    if (LADJ) {
+        if (DEFER) {
+            l += ls;
+            *pn *= product_of<T, GR>(n3);
+        } else {
+            l += ls + log_of_product<T, GR, SAFE>(n3, bad);                   // log S
+        }
+    }
 }
 
 // JohnsonTrafo: src/johnson_trafo.jl:29-32 (value), :39-42,49-52,76-80 (ladj).
-template <typename T, int GR, bool LADJ, bool SAFE>
+template <typename T, int GR, bool LADJ, bool SAFE, bool DEFER = false>
 __device__ __forceinline__ void jo_fwd_v(T* v, const T* il, const T* c0, const T* gamma, const T* delta2, T& l,
-                                         bool& bad) {
+                                         bool& bad, T* pn = nullptr) {
     using P = Prim<T>;
     T f[GR];
 #pragma unroll
@@ -205,14 +231,19 @@ __device__ __forceinline__ void jo_fwd_v(T* v, const T* il, const T* c0, const T
     }
     if (LADJ) {
         // -log(1+z^2)/2 :  lg(prod r) for f32 (r = rsqrt(s) is already there), -lg(prod s)/2 for f64
-        const T L = log_of_product<T, GR, SAFE>(f, bad);
-        l += sizeof(T) == 4 ? L : T(-0.5) * L;
+        if (DEFER) {
+            *pn *= product_of<T, GR>(f);
+        } else {
+            const T L = log_of_product<T, GR, SAFE>(f, bad);
+            l += sizeof(T) == 4 ? L : T(-0.5) * L;
+        }
     }
 }
 
 // JohnsonTrafoInv: src/johnson_trafo.jl:34-37 (value), :101-105 (ladj = -johnsontrafo_ladj(y)).
-template <typename T, int GR, bool LADJ, bool SAFE>
-__device__ __forceinline__ void ji_fwd_v(T* v, const T* k0, const T* k1, const T* lam, const T* xi, T& l, bool& bad) {
+template <typename T, int GR, bool LADJ, bool SAFE, bool DEFER = false>
+__device__ __forceinline__ void ji_fwd_v(T* v, const T* k0, const T* k1, const T* lam, const T* xi, T& l, bool& bad,
+                                         T* pn = nullptr) {
     using P = Prim<T>;
     T chs[GR];
 #pragma unroll
@@ -223,7 +254,10 @@ __device__ __forceinline__ void ji_fwd_v(T* v, const T* k0, const T* k1, const T
         v[e] = P::fma_(lam[e], sh, xi[e]);
         chs[e] = ch;
     }
-    if (LADJ) l += log_of_product<T, GR, SAFE>(chs, bad);                    // log sqrt(1 + sinh^2)
+    if (LADJ) {
+        if (DEFER) *pn *= product_of<T, GR>(chs);
+        else l += log_of_product<T, GR, SAFE>(chs, bad);                     // log sqrt(1 + sinh^2)
+    }
 }
 
 // ---------------------------------------------------------------- backward
