@@ -159,6 +159,9 @@ struct enf_chain {
     // Householder/ScaleShift-only chains at large D: folded affine map for the tensor-core kernel (enf_affine.cu)
     bool affine = false;
     float* d_affine = nullptr;  // Wh | Wl | bias
+    // ... and their loss/gradient from the batch's second moments (enf_moments.cu): the raw sums are
+    // [[S, m], [m^T, N]] ((D+1)^2 doubles) instead of per-op sums
+    bool moments = false;
 };
 
 namespace {
@@ -317,8 +320,109 @@ int pick_mode(const enf_chain* ch, const void* x, const void* y) {
     return (al && ch->D % VE == 0) ? MODE_VEC : MODE_SCALAR;
 }
 
+// Householder/ScaleShift-only chains: second moments [[S, m], [m^T, N]] -> (negll, grads), O(K D^2) in float64.
+// With x^ = [x; 1], every intermediate of the chain is x_i = B_i x^ (B_i: D x (D+1)), the loss cotangent of
+// the output is y/N, and for every op  sum_j g_ij x_(i-1)j^T = Z_i B_(i-1)^T  with  Z_n = B_n S^/N,
+// Z_(i-1) = A_i^T Z_i.  The reverse sweep recovers B_(i-1) from B_i exactly like the reference recovers a
+// reflection's input from its output (src/householder_trafo.jl:88-103) and applies the closed forms of
+// SURVEY §8a (pullback_v: :22-40) to the D x D moment matrix instead of to the D x N batch.
+void finish_moments(const enf_chain* ch, const double* sums, int64_t N, int flags, double* negll, std::vector<double>* grads) {
+    const int D = ch->D, D1 = D + 1;
+    const double Nd = double(N);
+    std::vector<double> B(size_t(D) * D1, 0.0), Z(size_t(D) * D1), w(D1), tB(D1), tZ(D1);
+    for (int k = 0; k < D; ++k) {
+        B[size_t(k) * D1 + k] = 1.0;
+        for (int c = 0; c < D1; ++c) Z[size_t(k) * D1 + c] = sums[size_t(k) * D1 + c] / Nd;
+    }
+    for (int c = 0; c < D1; ++c) w[c] = sums[size_t(D) * D1 + c] / Nd;
+    // t = v^T M, then M -= s v t^T   (M: D x D1 row-major)
+    auto reflect = [&](std::vector<double>& M, const double* v, double s, std::vector<double>& t) {
+        std::fill(t.begin(), t.end(), 0.0);
+        for (int k = 0; k < D; ++k) {
+            const double vk = v[k];
+            const double* row = M.data() + size_t(k) * D1;
+            for (int c = 0; c < D1; ++c) t[c] += vk * row[c];
+        }
+        for (int k = 0; k < D; ++k) {
+            const double f = s * v[k];
+            double* row = M.data() + size_t(k) * D1;
+            for (int c = 0; c < D1; ++c) row[c] -= f * t[c];
+        }
+    };
+    auto norm2 = [&](const double* v) { double n = 0.0; for (int k = 0; k < D; ++k) n += v[k] * v[k]; return n; };
+    // forward: B_n and Z_n = B_n S^/N (the chain applied to the columns of S^/N; w carries the homogeneous weight)
+    for (size_t o = 0; o < ch->ops.size(); ++o) {
+        const HostOp& op = ch->ops[o];
+        const double* p = ch->params.data() + op.poff;
+        if (op.kind == OP_SS) {
+            for (int k = 0; k < D; ++k) {
+                const double a = p[k], b = p[D + k];
+                double* rb = B.data() + size_t(k) * D1;
+                double* rz = Z.data() + size_t(k) * D1;
+                for (int c = 0; c < D1; ++c) { rb[c] *= a; rz[c] = a * rz[c] + b * w[c]; }
+                rb[D] += b;
+            }
+        } else {
+            for (int r = 0; r < op.K; ++r) {
+                const double* v = p + size_t(r) * D;
+                const double s = 2.0 / norm2(v);
+                reflect(B, v, s, tB);
+                reflect(Z, v, s, tZ);
+            }
+        }
+    }
+    double sum_y = 0.0;   // sum_j |y_j|^2 / 2 = N/2 <Z_n, B_n>
+    for (size_t i = 0; i < B.size(); ++i) sum_y += Z[i] * B[i];
+    sum_y *= 0.5 * Nd;
+    const double lconst = ch->ladj_const_other + ((flags & ENF_NEGLL_ZYGOTE_PRIMAL) ? 0.0 : ch->ladj_const_ss);
+    if (negll) *negll = (sum_y + 0.5 * LOG2PI * Nd * D - Nd * lconst) / Nd;
+    if (!grads) return;
+    grads->assign(ch->n_params, 0.0);
+    for (size_t oo = ch->ops.size(); oo-- > 0;) {
+        const HostOp& op = ch->ops[oo];
+        const double* p = ch->params.data() + op.poff;
+        double* g = grads->data() + op.poff;
+        if (op.kind == OP_SS) {
+            for (int k = 0; k < D; ++k) {
+                const double a = p[k], b = p[D + k], ia = 1.0 / a;
+                double* rb = B.data() + size_t(k) * D1;
+                double* rz = Z.data() + size_t(k) * D1;
+                g[D + k] = rz[D];
+                rb[D] -= b;
+                double acc = 0.0;
+                for (int c = 0; c < D1; ++c) { rb[c] *= ia; acc += rz[c] * rb[c]; rz[c] *= a; }
+                g[k] = acc - ia;
+            }
+        } else {
+            for (int r = op.K; r-- > 0;) {
+                const double* v = p + size_t(r) * D;
+                const double n = norm2(v), s = 2.0 / n;
+                reflect(B, v, s, tB);                       // B: output -> input of this reflection; v^T B_in = -tB
+                std::fill(tZ.begin(), tZ.end(), 0.0);
+                for (int k = 0; k < D; ++k) {
+                    const double vk = v[k];
+                    const double* rz = Z.data() + size_t(k) * D1;
+                    for (int c = 0; c < D1; ++c) tZ[c] += vk * rz[c];
+                }
+                double vcv = 0.0;
+                for (int c = 0; c < D1; ++c) vcv -= tZ[c] * tB[c];
+                for (int k = 0; k < D; ++k) {
+                    const double* rb = B.data() + size_t(k) * D1;
+                    double* rz = Z.data() + size_t(k) * D1;
+                    double cv = 0.0, ctv = 0.0;
+                    for (int c = 0; c < D1; ++c) { cv -= rz[c] * tB[c]; ctv += rb[c] * tZ[c]; }
+                    g[size_t(r) * D + k] = -s * (cv + ctv) + (4.0 / (n * n)) * vcv * v[k];
+                    const double f = s * v[k];
+                    for (int c = 0; c < D1; ++c) rz[c] -= f * tZ[c];   // Z: output -> input cotangent moments
+                }
+            }
+        }
+    }
+}
+
 // raw device sums -> (negll, grads).  Transcribes tests/device_model.py *_finish.
 void finish(const enf_chain* ch, const double* sums, int64_t N, int flags, double* negll, std::vector<double>* grads) {
+    if (ch->moments) return finish_moments(ch, sums, N, flags, negll, grads);
     const int D = ch->D, Dp = ch->desc.Dp;
     const bool packed = ch->plan.packed;
     const double Nd = double(N);
@@ -407,6 +511,13 @@ void export_grads(const enf_chain* ch, const std::vector<double>& g, void* out) 
 int run_partial(enf_chain* ch, const void* x, int64_t N, bool grad) {
     enf_ctx* ctx = ch->ctx;
     if (N < 0) return fail(ctx, ENF_ERR_INVALID, "N must be >= 0");
+    if (ch->moments) {
+        if (N > 0 && !aligned16(x))
+            return fail(ctx, ENF_ERR_INVALID, "loss/gradient of Householder/ScaleShift chains at D=%d needs a 16-byte aligned sample matrix", ch->D);
+        CU(ctx, launch_moments(ch->D, x, N, ch->d_partials, ch->d_sums, ctx->sm_count, ctx->stream));
+        ctx->launches += 2;
+        return ENF_OK;
+    }
     KernelSet ks;
     const int mode = pick_mode(ch, x, nullptr);
     if (!select_kernels(ch->dtype, ch->plan, mode, ks))
@@ -646,6 +757,9 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
     d.n_scalars = soff;
     d.n_save = save;
     ch->n_raw = d.n_rowslots * d.Dp + d.n_scalars + 2;
+    ch->affine = affine_supported(dtype, D, d);
+    ch->moments = ch->affine && moments_supported(dtype, D) && getenv("ENF_NO_MOMENTS") == nullptr;
+    if (ch->moments) ch->n_raw = (D + 1) * (D + 1);
     if (fwd_smem_bytes(dtype, d) > 200 * 1024) {
         delete ch;
         return fail(ctx, ENF_ERR_INVALID, "chain constants (%zu bytes) exceed the shared-memory budget", fwd_smem_bytes(dtype, d));
@@ -663,14 +777,14 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
     cudaError_t e;
     if ((e = cudaMalloc(&ch->d_consts, cbytes)) != cudaSuccess ||
         (e = cudaMallocHost(&ch->h_consts, cbytes)) != cudaSuccess ||
-        (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_partials), size_t(ch->max_blocks) * ch->n_raw * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_partials),
+                        ch->moments ? moments_partial_bytes(D, ctx->sm_count) : size_t(ch->max_blocks) * ch->n_raw * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_sums), size_t(ch->n_raw + 1) * sizeof(double))) != cudaSuccess ||
         (e = cudaMallocHost(reinterpret_cast<void**>(&ch->h_sums), size_t(ch->n_raw + 1) * sizeof(double))) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ch->consts_copied, cudaEventDisableTiming)) != cudaSuccess) {
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
     }
-    ch->affine = affine_supported(dtype, D, d);
     if (ch->affine && (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_affine), (2 * size_t(D) * D + D) * sizeof(float))) != cudaSuccess) {
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
@@ -935,6 +1049,10 @@ extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, i
     if (!x || !state_inout || !params_out || !history_out) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
     if (N < 1 || nbatches < 1 || nepochs < 0) return fail(ctx, ENF_ERR_INVALID, "bad N / nbatches / nepochs");
     if (use_group && !ctx->comm) return fail(ctx, ENF_ERR_INVALID, "enf_group_init has not been called on this context");
+    if (ch->moments)
+        return fail(ctx, ENF_ERR_INVALID,
+                    "the device-side fit loop does not cover second-moment (Householder/ScaleShift, D=%d) chains yet: "
+                    "drive enf_negll_grad from the host loop", ch->D);
     CU(ctx, cudaSetDevice(ctx->device));
     // src/optimize_whitening.jl:31: batchsize = round(Int, length(smpls) / nbatches)  (ties to even)
     const int64_t batchsize = int64_t(std::nearbyint(double(N) / double(nbatches)));

@@ -29,102 +29,15 @@
 
 #include "enf_chain.cuh"
 #include "enf_launch.h"
+#include "enf_tc.cuh"
 
 namespace enf {
 namespace {
 
 constexpr int AF_TILE_M = 128;     // samples per tile (UMMA M)
-constexpr int AF_KC = 32;          // K chunk: 32 floats = one 128-byte swizzle atom
 constexpr int AF_THREADS = 256;    // warp 0 TMA, warp 1 MMA, warps 2-3 split, warps 4-7 epilogue
 constexpr int AF_SPLITTERS = 64;
 constexpr int AF_EPI_WARPS = 4;
-
-// ---- PTX wrappers -------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 bytes,
-// 8-row groups 1024 bytes apart; the tile base must be 1024-byte aligned.
-__device__ __forceinline__ uint64_t make_desc_sw128(const void* smem_ptr) {
-    const uint32_t addr = smem_u32(smem_ptr);
-    uint64_t d = 0;
-    d |= uint64_t((addr & 0x3FFFF) >> 4);            // start address, 16-byte units     [0,14)
-    d |= uint64_t(1) << 16;                           // leading byte offset (unused here) [16,30)
-    d |= uint64_t(1024 >> 4) << 32;                   // stride byte offset = 8 rows       [32,46)
-    d |= uint64_t(1) << 46;                           // descriptor version (sm_100)       [46,48)
-    d |= uint64_t(2) << 61;                           // layout type SWIZZLE_128B          [61,64)
-    return d;
-}
-
-// K-major descriptor for rows of KC floats: KC = 32 -> SWIZZLE_128B, KC = 16 -> SWIZZLE_64B (8-row groups KC*32 bytes apart)
-template <int KC>
-__device__ __forceinline__ uint64_t make_desc_kmajor(const void* smem_ptr) {
-    static_assert(KC == 32 || KC == 16, "one swizzle atom per row");
-    const uint32_t addr = smem_u32(smem_ptr);
-    uint64_t d = 0;
-    d |= uint64_t((addr & 0x3FFFF) >> 4);
-    d |= uint64_t(1) << 16;
-    d |= uint64_t((8 * KC * 4) >> 4) << 32;
-    d |= uint64_t(1) << 46;
-    d |= uint64_t(KC == 32 ? 2 : 4) << 61;
-    return d;
-}
-
-// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-    return (1u << 4)                 // c_format = F32
-           | (2u << 7)               // a_format = TF32
-           | (2u << 10)              // b_format = TF32
-           | (uint32_t(N >> 3) << 17)
-           | (uint32_t(M >> 4) << 24);
-}
-
-// round-to-nearest tf32 (10-bit mantissa) / remainder
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 template <int ND, int KC>
 struct AffineSmem {
@@ -520,37 +433,6 @@ affine2_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     __syncthreads();
     cluster_sync_all();          // nobody leaves while the peer may still signal or read this CTA
     if (warp == 1) tmem_dealloc2(tmem_base, S::TMEM_COLS);
-}
-
-// ---- host side ------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// row-major [rows][cols] float32 matrix, box [box_rows][32 cols], 128-byte swizzle
-bool make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols = AF_KC) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return false;
-    const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {cols * sizeof(float)};
-    const cuuint32_t box[2] = {box_cols, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace

@@ -61,6 +61,11 @@ cudaError_t launch_reduce(const double* partials, int n_blocks, int n_raw, doubl
 
 // affine chains on the tensor cores (enf_affine.cu)
 bool affine_supported(int dtype, int D, const ChainDesc& d);
+// second moments [[S, m], [m^T, N]] of a D x N batch on tensor cores (enf_moments.cu); d_part: scratch of
+// moments_partial_bytes() bytes, d_sums: (D+1)^2 + 1 doubles
+bool moments_supported(int dtype, int D);
+size_t moments_partial_bytes(int D, int sm_count);
+cudaError_t launch_moments(int D, const void* x, int64_t N, void* d_part, double* d_sums, int sm_count, cudaStream_t st);
 cudaError_t launch_affine(int D, const float* d_w, const void* x, void* y, void* ladj, int64_t N, double ladj_const,
                           int sm_count, cudaStream_t st);
 

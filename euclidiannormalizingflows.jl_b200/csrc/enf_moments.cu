@@ -1,0 +1,301 @@
+// loss and parameter gradients of Householder/ScaleShift-only chains at large D
+// (mvnormal_negll_trafograd, src/optimize_whitening.jl:7-22, through src/householder_trafo.jl:88-124).
+//
+// Such a chain is an affine map y = W x + c, and the whitening loss is quadratic in y, so the loss and every
+// parameter gradient depend on the batch only through its second moments
+//        S = sum_j x_j x_j^T (D x D),   m = sum_j x_j,   N.
+// The reverse sweep of the reference (one pass over the D x N batch per reflection) collapses into ONE
+// reduction over the samples, which is a GEMM with the SAMPLES as the contraction dimension - this is the
+// tensor-core reduction over N.  A D x N column-major sample matrix is exactly the MN-major operand of that
+// GEMM (row index contiguous), for A and for B, so TMA feeds tcgen05.mma without a transpose.  The chain
+// rule from (S, m, N) to (negll, dV, da, db) costs O(K D^2), independent of N (enf_abi.cu: finish_moments).
+//
+// Float32 accuracy on TF32 tensor cores: with x = xh + xl (xh = tf32(x)) the kernel accumulates
+//        P = Xh Xh^T + Xh (2 Xl)^T            (2 MMAs per k-step instead of 3)
+// and the reduction kernel symmetrises, (P + P^T)/2 = Xh Xh^T + Xh Xl^T + Xl Xh^T = X X^T - Xl Xl^T (2^-22).
+// The tensor core truncates when it adds into the f32 accumulator, so TMEM is drained into a per-CTA f32
+// partial in global memory (L2-resident) every MO_FLUSH_STAGES stages; partials are summed in f64.
+//
+// Warp roles (320 threads, one CTA per SM): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
+// warps 2-5 hi/lo split + row sums (m), warps 6-9 TMEM drain.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+#include "enf_chain.cuh"
+#include "enf_launch.h"
+#include "enf_tc.cuh"
+
+namespace enf {
+namespace {
+
+constexpr int MO_KC = 32;             // samples per pipeline stage = 4 UMMA k-steps (K = 8 for tf32)
+constexpr int MO_THREADS = 320;
+constexpr int MO_SPLIT_THREADS = 128;
+constexpr int MO_EPI_WARPS = 4;
+#ifndef ENF_MO_FLUSH_STAGES
+#define ENF_MO_FLUSH_STAGES 16        // 512 samples (128 truncating accumulations) per TMEM drain
+#endif
+constexpr int MO_FLUSH_STAGES = ENF_MO_FLUSH_STAGES;
+
+template <int ND>
+struct MomSmem {
+    static constexpr int NG = ND / 32;                  // groups of 32 rows (one 128-byte swizzle row per sample)
+    static constexpr int GROUP_BYTES = MO_KC * 128;     // [sample][32 rows] : swizzle atoms of 4 samples
+    static constexpr int X_BYTES = NG * GROUP_BYTES;    // 32 KB at ND = 256
+    static constexpr int STAGE_BYTES = 2 * X_BYTES;     // xh | 2 xl
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 6 ? 6 : (192 * 1024) / STAGE_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int NH = ND / 128;                 // 128-row halves of the accumulator (UMMA M = 128)
+    static constexpr uint32_t TMEM_COLS = uint32_t(NH) * ND;   // 512 at ND = 256, 128 at ND = 128
+    static constexpr int REPS = MO_SPLIT_THREADS / (ND / 4);   // splitter threads that share the same 4 rows
+};
+
+// MN-major shared-memory matrix descriptor for tf32 (cute::UMMA::SmemDescriptor).  32-bit MN-major operands only
+// exist in the SWIZZLE_128B_BASE32B layout (layout type 1; canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in
+// 16-byte units, address swizzle Swizzle<2,5,2>): 32 consecutive rows (128 bytes) per sample, 4 samples per
+// 512-byte atom whose 32-byte chunks are XOR-ed with (sample & 3) - what TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; the next 32 rows are `lbo_bytes` further, the next 4 samples 512 bytes.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((addr & 0x3FFFF) >> 4);
+    d |= uint64_t(lbo_bytes >> 4) << 16;
+    d |= uint64_t(512 >> 4) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(1) << 61;
+    return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// part_s: [gridDim.x][ND*ND] float (row-major P of this CTA), part_m: [gridDim.x][REPS][ND] double
+template <int ND>
+__global__ void __launch_bounds__(MO_THREADS, 1)
+moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ part_s, double* __restrict__ part_m,
+               int64_t N, int stages_per_cta) {
+    using S = MomSmem<ND>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // TMA landed              (1 + tx)
+    uint64_t* split = full + S::STAGES;                                // xh / 2xl written        (4 warps)
+    uint64_t* empty = split + S::STAGES;                               // MMAs of the stage done  (tcgen05.commit)
+    uint64_t* acc_full = empty + S::STAGES;                            // flush period accumulated
+    uint64_t* acc_empty = acc_full + 1;                                // TMEM drained            (4 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total_stages = (N + MO_KC - 1) / MO_KC;
+    const int64_t st0 = int64_t(blockIdx.x) * stages_per_cta;
+    int64_t st1 = st0 + stages_per_cta;
+    if (st1 > total_stages) st1 = total_stages;
+    const int my_stages = int(st1 - st0);                              // >= 1 by construction of the grid
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], MO_SPLIT_THREADS / 32);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, MO_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: one box of 32 rows x 32 samples per row group =====
+        if (lane == 0) {
+            for (int it = 0; it < my_stages; ++it) {
+                const int s = it % S::STAGES;
+                if (it >= S::STAGES) mbar_wait(&empty[s], uint32_t(it / S::STAGES - 1) & 1u);
+                unsigned char* st = smem + size_t(s) * S::STAGE_BYTES;
+                mbar_expect_tx(&full[s], S::X_BYTES);
+                const int col = int((st0 + it) * MO_KC);               // samples beyond N are zero-filled by TMA
+#pragma unroll
+                for (int g = 0; g < S::NG; ++g) tma_load_2d(st + g * S::GROUP_BYTES, &map_x, g * 32, col, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: P[h] += Xh[h] Xh^T + Xh[h] (2 Xl)^T, both operands MN-major =====
+        constexpr uint32_t idesc = make_idesc_tf32(128, ND) | (1u << 15) | (1u << 16);
+        int nflush = 0;
+        for (int it = 0; it < my_stages; ++it) {
+            const int s = it % S::STAGES;
+            const uint32_t ph = uint32_t(it / S::STAGES) & 1u;
+            const int fs = it % MO_FLUSH_STAGES;
+            if (fs == 0 && it > 0) {
+                mbar_wait(acc_empty, uint32_t(nflush - 1) & 1u);     // the previous period has been drained
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            mbar_wait(&full[s], ph);
+            mbar_wait(&split[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool last = (fs == MO_FLUSH_STAGES - 1) || (it == my_stages - 1);
+            if (lane == 0) {
+                const uint32_t xh = smem_u32(smem + size_t(s) * S::STAGE_BYTES), xl = xh + S::X_BYTES;
+#pragma unroll
+                for (int j = 0; j < MO_KC / 8; ++j) {
+                    const uint64_t dbh = make_desc_mn_sw128(xh + j * 1024, S::GROUP_BYTES);
+                    const uint64_t dbl = make_desc_mn_sw128(xl + j * 1024, S::GROUP_BYTES);
+#pragma unroll
+                    for (int h = 0; h < S::NH; ++h) {
+                        const uint64_t da = make_desc_mn_sw128(xh + h * 4 * S::GROUP_BYTES + j * 1024, S::GROUP_BYTES);
+                        umma_tf32(tmem_base + uint32_t(h * ND), da, dbh, idesc, (fs | j) != 0);
+                        umma_tf32(tmem_base + uint32_t(h * ND), da, dbl, idesc, 1);
+                    }
+                }
+                umma_commit(&empty[s]);
+                if (last) umma_commit(acc_full);
+            }
+            if (last) ++nflush;
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // ===== splitters: x -> xh (in place), 2 (x - xh) (second buffer); row sums for m =====
+        constexpr int PAIRS = ND / 4;                                  // (row group, 16-byte chunk) pairs
+        const int t = threadIdx.x - 64;
+        const int pair = t % PAIRS, rep = t / PAIRS;
+        const int g = pair >> 3, c = pair & 7;
+        double macc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int it = 0; it < my_stages; ++it) {
+            const int s = it % S::STAGES;
+            mbar_wait(&full[s], uint32_t(it / S::STAGES) & 1u);
+            unsigned char* gb = smem + size_t(s) * S::STAGE_BYTES + g * S::GROUP_BYTES;
+            float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll 4
+            for (int k = rep; k < MO_KC; k += S::REPS) {
+                // 128B swizzle with 32-byte atoms: 32-byte chunk c/2 of sample row k lives at chunk ((c/2) ^ (k & 3))
+                float4* px = reinterpret_cast<float4*>(gb + k * 128 + ((((c >> 1) ^ (k & 3)) << 5) | ((c & 1) << 4)));
+                const float4 v = *px;
+                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                *px = h;
+                *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(px) + S::X_BYTES) =
+                    make_float4(tf32_hi(2.f * (v.x - h.x)), tf32_hi(2.f * (v.y - h.y)), tf32_hi(2.f * (v.z - h.z)),
+                                tf32_hi(2.f * (v.w - h.w)));
+                r0 += v.x; r1 += v.y; r2 += v.z; r3 += v.w;
+            }
+            macc[0] += double(r0); macc[1] += double(r1); macc[2] += double(r2); macc[3] += double(r3);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split[s]);
+        }
+        double* pm = part_m + (size_t(blockIdx.x) * S::REPS + rep) * ND + g * 32 + c * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pm[e] = macc[e];
+    } else {
+        // ===== drain: TMEM -> registers -> this CTA's partial P in global memory (store, then red.add) =====
+        const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int nfl = (my_stages + MO_FLUSH_STAGES - 1) / MO_FLUSH_STAGES;
+        float* mine = part_s + size_t(blockIdx.x) * ND * ND;
+        for (int f = 0; f < nfl; ++f) {
+            mbar_wait(acc_full, uint32_t(f) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int h = 0; h < S::NH; ++h) {
+                float* rowp = mine + size_t(h * 128 + quarter * 32 + lane) * ND;
+#pragma unroll 1
+                for (int cc = 0; cc < ND / 32; ++cc) {
+                    float v[32];
+                    tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(h * ND + cc * 32), v);
+                    float* dst = rowp + cc * 32;
+                    if (f == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+// sums[(D+1)*(D+1)] = [[S, m], [m^T, N]] (row-major, float64, fixed summation order), sums[(D+1)^2] = N
+__global__ void moments_reduce_kernel(const float* __restrict__ part_s, const double* __restrict__ part_m, int n_cta,
+                                      int reps, int D, int64_t N, double* __restrict__ sums) {
+    const int D1 = D + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) {
+        sums[size_t(D) * D1 + D] = double(N);
+        sums[size_t(D1) * D1] = double(N);
+    }
+    if (idx < D * D) {
+        const int a = idx / D, b = idx % D;
+        double s = 0.0;
+        for (int c = 0; c < n_cta; ++c) {
+            const float* p = part_s + size_t(c) * D * D;
+            s += 0.5 * (double(p[size_t(a) * D + b]) + double(p[size_t(b) * D + a]));
+        }
+        sums[size_t(a) * D1 + b] = s;
+    } else if (idx < D * D + D) {
+        const int a = idx - D * D;
+        double s = 0.0;
+        for (int c = 0; c < n_cta * reps; ++c) s += part_m[size_t(c) * D + a];
+        sums[size_t(a) * D1 + D] = s;
+        sums[size_t(D) * D1 + a] = s;
+    }
+}
+
+}  // namespace
+
+bool moments_supported(int dtype, int D) { return dtype == 0 && (D == 128 || D == 256); }
+
+size_t moments_partial_bytes(int D, int sm_count) {
+    return size_t(sm_count) * D * D * sizeof(float) + size_t(sm_count) * 4 * D * sizeof(double);
+}
+
+// d_part: moments_partial_bytes(D, sm_count) bytes of scratch; d_sums: (D+1)^2 + 1 doubles
+cudaError_t launch_moments(int D, const void* x, int64_t N, void* d_part, double* d_sums, int sm_count, cudaStream_t st) {
+    float* part_s = static_cast<float*>(d_part);
+    double* part_m = reinterpret_cast<double*>(part_s + size_t(sm_count) * D * D);
+    const int64_t total = (N + MO_KC - 1) / MO_KC;
+    int n_cta = 0, reps = MO_SPLIT_THREADS / (D / 4);
+    if (N > 0) {
+        CUtensorMap mx;
+        if (!make_map(&mx, x, uint64_t(N), uint64_t(D), MO_KC, 32, true)) return cudaErrorInvalidValue;
+        const int per = int((total + sm_count - 1) / sm_count);
+        n_cta = int((total + per - 1) / per);
+        cudaError_t e = cudaSuccess;
+#define ENF_MOMENTS_LAUNCH(ND)                                                                                     \
+    {                                                                                                              \
+        const int smem = MomSmem<ND>::TOTAL;                                                                       \
+        static bool set[64] = {};                                                                                  \
+        int dev = 0;                                                                                               \
+        cudaGetDevice(&dev);                                                                                       \
+        if (!set[dev & 63]) {                                                                                      \
+            e = cudaFuncSetAttribute(moments_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);       \
+            if (e != cudaSuccess) return e;                                                                        \
+            set[dev & 63] = true;                                                                                  \
+        }                                                                                                          \
+        moments_kernel<ND><<<n_cta, MO_THREADS, smem, st>>>(mx, part_s, part_m, N, per);                           \
+    }
+        if (D == 256) ENF_MOMENTS_LAUNCH(256)
+        else if (D == 128) ENF_MOMENTS_LAUNCH(128)
+        else return cudaErrorInvalidValue;
+#undef ENF_MOMENTS_LAUNCH
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    const int n = D * D + D;
+    moments_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part_s, part_m, n_cta, reps, D, N, d_sums);
+    return cudaGetLastError();
+}
+
+}  // namespace enf

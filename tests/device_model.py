@@ -227,3 +227,64 @@ def hh_finish(raw, N, V):
     # acc1 was accumulated with z = reflection *input*; p' uses the input too.
     dV = -np.sqrt(2.0 / n)[None, :] * acc1 + (2.0 / n * acc2)[None, :] * Vm
     return {"V": dV[:, 0] if vec else dV}
+
+
+# ---------------------------------------------------------------- affine chains from second moments
+def affine_moments_finish(ops, Shat, N, zygote_primal=False):
+    """Loss and gradients of a Householder/ScaleShift-only chain from the batch's second moments
+    Shat = [[S, m], [m^T, N]] (csrc/enf_abi.cu: finish_moments transcribes this).
+
+    ops: list of ("ss", a, b) / ("hh", V) in application order (V: D x K, columns applied in order).
+    Returns (negll, [grad dicts in application order])."""
+    D = Shat.shape[0] - 1
+    B = np.hstack([np.eye(D), np.zeros((D, 1))])          # x_i = B_i [x; 1]
+    Z = Shat[:D, :] / N                                    # becomes B_n Shat / N
+    w = Shat[D, :] / N                                     # homogeneous weight of every column of Shat / N
+    lconst = 0.0
+
+    def reflect(M, v, s):
+        t = v @ M
+        return M - s * np.outer(v, t), t
+
+    for op in ops:
+        if op[0] == "ss":
+            a, b = op[1], op[2]
+            B = a[:, None] * B
+            B[:, D] += b
+            Z = a[:, None] * Z + np.outer(b, w)
+            lconst += np.log(np.abs(a)).sum()
+        else:
+            V = op[1]
+            for r in range(V.shape[1]):
+                v = V[:, r]
+                s = 2.0 / (v @ v)
+                B, _ = reflect(B, v, s)
+                Z, _ = reflect(Z, v, s)
+    sum_y = 0.5 * N * (Z * B).sum()
+    negll = (sum_y + 0.5 * np.log(2 * np.pi) * N * D - N * (0.0 if zygote_primal else lconst)) / N
+    grads = [None] * len(ops)
+    for i in reversed(range(len(ops))):
+        op = ops[i]
+        if op[0] == "ss":
+            a, b = op[1], op[2]
+            gb = Z[:, D].copy()
+            B = B.copy()
+            B[:, D] -= b
+            B = B / a[:, None]
+            ga = (Z * B).sum(1) - 1.0 / a
+            Z = a[:, None] * Z
+            grads[i] = {"a": ga, "b": gb}
+        else:
+            V = op[1]
+            gV = np.zeros_like(V)
+            for r in reversed(range(V.shape[1])):
+                v = V[:, r]
+                n = v @ v
+                s = 2.0 / n
+                B, tB = reflect(B, v, s)          # B is now the reflection's input; v^T B_in = -tB
+                tZ = v @ Z
+                u = -tB
+                gV[:, r] = -s * (Z @ u + B @ tZ) + (4.0 / n ** 2) * (tZ @ u) * v
+                Z = Z - s * np.outer(v, tZ)
+            grads[i] = {"V": gV}
+    return negll, grads

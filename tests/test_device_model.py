@@ -86,3 +86,28 @@ def test_center_stretch_form_has_no_overflow():
     y, _ = M.cs_fwd(x.astype(np.float32), a.astype(np.float32), b.astype(np.float32), c.astype(np.float32))
     assert np.isfinite(y).all()
     np.testing.assert_allclose(y[0, 0], float(O.center_stretch(20.0, 7.0, 2.0, 4.0)), rtol=1e-6)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_affine_chain_gradient_from_second_moments(seed):
+    """Householder/ScaleShift chains: (negll, grads) from [[S, m], [m^T, N]] == oracle autograd on the batch."""
+    rng = np.random.default_rng(seed)
+    D, N = 6, 57
+    V1, V2 = rng.normal(size=(D, 3)), rng.normal(size=(D, 2))
+    a1, b1 = rng.uniform(0.5, 2, D) * rng.choice([-1.0, 1.0], D), rng.uniform(-1, 1, D)
+    a2, b2 = rng.uniform(0.5, 2, D), rng.uniform(-1, 1, D)
+    x = rng.normal(size=(D, N)) * 1.7 + rng.uniform(-1, 1, (D, 1))
+    f = O.compose(O.ScaleShiftTrafo(a2, b2), O.HouseholderTrafo(V2), O.ScaleShiftTrafo(a1, b1), O.HouseholderTrafo(V1))
+    ops = [("hh", V1), ("ss", a1, b1), ("hh", V2), ("ss", a2, b2)]
+    xh = np.vstack([x, np.ones((1, N))])
+    Shat = xh @ xh.T
+    for zp in (False, True):
+        ref_l, ref_g = O.mvnormal_negll_trafograd(f, x, zygote_primal=zp)
+        got_l, got_g = M.affine_moments_finish(ops, Shat, N, zygote_primal=zp)
+        assert abs(got_l - ref_l) < 1e-12 * max(1.0, abs(ref_l))
+        ref_flat = _flat(ref_g, f)
+        assert len(ref_flat) == len(got_g)
+        for r, g in zip(ref_flat, got_g):
+            assert set(r) == set(g)
+            for k in r:
+                np.testing.assert_allclose(np.asarray(g[k]).reshape(np.asarray(r[k]).shape), r[k], rtol=1e-10, atol=1e-12)

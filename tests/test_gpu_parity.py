@@ -372,3 +372,33 @@ def test_device_side_fit_loop_matches_host_loop(ctx, dtype):
     v = E.mvnormal_negll_trafo(r_dev["result"], Xd)
     v_ref = float(O.mvnormal_negll_trafo(r_ref["result"], X.astype(np.float64)))
     assert abs(v - v_ref) < (5e-3 if dtype == np.float32 else 1e-8) * (abs(v_ref) + 1)
+
+
+# ---- loss / gradients of Householder+ScaleShift chains at large D from tensor-core second moments
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec,D,N", [
+    (["hh8", "ss"], 128, 3001),          # ragged: not a multiple of the 32-sample stage
+    (["ss", "hh12", "ss"], 128, 40000),  # several TMEM flush periods per CTA
+    (["hh64", "ss"], 256, 4100),         # C4 chain
+    (["hh16", "ss"], 256, 70001),    # several flush periods per CTA at D = 256
+])
+def test_affine_chain_grad_from_tensor_core_moments(ctx, spec, D, N):
+    import enf_b200 as E
+    fo, fe = both(spec, D, 31, np.float32)
+    X = _data(D, N, 32, np.float32, spread=1.1) + np.linspace(-0.5, 0.5, D, dtype=np.float32)[:, None]
+    Xd = E.B200Matrix.from_host(X, ctx)
+    v_ref = float(O.mvnormal_negll_trafo(fo, X.astype(np.float64)))
+    v = E.mvnormal_negll_trafo(fe, Xd)
+    assert abs(v - v_ref) <= 1e-5 * (abs(v_ref) + 1), (v, v_ref)
+    for zp in (True, False):
+        vz_ref, g_ref = O.mvnormal_negll_trafograd(fo, X.astype(np.float64), zygote_primal=zp)
+        vz, g = E.mvnormal_negll_trafograd(fe, Xd, zygote_primal=zp)
+        assert abs(vz - vz_ref) <= 1e-5 * (abs(vz_ref) + 1), (zp, vz, vz_ref)
+        got, ref = flat_grads(g, fe), flat_grads(g_ref, fo)
+        assert [k for k, _ in got] == [k for k, _ in ref]
+        for (k, a), (_, b) in zip(got, ref):
+            assert_close(a, b.reshape(a.shape), np.float32, f"grad {k} {spec}", factor=4.0)
+    # same call twice -> identical result (fixed-order reductions)
+    _, g2 = E.mvnormal_negll_trafograd(fe, Xd)
+    for (_, a), (_, b) in zip(flat_grads(g, fe), flat_grads(g2, fe)):
+        assert np.array_equal(a, b)
