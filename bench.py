@@ -315,6 +315,35 @@ def main():
                                         "tf32_tflops_issued": flops * n4 / (c4_ms * 1e-3) / 1e12,
                                         "path": "tcgen05.mma kind::tf32, 3xTF32 split, y = W x + c folded on the host"}
 
+        # C4 gradient: loss + dV, da, db of the same chain from tensor-core second moments
+        # (enf_moments.cu: S = X X^T with the samples as the contraction dimension) + cluster chain-rule kernel
+        import ctypes as C
+        ch4 = E.get_chain(f4, 256, np.float32, ctx)
+        part = lambda Xm: E._lib.check(ctx._lib.enf_negll_grad_partial(ch4.handle, C.c_void_p(Xm.ptr), Xm.N, None, None), ctx.handle)
+        for _ in range(2):
+            part(X4)
+        ctx.record(8)
+        for _ in range(3):
+            part(X4)
+        ctx.record(9)
+        m4_ms = max_over_ranks(ctx.elapsed_ms(8, 9) / 3)
+        nb4 = 100_000                                   # C4: N = 1e7, nbatches = 100
+        for i in range(3):
+            E.mvnormal_negll_trafograd(f4, X4.cols(i * nb4, (i + 1) * nb4), group=world > 1)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(8):
+            E.mvnormal_negll_trafograd(f4, X4.cols(i * nb4, (i + 1) * nb4), group=world > 1)
+        g4_s = max_over_ranks(time.perf_counter() - t0) / 8
+        extras["grad_c4_d256_k64_moments"] = {
+            "moments_samples_per_s": n4 * world / (m4_ms * 1e-3), "moments_ms_per_pass": m4_ms, "samples_per_gpu": n4,
+            "hbm_frac": 256 * 4 * n4 / (m4_ms * 1e-3) / 1e9 / hbm_peak,
+            "tf32_tflops_issued": 2 * 2 * 256 * 256 * n4 / (m4_ms * 1e-3) / 1e12,
+            "ms_per_step_batch_1e5": g4_s * 1e3, "step_samples_per_s": nb4 * world / g4_s,
+            "path": "tcgen05.mma kind::tf32, MN-major operands (TMA 128B/32B-atom swizzle), P = Xh Xh^T + Xh (2Xl)^T, "
+                    "float64 chain rule in one 8-CTA cluster; step = set_params + moments + chain rule + D2H"
+                    + (" + ncclAllReduce of the moments" if world > 1 else "")}
+
         # C2: 1-D JohnsonTrafo + ScaleShiftTrafo whitening fit, 1e7 samples, nbatches=100 (examples/nf_example_1d.jl shape):
         # time per gradient step of the host loop (one fused kernel + host optimizer per step) and of the device loop
         n2 = min(10_000_000, Nl * D_MAIN)

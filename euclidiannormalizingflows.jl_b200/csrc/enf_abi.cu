@@ -162,6 +162,10 @@ struct enf_chain {
     // ... and their loss/gradient from the batch's second moments (enf_moments.cu): the raw sums are
     // [[S, m], [m^T, N]] ((D+1)^2 doubles) instead of per-op sums
     bool moments = false;
+    bool affine_dirty = false;
+    double* d_params64 = nullptr;  // packed float64 parameters (device-side chain rule)
+    double* d_mom_out = nullptr;   // [negll, grads...]
+    double* h_mom_out = nullptr;   // pinned
 };
 
 namespace {
@@ -291,7 +295,29 @@ int derive_constants(enf_chain* ch) {
                             cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaEventRecord(ch->consts_copied, ctx->stream));
     ch->consts_pending = true;
-    if (ch->affine) {
+    ch->affine_dirty = ch->affine;   // W = fold of the chain is rebuilt lazily, by the first forward call that needs it
+    if (ch->moments) {
+        // float64 parameters for the device-side chain rule (pageable source is staged before the call returns)
+        CU(ctx, cudaMemcpyAsync(ch->d_params64, ch->params.data(), ch->n_params * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<double> norms;   // v.v of every reflection, in application order
+        for (const HostOp& op : ch->ops)
+            if (op.kind == OP_HH)
+                for (int k = 0; k < op.K; ++k) {
+                    const double* v = ch->params.data() + op.poff + size_t(k) * D;
+                    double n = 0.0;
+                    for (int i = 0; i < D; ++i) n += v[i] * v[i];
+                    norms.push_back(n);
+                }
+        CU(ctx, cudaMemcpyAsync(ch->d_params64 + ch->n_params, norms.data(), norms.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return ENF_OK;
+}
+
+// Householder/ScaleShift chains on the tensor-core forward path: fold the chain into y = W x + c (host, float64)
+int ensure_affine(enf_chain* ch) {
+    enf_ctx* ctx = ch->ctx;
+    const int D = ch->D;
+    if (ch->affine && ch->affine_dirty) {
         std::vector<int> kinds, Ks;
         std::vector<const double*> pp;
         for (const HostOp& op : ch->ops) {
@@ -307,11 +333,19 @@ int derive_constants(enf_chain* ch) {
         CU(ctx, cudaMemcpyAsync(ch->d_affine + n2, wl.data(), n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaMemcpyAsync(ch->d_affine + 2 * n2, bias.data(), size_t(D) * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
+        ch->affine_dirty = false;
     }
     return ENF_OK;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ENF_MOMENTS_HOST=1: map second moments to gradients with the float64 host code (finish_moments) instead of the
+// cluster kernel - the cross-check of the two implementations
+bool host_chain_rule() {
+    static const bool v = getenv("ENF_MOMENTS_HOST") != nullptr;
+    return v;
+}
 
 int pick_mode(const enf_chain* ch, const void* x, const void* y) {
     const int VE = ch->dtype == ENF_F32 ? 4 : 2;
@@ -532,6 +566,29 @@ int run_partial(enf_chain* ch, const void* x, int64_t N, bool grad) {
                         ctx->sm_count, ctx->stream));
     CU(ctx, launch_reduce(ch->d_partials, blocks, ch->n_raw, ch->d_sums, false, ctx->stream));
     ctx->launches += 2;
+    return ENF_OK;
+}
+
+// second-moment chains: d_sums (possibly all-reduced) -> negll, grads through the device-side chain rule
+int moments_finish_device(enf_chain* ch, int flags, double* negll, void* grads_host) {
+    enf_ctx* ctx = ch->ctx;
+    std::vector<int> kinds, Ks, poffs;
+    for (const HostOp& op : ch->ops) {
+        kinds.push_back(op.kind);
+        Ks.push_back(op.K);
+        poffs.push_back(int(op.poff));
+    }
+    const double lconst = ch->ladj_const_other + ((flags & ENF_NEGLL_ZYGOTE_PRIMAL) ? 0.0 : ch->ladj_const_ss);
+    CU(ctx, launch_moments_chainrule(ch->D, int(kinds.size()), kinds.data(), Ks.data(), poffs.data(), ch->d_params64, ch->d_params64 + ch->n_params, ch->d_sums,
+                                     lconst, ch->d_mom_out, ctx->stream));
+    ctx->launches += 1;
+    CU(ctx, cudaMemcpyAsync(ch->h_mom_out, ch->d_mom_out, (ch->n_params + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (negll) *negll = ch->h_mom_out[0];
+    if (grads_host) {
+        std::vector<double> g(ch->h_mom_out + 1, ch->h_mom_out + 1 + ch->n_params);
+        export_grads(ch, g, grads_host);
+    }
     return ENF_OK;
 }
 
@@ -785,6 +842,13 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
     }
+    if (ch->moments &&
+        ((e = cudaMalloc(reinterpret_cast<void**>(&ch->d_params64), (ch->n_params + size_t(d.n_scalars) + 1) * sizeof(double))) != cudaSuccess ||
+         (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_mom_out), (ch->n_params + 1) * sizeof(double))) != cudaSuccess ||
+         (e = cudaMallocHost(reinterpret_cast<void**>(&ch->h_mom_out), (ch->n_params + 1) * sizeof(double))) != cudaSuccess)) {
+        enf_chain_destroy(ch);
+        return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
+    }
     if (ch->affine && (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_affine), (2 * size_t(D) * D + D) * sizeof(float))) != cudaSuccess) {
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
@@ -821,6 +885,9 @@ extern "C" int enf_chain_destroy(enf_chain* ch) {
     if (ch->d_sums) cudaFree(ch->d_sums);
     if (ch->h_sums) cudaFreeHost(ch->h_sums);
     if (ch->d_affine) cudaFree(ch->d_affine);
+    if (ch->d_params64) cudaFree(ch->d_params64);
+    if (ch->d_mom_out) cudaFree(ch->d_mom_out);
+    if (ch->h_mom_out) cudaFreeHost(ch->h_mom_out);
     if (ch->consts_copied) cudaEventDestroy(ch->consts_copied);
     delete ch;
     return ENF_OK;
@@ -852,6 +919,8 @@ static int forward_impl(enf_chain* ch, const void* x, int64_t N, void* y, void* 
     static const bool no_affine = getenv("ENF_NO_AFFINE") != nullptr;
     if (ch->affine && mode == MODE_VEC && !no_affine) {
         // Householder / ScaleShift stack at large D: one tcgen05 GEMM per tile (enf_affine.cu)
+        int rca = ensure_affine(ch);
+        if (rca != ENF_OK) return rca;
         CU(ctx, launch_affine(ch->D, ch->d_affine, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));
         ctx->launches += 1;
         return ENF_OK;
@@ -944,6 +1013,7 @@ extern "C" int enf_negll(enf_chain* ch, const void* x, int64_t N, double* negll)
     CU(ctx, cudaSetDevice(ctx->device));
     int rc = run_partial(ch, x, N, false);
     if (rc != ENF_OK) return rc;
+    if (ch->moments && !host_chain_rule()) return moments_finish_device(ch, 0, negll, nullptr);
     CU(ctx, cudaMemcpyAsync(ch->h_sums, ch->d_sums, size_t(ch->n_raw) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     finish(ch, ch->h_sums, N, 0, negll, nullptr);
@@ -978,6 +1048,7 @@ extern "C" int enf_negll_grad(enf_chain* ch, const void* x, int64_t N, int flags
     if (N < 1) return fail(ctx, ENF_ERR_INVALID, "N must be >= 1");
     int rc = enf_negll_grad_partial(ch, x, N, nullptr, nullptr);
     if (rc != ENF_OK) return rc;
+    if (ch->moments && !host_chain_rule()) return moments_finish_device(ch, flags, negll, grads_host);
     CU(ctx, cudaMemcpyAsync(ch->h_sums, ch->d_sums, size_t(ch->n_raw) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return enf_negll_grad_finish(ch, ch->h_sums, N, flags, negll, grads_host);
@@ -1034,6 +1105,7 @@ extern "C" int enf_negll_grad_group(enf_chain* ch, const void* x, int64_t N_loca
     ch->h_sums[ch->n_raw] = double(N_local);
     CU(ctx, cudaMemcpyAsync(ch->d_sums + ch->n_raw, ch->h_sums + ch->n_raw, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     NC(ctx, g_nccl.AllReduce(ch->d_sums, ch->d_sums, size_t(ch->n_raw + 1), ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    if (ch->moments && !host_chain_rule()) return moments_finish_device(ch, flags, negll, grads_host);   // N_global = S^[D][D]
     CU(ctx, cudaMemcpyAsync(ch->h_sums, ch->d_sums, size_t(ch->n_raw + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     const int64_t N_global = int64_t(std::llround(ch->h_sums[ch->n_raw]));

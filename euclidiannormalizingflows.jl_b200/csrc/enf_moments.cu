@@ -21,6 +21,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "enf_chain.cuh"
@@ -253,6 +255,191 @@ __global__ void moments_reduce_kernel(const float* __restrict__ part_s, const do
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Chain rule on the device: second moments -> (negll, gradients), float64.
+//
+// One thread-block CLUSTER of MC_CL CTAs; CTA r keeps rows [r RB, (r+1) RB) of B (x_i = B_i [x; 1]) and of Z
+// (moments of the cotangent, Z_n = B_n S^/N) in shared memory.  A reflection needs the column sums v^T B and
+// v^T Z over ALL rows: every CTA publishes its partial sums in its own shared memory, one cluster barrier, and
+// every CTA adds the MC_CL partials it reads through distributed shared memory (fixed order: bitwise
+// reproducible).  Everything else is row-local.  Same algebra as enf_abi.cu: finish_moments and
+// tests/device_model.py: affine_moments_finish.
+constexpr int MC_CL = 8;           // CTAs per cluster
+constexpr double MO_LOG2PI = 1.8378770664093454835606594728112;
+constexpr int MC_THREADS = 256;
+
+struct MomOp { int kind, K, poff, noff; };   // noff: offset of this op's reflections in the v.v array
+struct MomChain { int n_ops, D; MomOp ops[MAX_OPS]; };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// out[0] = negll, out[1 .. 1+P) = gradients (packed like the parameters)
+__global__ void __cluster_dims__(MC_CL, 1, 1) __launch_bounds__(MC_THREADS, 1)
+moments_chainrule_kernel(const __grid_constant__ MomChain mc, const double* __restrict__ params,
+                         const double* __restrict__ norms, const double* __restrict__ sums, double lconst,
+                         double* __restrict__ out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = int(cluster.block_rank());
+    const int D = mc.D, D1 = D + 1, RB = D / MC_CL, r0 = rank * RB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = MC_THREADS / 32;
+    extern __shared__ double sm[];
+    double* Bs = sm;                              // [RB][D1]
+    double* Zs = Bs + size_t(RB) * D1;            // [RB][D1]
+    double* part = Zs + size_t(RB) * D1;          // [2 buffers][2 matrices][D1] partial column sums (read by peers)
+    double* tB = part + 4 * D1;                   // [D1] v^T B
+    double* tZ = tB + D1;                         // [D1] v^T Z
+    double* red = tZ + D1;                        // [NW + 1] block reduction scratch / this CTA's loss partial
+    const double Nd = sums[size_t(D) * D1 + D];
+
+    for (int i = tid; i < RB * D1; i += MC_THREADS) {
+        const int k = i / D1, c = i % D1;
+        Bs[i] = (c == r0 + k) ? 1.0 : 0.0;
+        Zs[i] = sums[size_t(r0 + k) * D1 + c] / Nd;
+    }
+    __syncthreads();
+
+    int nsync = 0;                                // reflections processed so far -> partial buffer parity
+    // column sums over all rows of the cluster: tB = v^T B, tZ = v^T Z
+    auto column_sums = [&](const double* v) {
+        double* mine = part + (nsync & 1) * 2 * D1;
+        for (int c = tid; c < D1; c += MC_THREADS) {
+            double sb = 0.0, sz = 0.0;
+            for (int k = 0; k < RB; ++k) {
+                const double vk = v[r0 + k];
+                sb += vk * Bs[k * D1 + c];
+                sz += vk * Zs[k * D1 + c];
+            }
+            mine[c] = sb;
+            mine[D1 + c] = sz;
+        }
+        cluster.sync();
+        for (int c = tid; c < D1; c += MC_THREADS) {
+            double sb = 0.0, sz = 0.0;
+            for (int r = 0; r < MC_CL; ++r) {
+                const double* peer = cluster.map_shared_rank(mine, r);
+                sb += peer[c];
+                sz += peer[D1 + c];
+            }
+            tB[c] = sb;
+            tZ[c] = sz;
+        }
+        ++nsync;
+        __syncthreads();
+    };
+
+    // ---- forward: B_n, Z_n
+    for (int o = 0; o < mc.n_ops; ++o) {
+        const MomOp op = mc.ops[o];
+        const double* p = params + op.poff;
+        if (op.kind == OP_SS) {
+            for (int i = tid; i < RB * D1; i += MC_THREADS) {
+                const int k = i / D1, c = i % D1;
+                const double a = p[r0 + k], b = p[D + r0 + k];
+                const double w = sums[size_t(D) * D1 + c] / Nd;
+                Bs[i] = a * Bs[i] + (c == D ? b : 0.0);
+                Zs[i] = a * Zs[i] + b * w;
+            }
+            __syncthreads();
+        } else {
+            for (int r = 0; r < op.K; ++r) {
+                const double* v = p + size_t(r) * D;
+                const double s = 2.0 / norms[op.noff + r];      // v.v, float64, from the host
+                column_sums(v);
+                for (int i = tid; i < RB * D1; i += MC_THREADS) {
+                    const int k = i / D1, c = i % D1;
+                    const double f = s * v[r0 + k];
+                    Bs[i] -= f * tB[c];
+                    Zs[i] -= f * tZ[c];
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // ---- loss: sum_j |y_j|^2 / 2 = N/2 <Z_n, B_n>
+    {
+        double acc = 0.0;
+        for (int i = tid; i < RB * D1; i += MC_THREADS) acc += Zs[i] * Bs[i];
+        acc = warp_sum(acc);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < NW; ++w) t += red[w];
+            red[NW] = t;
+        }
+        cluster.sync();
+        if (rank == 0 && tid == 0) {
+            double t = 0.0;
+            for (int r = 0; r < MC_CL; ++r) t += cluster.map_shared_rank(red, r)[NW];
+            out[0] = 0.5 * t + 0.5 * MO_LOG2PI * D - lconst;
+        }
+    }
+    // ---- reverse sweep
+    double* g_all = out + 1;
+    for (int o = mc.n_ops - 1; o >= 0; --o) {
+        const MomOp op = mc.ops[o];
+        const double* p = params + op.poff;
+        double* g = g_all + op.poff;
+        if (op.kind == OP_SS) {
+            for (int k = warp; k < RB; k += NW) {                    // one warp per row
+                const double a = p[r0 + k], b = p[D + r0 + k], ia = 1.0 / a;
+                double* rb = Bs + k * D1;
+                double* rz = Zs + k * D1;
+                const double gb = rz[D];
+                __syncwarp();
+                double acc = 0.0;
+                for (int c = lane; c < D1; c += 32) {
+                    const double bin = (rb[c] - (c == D ? b : 0.0)) * ia;
+                    rb[c] = bin;
+                    acc += rz[c] * bin;
+                    rz[c] *= a;
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    g[r0 + k] = acc - ia;
+                    g[D + r0 + k] = gb;
+                }
+            }
+            __syncthreads();
+        } else {
+            for (int r = op.K - 1; r >= 0; --r) {
+                const double* v = p + size_t(r) * D;
+                const double n = norms[op.noff + r], s = 2.0 / n;
+                column_sums(v);                                       // of B_out and Z_out
+                double vcv = 0.0;                                     // v^T C v = -(v^T Z_out).(v^T B_out)
+                for (int c = lane; c < D1; c += 32) vcv -= tZ[c] * tB[c];
+                vcv = warp_sum(vcv);
+                for (int k = warp; k < RB; k += NW) {
+                    const double vk = v[r0 + k], f = s * vk;
+                    double* rb = Bs + k * D1;
+                    double* rz = Zs + k * D1;
+                    double cv = 0.0, ctv = 0.0;
+                    for (int c = lane; c < D1; c += 32) {
+                        const double bin = rb[c] - f * tB[c];         // B: output -> input of this reflection
+                        rb[c] = bin;
+                        const double z = rz[c];
+                        cv -= z * tB[c];                              // v^T B_in = -tB
+                        ctv += bin * tZ[c];
+                        rz[c] = z - f * tZ[c];
+                    }
+                    cv = warp_sum(cv);
+                    ctv = warp_sum(ctv);
+                    if (lane == 0) g[size_t(r) * D + r0 + k] = -s * (cv + ctv) + (4.0 / (n * n)) * vcv * vk;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    cluster.sync();   // nobody exits while a peer may still read its partial sums
+}
+
 }  // namespace
 
 bool moments_supported(int dtype, int D) { return dtype == 0 && (D == 128 || D == 256); }
@@ -295,6 +482,33 @@ cudaError_t launch_moments(int D, const void* x, int64_t N, void* d_part, double
     }
     const int n = D * D + D;
     moments_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part_s, part_m, n_cta, reps, D, N, d_sums);
+    return cudaGetLastError();
+}
+
+
+// sums -> out[0] = negll, out[1 .. 1+P) = gradients; kinds/Ks/poffs: the chain's ops in application order,
+// d_params: packed float64 parameters on the device, d_norms: v.v of every reflection in application order
+cudaError_t launch_moments_chainrule(int D, int n_ops, const int* kinds, const int* Ks, const int* poffs, const double* d_params,
+                                     const double* d_norms, const double* d_sums, double lconst, double* d_out, cudaStream_t st) {
+    MomChain mc;
+    mc.n_ops = n_ops;
+    mc.D = D;
+    int noff = 0;
+    for (int o = 0; o < n_ops; ++o) {
+        mc.ops[o] = MomOp{kinds[o], Ks[o], poffs[o], noff};
+        if (kinds[o] == OP_HH) noff += Ks[o];
+    }
+    const int D1 = D + 1, RB = D / MC_CL;
+    const size_t smem = (size_t(2) * RB * D1 + 6 * D1 + MC_THREADS / 32 + 1) * sizeof(double);
+    static size_t set[64] = {};   // largest dynamic shared-memory size enabled so far, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (set[dev & 63] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(moments_chainrule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        set[dev & 63] = smem;
+    }
+    moments_chainrule_kernel<<<MC_CL, MC_THREADS, smem, st>>>(mc, d_params, d_norms, d_sums, lconst, d_out);
     return cudaGetLastError();
 }
 

@@ -402,3 +402,30 @@ def test_affine_chain_grad_from_tensor_core_moments(ctx, spec, D, N):
     _, g2 = E.mvnormal_negll_trafograd(fe, Xd)
     for (_, a), (_, b) in zip(flat_grads(g, fe), flat_grads(g2, fe)):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_moments_chain_rule_device_kernel_matches_host_code(ctx):
+    """enf_negll_grad (cluster kernel) == enf_negll_grad_partial + enf_negll_grad_finish (float64 host code) on the same sums."""
+    import ctypes as C
+    import enf_b200 as E
+    from enf_b200 import _lib as L
+    D, N = 256, 5000
+    _, fe = both(["ss", "hh9", "ss", "hh3"], D, 41, np.float32)
+    Xd = E.B200Matrix.from_host(_data(D, N, 42, np.float32) + 0.3, ctx)
+    v_dev, g_dev = E.mvnormal_negll_trafograd(fe, Xd, zygote_primal=False)
+    ch = E.get_chain(fe, D, np.float32, ctx)
+    sums, n = C.c_void_p(), C.c_int64()
+    L.check(ctx._lib.enf_negll_grad_partial(ch.handle, C.c_void_p(Xd.ptr), N, C.byref(sums), C.byref(n)), ctx.handle)
+    assert n.value == (D + 1) ** 2
+    h = np.empty(n.value, dtype=np.float64)
+    L.check(ctx._lib.enf_d2h(ctx.handle, h.ctypes.data_as(C.c_void_p), sums, h.nbytes), ctx.handle)
+    v_host = C.c_double()
+    g_host = np.empty(ch.nparams, dtype=np.float32)
+    L.check(ctx._lib.enf_negll_grad_finish(ch.handle, h.ctypes.data_as(C.c_void_p), N, 0, C.byref(v_host),
+                                           g_host.ctypes.data_as(C.c_void_p)), ctx.handle)
+    assert abs(v_dev - v_host.value) <= 1e-12 * abs(v_host.value)
+    flat_dev = np.concatenate([a.ravel(order="F") for _, a in flat_grads(g_dev, fe)])
+    assert flat_dev.shape == g_host.shape
+    scale = np.abs(g_host).max()
+    assert np.abs(np.sort(flat_dev) - np.sort(g_host)).max() <= 1e-6 * scale   # same values (packing order aside)

@@ -44,6 +44,13 @@ ctx.record(1)
 ms = ctx.elapsed_ms(0, 1) / 5
 print(f"moments D={D} N={Nb}: {ms:.3f} ms  {Nb / ms * 1e-6:.3f}e9 samples/s  {Nb * D * 4 / ms * 1e-6:.1f} GB/s  "
       f"{2 * 2.0 * D * D * Nb / ms * 1e-9:.1f} TFLOP/s tf32 issued")
-t0 = time.perf_counter()
-l, g = E.mvnormal_negll_trafograd(f, Xb)
-print(f"full enf_negll_grad call (kernel + D2H + host chain rule): {(time.perf_counter() - t0) * 1e3:.2f} ms, negll {l:.6f}")
+for K in (16, 64):
+    fk = E.compose(E.ScaleShiftTrafo(np.full(D, 1.1, np.float32), np.full(D, 0.1, np.float32)),
+                   E.HouseholderTrafo(rng.normal(size=(D, K)).astype(np.float32)))
+    for nb in (100_000, Nb):
+        xb = Xb.cols(0, nb)
+        E.mvnormal_negll_trafograd(fk, xb)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            l, g = E.mvnormal_negll_trafograd(fk, xb)
+        print(f"enf_negll_grad D={D} K={K} batch={nb}: {(time.perf_counter() - t0) / 5 * 1e3:.3f} ms per call (set_params + moments + chain rule + D2H), negll {l:.6f}")
