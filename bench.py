@@ -153,10 +153,21 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": total,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------ our arm
+# The contract is ONE JSON line on stdout.  Native libraries (NCCL's version banner, ...) also write to fd 1, so
+# everything but the result line is sent to stderr: fd 1 is pointed at fd 2 and the line goes to the saved fd.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -411,7 +422,7 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -46,6 +46,19 @@ WORKER = textwrap.dedent("""
     r_ref = O.optimize_whitening(Xs, fo, O.ADAGrad(), nbatches=5, nepochs=2)
     h, h_ref = np.array(r["negll_history"]), np.array(r_ref["negll_history"])
     assert h.shape == h_ref.shape and np.max(np.abs(h - h_ref) / (np.abs(h_ref) + 1)) < 1e-9, (h, h_ref)
+    # second-moment chain (Householder + ScaleShift at D = 128): the all-reduced quantity is [[S, m], [m^T, N]]
+    D2, N2 = 128, 6001
+    fo2, fe2 = both(["hh8", "ss"], D2, 7, np.float32)
+    X2 = (np.random.default_rng(8).standard_normal((D2, N2)) * 1.2).astype(np.float32)
+    cut = (N2 // 2) // 4 * 4                                             # 16-byte aligned shard boundary (TMA)
+    lo = 0 if rank == 0 else cut
+    hi = N2 if rank == world - 1 else cut
+    v2, g2 = E.mvnormal_negll_trafograd(fe2, E.B200Matrix.from_host(X2[:, lo:hi], ctx), group=True)
+    v2_ref, g2_ref = O.mvnormal_negll_trafograd(fo2, X2.astype(np.float64))
+    assert abs(v2 - v2_ref) < 1e-5 * (abs(v2_ref) + 1), (v2, v2_ref)
+    for (k, x), (_, y) in zip(flat_grads(g2, fe2), flat_grads(g2_ref, fo2)):
+        y = y.reshape(x.shape)
+        assert np.max(np.abs(x - y) / (np.abs(y) + np.sqrt(np.mean(y * y)) + 1e-30)) < 4e-5, k
     dist.barrier(); dist.destroy_process_group()
     print("rank", rank, "ok")
 """) % (ROOT, ROOT)
