@@ -16,8 +16,8 @@
 // The tensor core truncates when it adds into the f32 accumulator, so TMEM is drained into a per-CTA f32
 // partial in global memory (L2-resident) every MO_FLUSH_STAGES stages; partials are summed in f64.
 //
-// Warp roles (320 threads, one CTA per SM): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
-// warps 2-5 hi/lo split + row sums (m), warps 6-9 TMEM drain.
+// Warp roles (448 threads, one CTA per SM): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
+// warps 2-5 hi/lo split + row sums (m), warps 6-13 TMEM drain.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -33,9 +33,9 @@ namespace enf {
 namespace {
 
 constexpr int MO_KC = 32;             // samples per pipeline stage = 4 UMMA k-steps (K = 8 for tf32)
-constexpr int MO_THREADS = 320;
+constexpr int MO_THREADS = 448;     // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-13 drain
 constexpr int MO_SPLIT_THREADS = 128;
-constexpr int MO_EPI_WARPS = 4;
+constexpr int MO_EPI_WARPS = 8;     // two warps per TMEM lane quarter, each drains half of the columns
 #ifndef ENF_MO_FLUSH_STAGES
 #define ENF_MO_FLUSH_STAGES 16        // 512 samples (128 truncating accumulations) per TMEM drain
 #endif
@@ -70,11 +70,11 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t addr, uint32_t l
     return d;
 }
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void red_add(float* p, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
-// part_s: [gridDim.x][ND*ND] float (row-major P of this CTA), part_m: [gridDim.x][REPS][ND] double
+// part_s: [gridDim.x][ND*ND] float (P^T of this CTA), part_m: [gridDim.x][REPS][ND] double
 template <int ND>
 __global__ void __launch_bounds__(MO_THREADS, 1)
 moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ part_s, double* __restrict__ part_m,
@@ -196,6 +196,8 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
     } else {
         // ===== drain: TMEM -> registers -> this CTA's partial P in global memory (store, then red.add) =====
         const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int chalf = (warp - 6) >> 2;                             // which half of the 32-column chunks
+        constexpr int NCC = ND / 32 / 2;                               // chunks per warp and accumulator half
         const int nfl = (my_stages + MO_FLUSH_STAGES - 1) / MO_FLUSH_STAGES;
         float* mine = part_s + size_t(blockIdx.x) * ND * ND;
         for (int f = 0; f < nfl; ++f) {
@@ -203,19 +205,20 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int h = 0; h < S::NH; ++h) {
-                float* rowp = mine + size_t(h * 128 + quarter * 32 + lane) * ND;
+                // the partial is stored TRANSPOSED (P^T[col][row]; the reduction symmetrises anyway): for one
+                // accumulator column the 32 lanes (rows) are contiguous, so every store / red.add is one 128-byte line
+                float* colp = mine + size_t(h * 128 + quarter * 32 + lane);
 #pragma unroll 1
-                for (int cc = 0; cc < ND / 32; ++cc) {
+                for (int cc = chalf * NCC; cc < (chalf + 1) * NCC; ++cc) {
                     float v[32];
                     tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(h * ND + cc * 32), v);
-                    float* dst = rowp + cc * 32;
+                    float* dst = colp + size_t(cc * 32) * ND;
                     if (f == 0) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int i = 0; i < 32; ++i) dst[size_t(i) * ND] = v[i];
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int i = 0; i < 32; ++i) red_add(dst + size_t(i) * ND, v[i]);
                     }
                 }
             }
