@@ -70,6 +70,10 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t addr, uint32_t l
     return d;
 }
 
+#ifndef ENF_MO_TRUNC
+#define ENF_MO_TRUNC 0   // 1: feed x itself as Xh (hardware truncation) and write only the remainder: faster at D=128, less accurate
+#endif
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ void red_add(float* p, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
@@ -178,8 +182,14 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
                 // 128B swizzle with 32-byte atoms: 32-byte chunk c/2 of sample row k lives at chunk ((c/2) ^ (k & 3))
                 float4* px = reinterpret_cast<float4*>(gb + k * 128 + ((((c >> 1) ^ (k & 3)) << 5) | ((c & 1) << 4)));
                 const float4 v = *px;
+#if ENF_MO_TRUNC
+                // the tensor core ignores the low 13 mantissa bits of a tf32 operand: x itself serves as Xh = trunc(x),
+                // only the remainder is written
+                const float4 h = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
+#else
                 const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                 *px = h;
+#endif
                 *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(px) + S::X_BYTES) =
                     make_float4(tf32_hi(2.f * (v.x - h.x)), tf32_hi(2.f * (v.y - h.y)), tf32_hi(2.f * (v.z - h.z)),
                                 tf32_hi(2.f * (v.w - h.w)));
