@@ -127,7 +127,10 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
                 mbar_expect_tx(&full[s], S::X_BYTES);
                 const int col = int((st0 + it) * MO_KC);               // samples beyond N are zero-filled by TMA
 #pragma unroll
-                for (int g = 0; g < S::NG; ++g) tma_load_2d(st + g * S::GROUP_BYTES, &map_x, g * 32, col, &full[s]);
+                                // the batch is read exactly once: evict-first, so that it does not push the CTAs' partial sums (which the
+                // drains update every MO_FLUSH_STAGES stages) out of L2
+                for (int g = 0; g < S::NG; ++g)
+                    tma_load_2d_hint(st + g * S::GROUP_BYTES, &map_x, g * 32, col, &full[s], L2_EVICT_FIRST);
             }
         }
     } else if (warp == 1) {
