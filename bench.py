@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -352,8 +352,26 @@ def main():
             "tf32_tflops_issued": 2 * 2 * 256 * 256 * n4 / (m4_ms * 1e-3) / 1e12,
             "ms_per_step_batch_1e5": g4_s * 1e3, "step_samples_per_s": nb4 * world / g4_s,
             "path": "tcgen05.mma kind::tf32, MN-major operands (TMA 128B/32B-atom swizzle), P = Xh Xh^T + Xh (2Xl)^T, "
-                    "float64 chain rule in one 8-CTA cluster; step = set_params + moments + chain rule + D2H"
+                    "float64 chain rule on column-sliced CTAs; step = set_params + moments + chain rule + D2H"
                     + (" + ncclAllReduce of the moments" if world > 1 else "")}
+
+        # the same chain through the whole optimize_whitening loop on the device: one pass for the per-batch moment
+        # matrices, then 2 launches per step whose cost does not depend on the number of samples
+        nfit = 60 * nb4
+        fit = lambda ne: E.optimize_whitening(X4.cols(0, nfit), f4, E.ADAGrad(), nbatches=60, nepochs=ne, device_loop=True, group=world > 1)
+        fit(1)                                          # warm-up: allocations, kernel attributes
+        barrier()
+        t0 = time.perf_counter()
+        fit(1)
+        fit1_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        t0 = time.perf_counter()
+        r4 = fit(5)
+        fit5_s = max_over_ranks(time.perf_counter() - t0)
+        extras["fit_c4_d256_k64_device_loop"] = {
+            "samples_per_gpu": nfit, "nbatches": 60, "total_ms_1_epoch": fit1_s * 1e3, "total_ms_5_epochs": fit5_s * 1e3,
+            "us_per_step_after_first_epoch": (fit5_s - fit1_s) / 240 * 1e6,
+            "negll_first_last": [float(r4["negll_history"][0]), float(r4["negll_history"][-1])]}
 
         # C2: 1-D JohnsonTrafo + ScaleShiftTrafo whitening fit, 1e7 samples, nbatches=100 (examples/nf_example_1d.jl shape):
         # time per gradient step of the host loop (one fused kernel + host optimizer per step) and of the device loop

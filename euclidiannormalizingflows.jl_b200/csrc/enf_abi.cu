@@ -165,6 +165,9 @@ struct enf_chain {
     bool affine_dirty = false;
     double* d_params64 = nullptr;  // packed float64 parameters (device-side chain rule)
     double* d_mom_out = nullptr;   // [negll, grads...]
+    double* d_mom_part = nullptr;  // per-CTA partial [negll, grads...] of the chain-rule kernel
+    double* d_mom_all = nullptr;   // per-batch moment matrices of the device-side fit loop (kept between calls)
+    size_t mom_all_cap = 0;        // ... capacity in doubles
     double* h_mom_out = nullptr;   // pinned
 };
 
@@ -579,9 +582,9 @@ int moments_finish_device(enf_chain* ch, int flags, double* negll, void* grads_h
         poffs.push_back(int(op.poff));
     }
     const double lconst = ch->ladj_const_other + ((flags & ENF_NEGLL_ZYGOTE_PRIMAL) ? 0.0 : ch->ladj_const_ss);
-    CU(ctx, launch_moments_chainrule(ch->D, int(kinds.size()), kinds.data(), Ks.data(), poffs.data(), ch->d_params64, ch->d_params64 + ch->n_params, ch->d_sums,
-                                     lconst, ch->d_mom_out, ctx->stream));
-    ctx->launches += 1;
+    CU(ctx, launch_moments_chainrule(ch->D, int(kinds.size()), kinds.data(), Ks.data(), poffs.data(), int(ch->n_params), ch->d_params64,
+                                     ch->d_params64 + ch->n_params, ch->d_sums, lconst, nullptr, ch->d_mom_part, ch->d_mom_out, ctx->stream));
+    ctx->launches += 2;
     CU(ctx, cudaMemcpyAsync(ch->h_mom_out, ch->d_mom_out, (ch->n_params + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (negll) *negll = ch->h_mom_out[0];
@@ -845,6 +848,7 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
     if (ch->moments &&
         ((e = cudaMalloc(reinterpret_cast<void**>(&ch->d_params64), (ch->n_params + size_t(d.n_scalars) + 1) * sizeof(double))) != cudaSuccess ||
          (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_mom_out), (ch->n_params + 1) * sizeof(double))) != cudaSuccess ||
+         (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_mom_part), moments_chainrule_part_bytes(D, int(ch->n_params)))) != cudaSuccess ||
          (e = cudaMallocHost(reinterpret_cast<void**>(&ch->h_mom_out), (ch->n_params + 1) * sizeof(double))) != cudaSuccess)) {
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
@@ -887,6 +891,8 @@ extern "C" int enf_chain_destroy(enf_chain* ch) {
     if (ch->d_affine) cudaFree(ch->d_affine);
     if (ch->d_params64) cudaFree(ch->d_params64);
     if (ch->d_mom_out) cudaFree(ch->d_mom_out);
+    if (ch->d_mom_part) cudaFree(ch->d_mom_part);
+    if (ch->d_mom_all) cudaFree(ch->d_mom_all);
     if (ch->h_mom_out) cudaFreeHost(ch->h_mom_out);
     if (ch->consts_copied) cudaEventDestroy(ch->consts_copied);
     delete ch;
@@ -1112,6 +1118,132 @@ extern "C" int enf_negll_grad_group(enf_chain* ch, const void* x, int64_t N_loca
     return enf_negll_grad_finish(ch, ch->h_sums, N_global, flags, negll, grads_host);
 }
 
+// Device-side fit loop for second-moment (Householder/ScaleShift) chains: the batches are contiguous, unshuffled and
+// the same in every epoch (src/optimize_whitening.jl:31-38), and the loss depends on a batch only through its moment
+// matrix, so ONE pass over the data computes [[S, m], [m^T, N]] of every batch; after that a step is two launches
+// (chain-rule cluster kernel + optimizer kernel) whose cost does not depend on the number of samples.
+static int optimize_whitening_moments(enf_chain* ch, const void* x, int64_t N, int64_t batchsize, int64_t nb, int64_t nepochs,
+                                      double eta, double epsilon, int flags, int use_group, int fresh_state,
+                                      double* state_inout, void* params_out, double* history_out) {
+    enf_ctx* ctx = ch->ctx;
+    const size_t P = ch->n_params, stride = size_t(ch->n_raw) + 1;
+    const int64_t n_steps = nb * nepochs;
+    if (!aligned16(x) || (batchsize * ch->D * 4) % 16 != 0)
+        return fail(ctx, ENF_ERR_INVALID, "second-moment chains need 16-byte aligned batches (D=%d, batch size %lld)", ch->D,
+                    static_cast<long long>(batchsize));
+    std::vector<int> kinds, Ks, poffs;
+    for (const HostOp& op : ch->ops) {
+        kinds.push_back(op.kind);
+        Ks.push_back(op.K);
+        poffs.push_back(int(op.poff));
+    }
+    double *d_all = nullptr, *d_state = nullptr, *d_hist = nullptr, *d_lc = nullptr;
+    long long* d_step = nullptr;
+    auto cleanup = [&]() {
+        if (d_state) cudaFree(d_state);
+        if (d_hist) cudaFree(d_hist);
+        if (d_lc) cudaFree(d_lc);
+        if (d_step) cudaFree(d_step);
+    };
+#define CUF(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            cleanup();                                                                                   \
+            return fail(ctx, ENF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                \
+    } while (0)
+    std::vector<double> st0(P);
+    for (size_t i = 0; i < P; ++i) st0[i] = fresh_state ? epsilon : state_inout[i];
+    // ladj row constants, one device slot per op (ScaleShift: sum log|a|; ENF_NEGLL_ZYGOTE_PRIMAL: dropped)
+    std::vector<double> lc0(ch->ops.size(), 0.0);
+    for (size_t o = 0; o < ch->ops.size(); ++o)
+        if (ch->ops[o].kind == OP_SS && !(flags & ENF_NEGLL_ZYGOTE_PRIMAL))
+            for (int i = 0; i < ch->D; ++i) lc0[o] += std::log(std::fabs(ch->params[ch->ops[o].poff + size_t(i)]));
+    if (ch->mom_all_cap < size_t(nb) * stride) {   // tens of MB: allocate once per chain, not once per call
+        if (ch->d_mom_all) cudaFree(ch->d_mom_all);
+        ch->d_mom_all = nullptr;
+        ch->mom_all_cap = 0;
+        CUF(cudaMalloc(reinterpret_cast<void**>(&ch->d_mom_all), size_t(nb) * stride * sizeof(double)));
+        ch->mom_all_cap = size_t(nb) * stride;
+    }
+    d_all = ch->d_mom_all;
+    CUF(cudaMalloc(reinterpret_cast<void**>(&d_state), P * sizeof(double)));
+    CUF(cudaMalloc(reinterpret_cast<void**>(&d_hist), size_t(n_steps ? n_steps : 1) * sizeof(double)));
+    CUF(cudaMalloc(reinterpret_cast<void**>(&d_lc), lc0.size() * sizeof(double)));
+    CUF(cudaMalloc(reinterpret_cast<void**>(&d_step), sizeof(long long)));
+    CUF(cudaMemcpyAsync(d_state, st0.data(), P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUF(cudaMemcpyAsync(d_lc, lc0.data(), lc0.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUF(cudaMemsetAsync(d_step, 0, sizeof(long long), ctx->stream));
+    CUF(cudaStreamSynchronize(ctx->stream));
+    // the one pass over the data
+    for (int64_t b = 0; b < nb; ++b) {
+        const int64_t start = b * batchsize, nbt = std::min(batchsize, N - start);
+        const char* xb = static_cast<const char*>(x) + size_t(start) * size_t(ch->D) * 4;
+        CUF(launch_moments(ch->D, xb, nbt, ch->d_partials, d_all + size_t(b) * stride, ctx->sm_count, ctx->stream));
+        ctx->launches += 2;
+    }
+    if (use_group) {
+        ncclResult_t r = g_nccl.AllReduce(d_all, d_all, size_t(nb) * stride, ncclDouble, ncclSum, ctx->comm, ctx->stream);
+        if (r != ncclSuccess) {
+            cleanup();
+            return fail(ctx, ENF_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+        }
+    }
+    double* d_par = ch->d_params64;          // parameters + v.v array: uploaded by derive_constants, updated in place
+    double* d_norms = ch->d_params64 + P;
+    auto enqueue_epoch = [&]() -> int {
+        for (int64_t b = 0; b < nb; ++b) {
+            CUF(launch_moments_chainrule(ch->D, int(kinds.size()), kinds.data(), Ks.data(), poffs.data(), int(P), d_par, d_norms,
+                                         d_all + size_t(b) * stride, 0.0, d_lc, ch->d_mom_part, ch->d_mom_out, ctx->stream));
+            CUF(launch_moments_update(ch->D, int(kinds.size()), kinds.data(), Ks.data(), poffs.data(), ch->d_mom_out, d_par,
+                                      d_norms, d_state, eta, epsilon, flags, d_lc, d_hist, d_step, ctx->stream));
+            ctx->launches += 3;
+        }
+        return ENF_OK;
+    };
+    int64_t ep = 0;
+    if (nepochs >= 1) {          // first epoch directly: sets the kernels' shared-memory attributes (not capturable)
+        int rc = enqueue_epoch();
+        if (rc != ENF_OK) return rc;
+        ep = 1;
+    }
+    static const bool no_graph = getenv("ENF_NO_GRAPH") != nullptr;
+    if (nepochs - ep >= 2 && !no_graph && nb <= 4096) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            int rc = enqueue_epoch();
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc != ENF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            ok = ce == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        }
+        if (ok) {
+            for (; ep < nepochs; ++ep)
+                if (cudaGraphLaunch(exec, ctx->stream) != cudaSuccess) { ok = false; break; }
+        } else {
+            cudaGetLastError();
+        }
+        if (exec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(exec); }
+        if (graph) cudaGraphDestroy(graph);
+    }
+    for (; ep < nepochs; ++ep) {
+        int rc = enqueue_epoch();
+        if (rc != ENF_OK) return rc;
+    }
+    std::vector<double> pfin(P);
+    CUF(cudaMemcpyAsync(pfin.data(), d_par, P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUF(cudaMemcpyAsync(state_inout, d_state, P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_steps) CUF(cudaMemcpyAsync(history_out, d_hist, size_t(n_steps) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUF(cudaStreamSynchronize(ctx->stream));
+#undef CUF
+    cleanup();
+    ch->params = pfin;
+    export_grads(ch, pfin, params_out);
+    return derive_constants(ch);
+}
+
 // ------------------------------------------------------------------ device-side fit loop
 extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, int64_t nbatches, int64_t nepochs,
                                       double eta, double epsilon, int flags, int use_group, int fresh_state,
@@ -1121,10 +1253,6 @@ extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, i
     if (!x || !state_inout || !params_out || !history_out) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
     if (N < 1 || nbatches < 1 || nepochs < 0) return fail(ctx, ENF_ERR_INVALID, "bad N / nbatches / nepochs");
     if (use_group && !ctx->comm) return fail(ctx, ENF_ERR_INVALID, "enf_group_init has not been called on this context");
-    if (ch->moments)
-        return fail(ctx, ENF_ERR_INVALID,
-                    "the device-side fit loop does not cover second-moment (Householder/ScaleShift, D=%d) chains yet: "
-                    "drive enf_negll_grad from the host loop", ch->D);
     CU(ctx, cudaSetDevice(ctx->device));
     // src/optimize_whitening.jl:31: batchsize = round(Int, length(smpls) / nbatches)  (ties to even)
     const int64_t batchsize = int64_t(std::nearbyint(double(N) / double(nbatches)));
@@ -1132,6 +1260,9 @@ extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, i
     const int64_t nb = (N + batchsize - 1) / batchsize;
     const int64_t n_steps = nb * nepochs;
     if (n_steps_out) *n_steps_out = n_steps;
+    if (ch->moments)
+        return optimize_whitening_moments(ch, x, N, batchsize, nb, nepochs, eta, epsilon, flags, use_group, fresh_state,
+                                          state_inout, params_out, history_out);
     const size_t P = ch->n_params;
     const size_t es = elem_size(ch->dtype);
 

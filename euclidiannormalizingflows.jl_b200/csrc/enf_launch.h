@@ -66,8 +66,14 @@ bool affine_supported(int dtype, int D, const ChainDesc& d);
 bool moments_supported(int dtype, int D);
 size_t moments_partial_bytes(int D, int sm_count);
 cudaError_t launch_moments(int D, const void* x, int64_t N, void* d_part, double* d_sums, int sm_count, cudaStream_t st);
-cudaError_t launch_moments_chainrule(int D, int n_ops, const int* kinds, const int* Ks, const int* poffs, const double* d_params,
-                                     const double* d_norms, const double* d_sums, double lconst, double* d_out, cudaStream_t st);
+size_t moments_chainrule_part_bytes(int D, int n_params);
+cudaError_t launch_moments_chainrule(int D, int n_ops, const int* kinds, const int* Ks, const int* poffs, int n_params,
+                                     const double* d_params, const double* d_norms, const double* d_sums, double lconst,
+                                     const double* d_lconst, double* d_part, double* d_out, cudaStream_t st);
+// device-side optimizer step on the chain-rule kernel's output (ADAGrad + Householder column normalisation)
+cudaError_t launch_moments_update(int D, int n_ops, const int* kinds, const int* Ks, const int* poffs, const double* d_out,
+                                  double* d_params, double* d_norms, double* d_state, double eta, double eps, int flags,
+                                  double* d_lconst, double* d_history, long long* d_step, cudaStream_t st);
 cudaError_t launch_affine(int D, const float* d_w, const void* x, void* y, void* ladj, int64_t N, double ladj_const,
                           int sm_count, cudaStream_t st);
 

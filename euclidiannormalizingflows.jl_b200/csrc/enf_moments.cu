@@ -21,8 +21,6 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
-#include <cooperative_groups.h>
-
 #include <cstdlib>
 
 #include "enf_chain.cuh"
@@ -275,185 +273,243 @@ __global__ void moments_reduce_kernel(const float* __restrict__ part_s, const do
 // ---------------------------------------------------------------------------------------------------------
 // Chain rule on the device: second moments -> (negll, gradients), float64.
 //
-// One thread-block CLUSTER of MC_CL CTAs; CTA r keeps rows [r RB, (r+1) RB) of B (x_i = B_i [x; 1]) and of Z
-// (moments of the cotangent, Z_n = B_n S^/N) in shared memory.  A reflection needs the column sums v^T B and
-// v^T Z over ALL rows: every CTA publishes its partial sums in its own shared memory, one cluster barrier, and
-// every CTA adds the MC_CL partials it reads through distributed shared memory (fixed order: bitwise
-// reproducible).  Everything else is row-local.  Same algebra as enf_abi.cu: finish_moments and
-// tests/device_model.py: affine_moments_finish.
-constexpr int MC_CL = 8;           // CTAs per cluster
+// With x^ = [x; 1] every intermediate of the chain is x_i = B_i x^ and the cotangent moments are Z_i (Z_n = B_n S^/N,
+// Z_(i-1) = A_i^T Z_i).  Both are D x (D+1) matrices on which every op acts COLUMN by column: a reflection needs
+// v^T B[:, c] and v^T Z[:, c] of the same column only.  So the columns are dealt out to independent CTAs (MC_NC
+// columns each, one thread per row, the 2 MC_NC entries of a row in registers) and the sweep needs no communication
+// between CTAs at all: what couples the columns - the row dot products of the parameter gradients and the loss - is
+// additive, every CTA writes its partial (negll, gradient) vector and a second kernel adds them in a fixed order.
+// Per reflection a CTA does one block-wide reduction of 2 MC_NC values.  Same algebra as enf_abi.cu: finish_moments
+// and tests/device_model.py: affine_moments_finish.
+constexpr int MC_NC = 2;           // columns of B and Z per CTA (129 CTAs at D = 256: one block reduction of 4 values per reflection)
 constexpr double MO_LOG2PI = 1.8378770664093454835606594728112;
-constexpr int MC_THREADS = 256;
 
 struct MomOp { int kind, K, poff, noff; };   // noff: offset of this op's reflections in the v.v array
 struct MomChain { int n_ops, D; MomOp ops[MAX_OPS]; };
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// out[0] = negll, out[1 .. 1+P) = gradients (packed like the parameters)
-__global__ void __cluster_dims__(MC_CL, 1, 1) __launch_bounds__(MC_THREADS, 1)
-moments_chainrule_kernel(const __grid_constant__ MomChain mc, const double* __restrict__ params,
-                         const double* __restrict__ norms, const double* __restrict__ sums, double lconst,
-                         double* __restrict__ out) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = int(cluster.block_rank());
-    const int D = mc.D, D1 = D + 1, RB = D / MC_CL, r0 = rank * RB;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int NW = MC_THREADS / 32;
-    extern __shared__ double sm[];
-    double* Bs = sm;                              // [RB][D1]
-    double* Zs = Bs + size_t(RB) * D1;            // [RB][D1]
-    double* part = Zs + size_t(RB) * D1;          // [2 buffers][2 matrices][D1] partial column sums (read by peers)
-    double* tB = part + 4 * D1;                   // [D1] v^T B
-    double* tZ = tB + D1;                         // [D1] v^T Z
-    double* red = tZ + D1;                        // [NW + 1] block reduction scratch / this CTA's loss partial
+// part: [gridDim.x][1 + P]  (partial sum_j |y_j|^2 / (2N), partial gradients)
+__global__ void __launch_bounds__(256) moments_chainrule_kernel(const __grid_constant__ MomChain mc, const double* __restrict__ params,
+                                                                const double* __restrict__ norms, const double* __restrict__ sums,
+                                                                int n_params, double* __restrict__ part) {
+    const int D = mc.D, D1 = D + 1, k = threadIdx.x, c0 = blockIdx.x * MC_NC;
+    const int warp = k >> 5, lane = k & 31, NW = blockDim.x >> 5;
+    __shared__ double s_w[2][8][2 * MC_NC];      // per-warp partial sums, double-buffered (one barrier per reduction)
     const double Nd = sums[size_t(D) * D1 + D];
-
-    for (int i = tid; i < RB * D1; i += MC_THREADS) {
-        const int k = i / D1, c = i % D1;
-        Bs[i] = (c == r0 + k) ? 1.0 : 0.0;
-        Zs[i] = sums[size_t(r0 + k) * D1 + c] / Nd;
+    double B[MC_NC], Z[MC_NC], w[MC_NC];
+    int jD = -1;                                  // which of my columns is the homogeneous one (c == D), if any
+#pragma unroll
+    for (int j = 0; j < MC_NC; ++j) {
+        const int c = c0 + j;
+        const bool valid = c < D1;
+        B[j] = (c == k) ? 1.0 : 0.0;
+        Z[j] = valid ? sums[size_t(k) * D1 + c] / Nd : 0.0;
+        w[j] = valid ? sums[size_t(D) * D1 + c] / Nd : 0.0;
+        if (c == D) jD = j;
     }
-    __syncthreads();
-
-    int nsync = 0;                                // reflections processed so far -> partial buffer parity
-    // column sums over all rows of the cluster: tB = v^T B, tZ = v^T Z
-    auto column_sums = [&](const double* v) {
-        double* mine = part + (nsync & 1) * 2 * D1;
-        for (int c = tid; c < D1; c += MC_THREADS) {
-            double sb = 0.0, sz = 0.0;
-            for (int k = 0; k < RB; ++k) {
-                const double vk = v[r0 + k];
-                sb += vk * Bs[k * D1 + c];
-                sz += vk * Zs[k * D1 + c];
-            }
-            mine[c] = sb;
-            mine[D1 + c] = sz;
+    int nred = 0;
+    // t[0..NC) = v^T B, t[NC..2NC) = v^T Z over the rows (all threads get all sums, fixed summation order)
+    auto column_sums = [&](double vk, double (&t)[2 * MC_NC]) {
+        double p[2 * MC_NC];
+#pragma unroll
+        for (int j = 0; j < MC_NC; ++j) {
+            p[j] = vk * B[j];
+            p[MC_NC + j] = vk * Z[j];
         }
-        cluster.sync();
-        for (int c = tid; c < D1; c += MC_THREADS) {
-            double sb = 0.0, sz = 0.0;
-            for (int r = 0; r < MC_CL; ++r) {
-                const double* peer = cluster.map_shared_rank(mine, r);
-                sb += peer[c];
-                sz += peer[D1 + c];
-            }
-            tB[c] = sb;
-            tZ[c] = sz;
+#pragma unroll
+        for (int i = 0; i < 2 * MC_NC; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) p[i] += __shfl_xor_sync(0xffffffffu, p[i], o);
         }
-        ++nsync;
+        double (*buf)[2 * MC_NC] = s_w[nred & 1];
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 2 * MC_NC; ++i) buf[warp][i] = p[i];
+        }
         __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2 * MC_NC; ++i) {
+            double a = 0.0;
+            for (int ww = 0; ww < NW; ++ww) a += buf[ww][i];
+            t[i] = a;
+        }
+        ++nred;
     };
-
     // ---- forward: B_n, Z_n
     for (int o = 0; o < mc.n_ops; ++o) {
         const MomOp op = mc.ops[o];
         const double* p = params + op.poff;
         if (op.kind == OP_SS) {
-            for (int i = tid; i < RB * D1; i += MC_THREADS) {
-                const int k = i / D1, c = i % D1;
-                const double a = p[r0 + k], b = p[D + r0 + k];
-                const double w = sums[size_t(D) * D1 + c] / Nd;
-                Bs[i] = a * Bs[i] + (c == D ? b : 0.0);
-                Zs[i] = a * Zs[i] + b * w;
+            const double a = p[k], b = p[D + k];
+#pragma unroll
+            for (int j = 0; j < MC_NC; ++j) {
+                B[j] = a * B[j] + (j == jD ? b : 0.0);
+                Z[j] = a * Z[j] + b * w[j];
             }
-            __syncthreads();
         } else {
             for (int r = 0; r < op.K; ++r) {
-                const double* v = p + size_t(r) * D;
-                const double s = 2.0 / norms[op.noff + r];      // v.v, float64, from the host
-                column_sums(v);
-                for (int i = tid; i < RB * D1; i += MC_THREADS) {
-                    const int k = i / D1, c = i % D1;
-                    const double f = s * v[r0 + k];
-                    Bs[i] -= f * tB[c];
-                    Zs[i] -= f * tZ[c];
+                const double vk = p[size_t(r) * D + k];
+                const double f = (2.0 / norms[op.noff + r]) * vk;
+                double t[2 * MC_NC];
+                column_sums(vk, t);
+#pragma unroll
+                for (int j = 0; j < MC_NC; ++j) {
+                    B[j] -= f * t[j];
+                    Z[j] -= f * t[MC_NC + j];
                 }
-                __syncthreads();
             }
         }
     }
-    // ---- loss: sum_j |y_j|^2 / 2 = N/2 <Z_n, B_n>
-    {
+    double* mine = part + size_t(blockIdx.x) * (1 + n_params);
+    {   // ---- loss: sum_j |y_j|^2 / (2N) = <Z_n, B_n> / 2, this CTA's columns
         double acc = 0.0;
-        for (int i = tid; i < RB * D1; i += MC_THREADS) acc += Zs[i] * Bs[i];
-        acc = warp_sum(acc);
-        if (lane == 0) red[warp] = acc;
+#pragma unroll
+        for (int j = 0; j < MC_NC; ++j) acc += Z[j] * B[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        double (*buf)[2 * MC_NC] = s_w[nred & 1];
+        if (lane == 0) buf[warp][0] = acc;
         __syncthreads();
-        if (tid == 0) {
-            double t = 0.0;
-            for (int w = 0; w < NW; ++w) t += red[w];
-            red[NW] = t;
+        if (k == 0) {
+            double a = 0.0;
+            for (int ww = 0; ww < NW; ++ww) a += buf[ww][0];
+            mine[0] = 0.5 * a;
         }
-        cluster.sync();
-        if (rank == 0 && tid == 0) {
-            double t = 0.0;
-            for (int r = 0; r < MC_CL; ++r) t += cluster.map_shared_rank(red, r)[NW];
-            out[0] = 0.5 * t + 0.5 * MO_LOG2PI * D - lconst;
-        }
+        ++nred;
     }
     // ---- reverse sweep
-    double* g_all = out + 1;
+    double* g_all = mine + 1;
     for (int o = mc.n_ops - 1; o >= 0; --o) {
         const MomOp op = mc.ops[o];
         const double* p = params + op.poff;
         double* g = g_all + op.poff;
         if (op.kind == OP_SS) {
-            for (int k = warp; k < RB; k += NW) {                    // one warp per row
-                const double a = p[r0 + k], b = p[D + r0 + k], ia = 1.0 / a;
-                double* rb = Bs + k * D1;
-                double* rz = Zs + k * D1;
-                const double gb = rz[D];
-                __syncwarp();
-                double acc = 0.0;
-                for (int c = lane; c < D1; c += 32) {
-                    const double bin = (rb[c] - (c == D ? b : 0.0)) * ia;
-                    rb[c] = bin;
-                    acc += rz[c] * bin;
-                    rz[c] *= a;
-                }
-                acc = warp_sum(acc);
-                if (lane == 0) {
-                    g[r0 + k] = acc - ia;
-                    g[D + r0 + k] = gb;
-                }
+            const double a = p[k], b = p[D + k], ia = 1.0 / a;
+            double gb = 0.0, acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < MC_NC; ++j) {
+                if (j == jD) gb = Z[j];                               // db = Z[:, D] (only the CTA that owns that column)
+                const double bin = (B[j] - (j == jD ? b : 0.0)) * ia;
+                B[j] = bin;
+                acc += Z[j] * bin;
+                Z[j] *= a;
             }
-            __syncthreads();
+            g[k] = acc - (blockIdx.x == 0 ? ia : 0.0);   // the ladj term -1/a enters once
+            g[D + k] = gb;
         } else {
             for (int r = op.K - 1; r >= 0; --r) {
-                const double* v = p + size_t(r) * D;
-                const double n = norms[op.noff + r], s = 2.0 / n;
-                column_sums(v);                                       // of B_out and Z_out
-                double vcv = 0.0;                                     // v^T C v = -(v^T Z_out).(v^T B_out)
-                for (int c = lane; c < D1; c += 32) vcv -= tZ[c] * tB[c];
-                vcv = warp_sum(vcv);
-                for (int k = warp; k < RB; k += NW) {
-                    const double vk = v[r0 + k], f = s * vk;
-                    double* rb = Bs + k * D1;
-                    double* rz = Zs + k * D1;
-                    double cv = 0.0, ctv = 0.0;
-                    for (int c = lane; c < D1; c += 32) {
-                        const double bin = rb[c] - f * tB[c];         // B: output -> input of this reflection
-                        rb[c] = bin;
-                        const double z = rz[c];
-                        cv -= z * tB[c];                              // v^T B_in = -tB
-                        ctv += bin * tZ[c];
-                        rz[c] = z - f * tZ[c];
-                    }
-                    cv = warp_sum(cv);
-                    ctv = warp_sum(ctv);
-                    if (lane == 0) g[size_t(r) * D + r0 + k] = -s * (cv + ctv) + (4.0 / (n * n)) * vcv * vk;
+                const double vk = p[size_t(r) * D + k];
+                const double n = norms[op.noff + r], s = 2.0 / n, f = s * vk;
+                double t[2 * MC_NC];
+                column_sums(vk, t);                                   // of B_out and Z_out
+                double cv = 0.0, ctv = 0.0, vcv = 0.0;
+#pragma unroll
+                for (int j = 0; j < MC_NC; ++j) {
+                    const double bin = B[j] - f * t[j];               // B: output -> input of this reflection
+                    B[j] = bin;
+                    cv -= Z[j] * t[j];                                // v^T B_in = -(v^T B_out)
+                    ctv += bin * t[MC_NC + j];
+                    vcv -= t[MC_NC + j] * t[j];
+                    Z[j] -= f * t[MC_NC + j];
                 }
-                __syncthreads();
+                g[size_t(r) * D + k] = -s * (cv + ctv) + (4.0 / (n * n)) * vcv * vk;
             }
         }
     }
-    cluster.sync();   // nobody exits while a peer may still read its partial sums
+}
+
+// out[0] = negll, out[1 .. 1+P) = gradients: fixed-order sum of the per-CTA partials
+__global__ void moments_chainrule_reduce_kernel(const double* __restrict__ part, int n_cta, int n_params, int D, double lconst,
+                                                const double* __restrict__ lconst_dev, int n_lconst, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_params) return;
+    double a = 0.0;
+    for (int c = 0; c < n_cta; ++c) a += part[size_t(c) * (1 + n_params) + i];
+    if (i == 0) {
+        double lc = lconst;                       // ladj row constants: host value, or one device slot per op
+        if (lconst_dev != nullptr) {
+            lc = 0.0;
+            for (int o = 0; o < n_lconst; ++o) lc += lconst_dev[o];
+        }
+        a += 0.5 * MO_LOG2PI * D - lc;
+    }
+    out[i] = a;
+}
+
+// Device-side optimizer step for second-moment chains (enf_optimize_whitening): ADAGrad per Optimisers 0.2
+// (acc += g^2; x -= eta g / (sqrt(acc) + eps)) on the gradients the chain-rule kernels left in out[1..], then the
+// HouseholderTrafo functor rebuild (src/householder_trafo.jl:134-146: every column normalised), the v.v array and
+// the ScaleShift ladj constants of the NEXT step (one slot per op), and the loss history.  One CTA per Householder
+// column / per ScaleShift op.
+__global__ void __launch_bounds__(256) moments_update_kernel(const __grid_constant__ MomChain mc, const double* __restrict__ out,
+                                                             double* __restrict__ params, double* __restrict__ norms,
+                                                             double* __restrict__ state, double eta, double eps, int flags,
+                                                             double* __restrict__ lconst_dev, double* __restrict__ history,
+                                                             long long* __restrict__ step_ctr) {
+    const int D = mc.D, tid = threadIdx.x;
+    __shared__ double s_red[256];
+    auto block_sum = [&](double v) {
+        s_red[tid] = v;
+        __syncthreads();
+        for (int s2 = 128; s2 > 0; s2 >>= 1) {
+            if (tid < s2) s_red[tid] += s_red[tid + s2];
+            __syncthreads();
+        }
+        const double r = s_red[0];
+        __syncthreads();
+        return r;
+    };
+    if (blockIdx.x == 0 && tid == 0) {
+        const long long step = *step_ctr;   // on the device so that a captured epoch can be replayed
+        history[step] = out[0];
+        *step_ctr = step + 1;
+    }
+    int o = 0, k = int(blockIdx.x);          // this CTA's unit: column k of Householder op o, or ScaleShift op o
+    for (; o < mc.n_ops; ++o) {
+        const int cnt = mc.ops[o].kind == OP_HH ? mc.ops[o].K : 1;
+        if (k < cnt) break;
+        k -= cnt;
+    }
+    if (o >= mc.n_ops) return;
+    const MomOp op = mc.ops[o];
+    const double* g_all = out + 1;
+    if (op.kind == OP_SS) {
+        double* p = params + op.poff;
+        double* st = state + op.poff;
+        const double* g = g_all + op.poff;
+        double part = 0.0;
+        for (int i = tid; i < 2 * D; i += blockDim.x) {
+            const double gg = g[i];
+            const double a = st[i] + gg * gg;
+            st[i] = a;
+            const double nv = p[i] - eta * gg / (sqrt(a) + eps);
+            p[i] = nv;
+            if (i < D) part += log(fabs(nv));
+        }
+        const double lc = block_sum(part);
+        if (tid == 0) lconst_dev[o] = (flags & 1) ? 0.0 : lc;   // ENF_NEGLL_ZYGOTE_PRIMAL drops the ScaleShift ladj value
+    } else {
+        double* v = params + op.poff + size_t(k) * D;
+        double* st = state + op.poff + size_t(k) * D;
+        const double* g = g_all + op.poff + size_t(k) * D;
+        double part = 0.0;
+        for (int i = tid; i < D; i += blockDim.x) {
+            const double gg = g[i];
+            const double a = st[i] + gg * gg;
+            st[i] = a;
+            const double nv = v[i] - eta * gg / (sqrt(a) + eps);
+            v[i] = nv;
+            part += nv * nv;
+        }
+        const double inv = 1.0 / sqrt(block_sum(part));
+        part = 0.0;
+        for (int i = tid; i < D; i += blockDim.x) {
+            const double nv = v[i] * inv;
+            v[i] = nv;
+            part += nv * nv;
+        }
+        const double n2 = block_sum(part);
+        if (tid == 0) norms[op.noff + k] = n2;
+    }
 }
 
 }  // namespace
@@ -504,8 +560,8 @@ cudaError_t launch_moments(int D, const void* x, int64_t N, void* d_part, double
 
 // sums -> out[0] = negll, out[1 .. 1+P) = gradients; kinds/Ks/poffs: the chain's ops in application order,
 // d_params: packed float64 parameters on the device, d_norms: v.v of every reflection in application order
-cudaError_t launch_moments_chainrule(int D, int n_ops, const int* kinds, const int* Ks, const int* poffs, const double* d_params,
-                                     const double* d_norms, const double* d_sums, double lconst, double* d_out, cudaStream_t st) {
+namespace {
+MomChain make_mom_chain(int D, int n_ops, const int* kinds, const int* Ks, const int* poffs) {
     MomChain mc;
     mc.n_ops = n_ops;
     mc.D = D;
@@ -514,17 +570,35 @@ cudaError_t launch_moments_chainrule(int D, int n_ops, const int* kinds, const i
         mc.ops[o] = MomOp{kinds[o], Ks[o], poffs[o], noff};
         if (kinds[o] == OP_HH) noff += Ks[o];
     }
-    const int D1 = D + 1, RB = D / MC_CL;
-    const size_t smem = (size_t(2) * RB * D1 + 6 * D1 + MC_THREADS / 32 + 1) * sizeof(double);
-    static size_t set[64] = {};   // largest dynamic shared-memory size enabled so far, per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (set[dev & 63] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(moments_chainrule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        set[dev & 63] = smem;
-    }
-    moments_chainrule_kernel<<<MC_CL, MC_THREADS, smem, st>>>(mc, d_params, d_norms, d_sums, lconst, d_out);
+    return mc;
+}
+}  // namespace
+
+cudaError_t launch_moments_update(int D, int n_ops, const int* kinds, const int* Ks, const int* poffs, const double* d_out,
+                                  double* d_params, double* d_norms, double* d_state, double eta, double eps, int flags,
+                                  double* d_lconst, double* d_history, long long* d_step, cudaStream_t st) {
+    const MomChain mc = make_mom_chain(D, n_ops, kinds, Ks, poffs);
+    int units = 0;
+    for (int o = 0; o < n_ops; ++o) units += kinds[o] == OP_HH ? Ks[o] : 1;
+    moments_update_kernel<<<units, 256, 0, st>>>(mc, d_out, d_params, d_norms, d_state, eta, eps, flags, d_lconst, d_history, d_step);
+    return cudaGetLastError();
+}
+
+size_t moments_chainrule_part_bytes(int D, int n_params) {
+    return size_t((D + 1 + MC_NC - 1) / MC_NC) * size_t(1 + n_params) * sizeof(double);
+}
+
+// d_part: moments_chainrule_part_bytes() of scratch; lconst / d_lconst: the ladj row constant (host value, or the sum of
+// the n_ops per-op device slots when d_lconst != nullptr)
+cudaError_t launch_moments_chainrule(int D, int n_ops, const int* kinds, const int* Ks, const int* poffs, int n_params,
+                                     const double* d_params, const double* d_norms, const double* d_sums, double lconst,
+                                     const double* d_lconst, double* d_part, double* d_out, cudaStream_t st) {
+    const MomChain mc = make_mom_chain(D, n_ops, kinds, Ks, poffs);
+    const int n_cta = (D + 1 + MC_NC - 1) / MC_NC;
+    moments_chainrule_kernel<<<n_cta, D, 0, st>>>(mc, d_params, d_norms, d_sums, n_params, d_part);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    moments_chainrule_reduce_kernel<<<(n_params + 1 + 255) / 256, 256, 0, st>>>(d_part, n_cta, n_params, D, lconst, d_lconst, n_ops, d_out);
     return cudaGetLastError();
 }
 

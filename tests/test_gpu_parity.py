@@ -429,3 +429,47 @@ def test_moments_chain_rule_device_kernel_matches_host_code(ctx):
     assert flat_dev.shape == g_host.shape
     scale = np.abs(g_host).max()
     assert np.abs(np.sort(flat_dev) - np.sort(g_host)).max() <= 1e-6 * scale   # same values (packing order aside)
+
+
+def type_map(ns, t):
+    """the same leaf trafo in another namespace (oracle <-> product), parameters as float64"""
+    return getattr(ns, type(t).__name__)(*[np.asarray(getattr(t, n), dtype=np.float64) for n in t.fields])
+
+
+@pytest.mark.gpu
+def test_device_side_fit_loop_for_second_moment_chains(ctx):
+    """optimize_whitening of a Householder+ScaleShift chain at D=128: the device loop (one pass for the per-batch
+    moment matrices, then chain-rule + optimizer kernels per step) against the host loop and the oracle's loop."""
+    import enf_b200 as E
+    rng = np.random.default_rng(13)
+    D, N = 128, 4000
+    X = (rng.standard_normal((D, N)) * rng.uniform(0.5, 2.0, (D, 1)) + rng.uniform(-0.5, 0.5, (D, 1))).astype(np.float32)
+
+    def init(ns):
+        r = np.random.default_rng(19)
+        one = np.ones(D, dtype=np.float32)
+        return ns.compose(ns.ScaleShiftTrafo(one.copy(), 0 * one), ns.HouseholderTrafo(r.standard_normal((D, 8)).astype(np.float32)))
+
+    Xd = E.B200Matrix.from_host(X, ctx)
+    r_dev = E.optimize_whitening(Xd, init(E), E.ADAGrad(), nbatches=5, nepochs=4, device_loop=True)
+    r_host = E.optimize_whitening(Xd, init(E), E.ADAGrad(), nbatches=5, nepochs=4)
+    r_ref = O.optimize_whitening(X.astype(np.float64), init(O), O.ADAGrad(), nbatches=5, nepochs=4)
+    hd, hh, hr = (np.array(r["negll_history"]) for r in (r_dev, r_host, r_ref))
+    assert hd.shape == hh.shape == hr.shape == (20,)
+    # the first epoch is a tight check of every step; later the (not contractive) ADAGrad trajectory amplifies the
+    # Float32 rounding of the moment matrices, so the tail gets a looser bound
+    assert np.max(np.abs(hd[:5] - hr[:5]) / (np.abs(hr[:5]) + 1)) < 1e-5
+    assert np.max(np.abs(hd[:5] - hh[:5]) / (np.abs(hh[:5]) + 1)) < 1e-5
+    assert np.max(np.abs(hd - hr) / (np.abs(hr) + 1)) < 2e-3
+    assert np.max(np.abs(hd - hh) / (np.abs(hh) + 1)) < 2e-3
+    assert hd[-1] < hd[0]                                            # it does learn
+    for a, b in zip(E.flatten(r_dev["result"]), O.flatten(r_ref["result"])):
+        for n in a.fields:
+            pa, pb = np.asarray(getattr(a, n), dtype=np.float64), np.asarray(getattr(b, n), dtype=np.float64)
+            assert np.max(np.abs(pa - pb)) < 2e-2, n
+    V = E.flatten(r_dev["result"])[0].V
+    np.testing.assert_allclose((np.asarray(V, dtype=np.float64) ** 2).sum(0), 1.0, rtol=1e-5)
+    # the chain is left consistent with the final parameters
+    v = E.mvnormal_negll_trafo(r_dev["result"], Xd)
+    v_own = float(O.mvnormal_negll_trafo(O.compose(*[type_map(O, t) for t in reversed(E.flatten(r_dev["result"]))]), X.astype(np.float64)))
+    assert abs(v - v_own) < 1e-5 * (abs(v_own) + 1)
