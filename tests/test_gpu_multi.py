@@ -59,6 +59,16 @@ WORKER = textwrap.dedent("""
     for (k, x), (_, y) in zip(flat_grads(g2, fe2), flat_grads(g2_ref, fo2)):
         y = y.reshape(x.shape)
         assert np.max(np.abs(x - y) / (np.abs(y) + np.sqrt(np.mean(y * y)) + 1e-30)) < 4e-5, k
+    # ... and the device-side fit loop on it: per-batch moment matrices all-reduced once, then identical steps on every rank
+    Xf = (np.random.default_rng(9).standard_normal((D2, 4800)) * 1.4).astype(np.float32)
+    ranges = E.batch_ranges(4800, 6)
+    mine = shard_batches(ranges, rank, world)
+    Xfl = np.concatenate([Xf[:, a:b] for a, b in mine], axis=1)
+    rf = E.optimize_whitening(E.B200Matrix.from_host(Xfl, ctx), fe2, E.ADAGrad(), nbatches=6, nepochs=2, group=True, device_loop=True)
+    rf_ref = O.optimize_whitening(Xf.astype(np.float64), fo2, O.ADAGrad(), nbatches=6, nepochs=2)
+    hf, hf_ref = np.array(rf["negll_history"]), np.array(rf_ref["negll_history"])
+    assert hf.shape == hf_ref.shape and np.max(np.abs(hf[:6] - hf_ref[:6]) / (np.abs(hf_ref[:6]) + 1)) < 1e-5, (hf, hf_ref)
+    assert np.max(np.abs(hf - hf_ref) / (np.abs(hf_ref) + 1)) < 2e-3, (hf, hf_ref)
     dist.barrier(); dist.destroy_process_group()
     print("rank", rank, "ok")
 """) % (ROOT, ROOT)
