@@ -136,21 +136,23 @@ template <class C> struct Tile {
 };
 
 // first sample (MODE_PACK: first vector) of row u of a tile, for this thread
-template <class C>
+// W = true: warp-private tiles (the forward kernels): `tile` counts tiles of SPT * (32 / G) items owned by ONE warp
+template <class C, bool W = false>
 __device__ __forceinline__ int64_t tile_item(int64_t tile, int u) {
+    if (W) return (tile * C::SPT + u) * (32 / C::G) + ((threadIdx.x & 31) >> C::LG);
     return (tile * C::SPT + u) * C::SB + (threadIdx.x >> C::LG);
 }
 
 // Loads tile `tile` of this thread.  nv[u] = number of valid samples in tile row u
 // (0/1 in the lane-group modes, 0..LN in the packed modes); invalid elements read 0.
-template <class C>
+template <class C, bool W = false>
 __device__ __forceinline__ void load_tile(const typename C::T* x, int64_t N, int D, int64_t tile,
                                           Tile<C>& t, int (&nv)[C::SPT]) {
     using T = typename C::T;
     const int g = threadIdx.x & (C::G - 1);
 #pragma unroll
     for (int u = 0; u < C::SPT; ++u) {
-        const int64_t s = tile_item<C>(tile, u);
+        const int64_t s = tile_item<C, W>(tile, u);
         if (C::PACKED) {
             const int64_t left = N - s * C::LN;
             nv[u] = left <= 0 ? 0 : (left >= C::LN ? C::LN : int(left));
@@ -181,14 +183,14 @@ __device__ __forceinline__ void load_tile(const typename C::T* x, int64_t N, int
     }
 }
 
-template <class C>
+template <class C, bool W = false>
 __device__ __forceinline__ void store_tile(typename C::T* y, int D, int64_t tile, const Tile<C>& t,
                                            const int (&nv)[C::SPT]) {
     const int g = threadIdx.x & (C::G - 1);
 #pragma unroll
     for (int u = 0; u < C::SPT; ++u) {
         if (nv[u] == 0) continue;
-        const int64_t s = tile_item<C>(tile, u);
+        const int64_t s = tile_item<C, W>(tile, u);
         if (C::PACKED) {
             if (C::MODE == MODE_PACK && nv[u] == C::LN) st16_stream(y + s * C::VE, t.v[u][0]);
             else {
@@ -472,13 +474,13 @@ __device__ __forceinline__ int64_t num_tiles(int64_t N) {
 }
 
 // per-sample ladj: finish the sum over the lanes of a group, convert from lg units, add the row constants
-template <class C>
+template <class C, bool W = false>
 __device__ __forceinline__ void store_ladj(typename C::T* ladj, int64_t tile, typename C::T (&l)[C::SPT][C::LN],
                                            const int (&nv)[C::SPT], typename C::T ladj_const) {
     using T = typename C::T;
 #pragma unroll
     for (int u = 0; u < C::SPT; ++u) {
-        const int64_t s = tile_item<C>(tile, u);
+        const int64_t s = tile_item<C, W>(tile, u);
         if (C::PACKED) {
 #pragma unroll
             for (int p = 0; p < C::LN; ++p)
@@ -742,10 +744,143 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
     }
 }
 
+
+// ------------------------------------------------------------------ warp-private rings (experiment, -DENF_WARP_RING=1)
+// Every WARP streams its own tiles (SPT * 32/G consecutive samples, 4 KB at 8 vectors per thread) through its own
+// RING-deep ring with its own mbarriers: lane 0 issues the bulk copies, the warp waits only for its own data and
+// refills a slot as soon as the warp has read it.  No warp ever waits for another warp, so the warps of a CTA drift
+// apart and their special-function-heavy (CenterStretch, Johnson) and FMA-heavy (Householder) phases interleave
+// instead of hitting the XU pipe and the issue port in lockstep.
+template <class C>
+struct WRing {
+    using T = typename C::T;
+    static constexpr bool ON = (C::MODE == MODE_VEC);
+    static constexpr int NWARP = NT / 32;
+    static constexpr int SBW = 32 / C::G;                         // items per warp row-step
+    static constexpr int TILE_SAMPLES = C::SPT * SBW;
+    static constexpr size_t STAGE_BYTES = ON ? size_t(TILE_SAMPLES) * C::DP * sizeof(T) : 0;
+    static constexpr size_t BYTES = ON ? size_t(NWARP) * RING * STAGE_BYTES + 256 : 0;   // + NWARP * RING barriers
+};
+
+template <class C, bool LADJ, class Apply>
+__device__ __forceinline__ void fwd_tile_loop_w(const typename C::T* x, typename C::T* y, typename C::T* ladj, int64_t N,
+                                                int D, typename C::T ladj_const, unsigned char* ring_smem, Apply&& apply) {
+    using T = typename C::T;
+    using R = WRing<C>;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t items = C::PACKED ? ((N + C::LN - 1) / C::LN) : N;
+    const int64_t nwt = (items + R::TILE_SAMPLES - 1) / R::TILE_SAMPLES;
+    const int64_t gw = int64_t(blockIdx.x) * R::NWARP + warp, stride = int64_t(gridDim.x) * R::NWARP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_smem + size_t(R::NWARP) * RING * R::STAGE_BYTES) + warp * RING;
+    const uint32_t stage_w = smem_u32(ring_smem) + uint32_t(warp * RING) * uint32_t(R::STAGE_BYTES);
+    auto issue = [&](int64_t wt, int slot) {      // lane 0: bulk copy of warp tile wt into this warp's slot
+        const int64_t first = wt * R::TILE_SAMPLES;
+        int64_t n = N - first;
+        if (n > R::TILE_SAMPLES) n = R::TILE_SAMPLES;
+        const uint32_t bytes = uint32_t(n) * uint32_t(D) * uint32_t(sizeof(T));
+        mbar_expect_tx(&bars[slot], bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         stage_w + uint32_t(slot) * uint32_t(R::STAGE_BYTES)),
+                     "l"(x + first * D), "r"(bytes), "r"(smem_u32(&bars[slot]))
+                     : "memory");
+    };
+    if (R::ON) {
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < RING; ++i) mbar_init(&bars[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < RING; ++i)
+                if (gw + i * stride < nwt) issue(gw + i * stride, i);
+        }
+        __syncwarp();
+    }
+    const int g = lane & (C::G - 1);
+    int k = 0;
+    for (int64_t wt = gw; wt < nwt; wt += stride, ++k) {
+        Tile<C> t;
+        int nv[C::SPT];
+        T l[C::SPT][C::LN];
+        const bool full_tile = R::ON && (wt + 1) * R::TILE_SAMPLES <= N;
+        if (R::ON) {
+            const int slot = k % RING;
+            while (!mbar_try_wait(&bars[slot], uint32_t(k / RING) & 1u)) {}
+            const uint32_t base = stage_w + uint32_t(slot) * uint32_t(R::STAGE_BYTES) +
+                                  uint32_t(((lane >> C::LG) * D + g * C::VE) * int(sizeof(T)));
+            const uint32_t ustride = uint32_t(R::SBW * D * int(sizeof(T)));
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u) {
+                nv[u] = (full_tile || tile_item<C, true>(wt, u) < N) ? 1 : 0;
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q) {
+                    if (nv[u] && (q * C::G + g) * C::VE < D) lds16(base + u * ustride + uint32_t(q * C::G * C::VE * int(sizeof(T))), t.v[u][q]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < C::VE; ++e) t.v[u][q][e] = T(0);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && wt + RING * stride < nwt) issue(wt + RING * stride, slot);   // the slot is free again
+        } else {
+            load_tile<C, true>(x, N, D, wt, t, nv);
+        }
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int p = 0; p < C::LN; ++p) l[u][p] = T(0);
+        bool bad = false;
+        apply(std::false_type{}, t, l, bad);
+        if (LADJ && __any_sync(0xffffffffu, bad)) {
+            // a Jacobian-factor product left the float range somewhere in this warp: redo the tile
+            // with per-element logs (x is still intact: the outputs have not been stored yet)
+            load_tile<C, true>(x, N, D, wt, t, nv);
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                for (int p = 0; p < C::LN; ++p) l[u][p] = T(0);
+            apply(std::true_type{}, t, l, bad);
+        }
+        if (full_tile) {
+            T* yb = y + tile_item<C, true>(wt, 0) * D + g * C::VE;
+            const int ustride = R::SBW * D;
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u) {
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q)
+                    if ((q * C::G + g) * C::VE < D) st16_stream(yb + u * ustride + q * C::G * C::VE, t.v[u][q]);
+            }
+            if (LADJ) {
+                T* lb = ladj + tile_item<C, true>(wt, 0);
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u) {
+                    const T tot = group_sum<C>(l[u][0]);
+                    if (g == 0) __stcs(lb + u * R::SBW, Prim<T>::fma_(tot, Prim<T>::LGU, ladj_const));
+                }
+            }
+        } else {
+            store_tile<C, true>(y, D, wt, t, nv);
+            if (LADJ) store_ladj<C, true>(ladj, wt, l, nv, ladj_const);
+        }
+    }
+}
+
 template <class C>
 __device__ __forceinline__ unsigned char* ring_base(unsigned char* after_consts) {
     return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(after_consts) + 127) & ~uintptr_t(127));
 }
+
+#ifndef ENF_WARP_RING
+#define ENF_WARP_RING 0   // 1: warp-private rings (fwd_tile_loop_w; measured 3 % slower, profiles/README.md), 0: one ring per CTA
+#endif
+#if ENF_WARP_RING
+template <class C> using FwdRing = WRing<C>;
+#define ENF_FWD_LOOP fwd_tile_loop_w
+#else
+template <class C> using FwdRing = Ring<C>;
+#define ENF_FWD_LOOP fwd_tile_loop
+#endif
 
 // F1/F2 of SURVEY §2.3: (f::Trafo)(x) and with_logabsdet_jacobian(f, x) for a whole chain.
 #ifndef ENF_FWD_MIN_CTAS
@@ -761,7 +896,7 @@ __global__ void __launch_bounds__(NT + 32 * ENF_PRODUCER_WARP, ENF_FWD_MIN_CTAS)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* s_c = reinterpret_cast<T*>(smem_raw);
     stage_constants<C>(desc, consts, s_c);
-    fwd_tile_loop<C, LADJ>(x, y, ladj, N, desc.D, ladj_const, ring_base<C>(smem_raw + size_t(desc.n_consts) * sizeof(T)),
+    ENF_FWD_LOOP<C, LADJ>(x, y, ladj, N, desc.D, ladj_const, ring_base<C>(smem_raw + size_t(desc.n_consts) * sizeof(T)),
                            [&](auto safe, Tile<C>& t, T (&l)[C::SPT][C::LN], bool& bad) {
                                constexpr bool SAFE = decltype(safe)::value;
                                for (int o = 0; o < desc.n_ops; ++o) apply_op_fwd<C, LADJ, SAFE>(desc.ops[o], s_c, t, l, bad);
@@ -781,7 +916,7 @@ __global__ void __launch_bounds__(NT + 32 * ENF_PRODUCER_WARP, 2) chain_fwd_stat
     stage_constants<C>(desc, consts, s_c);
     StaticStages<C, LADJ, CODES...> stages;
     stages.load(desc, s_c, 0);
-    fwd_tile_loop<C, LADJ>(x, y, ladj, N, desc.D, ladj_const, ring_base<C>(smem_raw + size_t(desc.n_consts) * sizeof(T)),
+    ENF_FWD_LOOP<C, LADJ>(x, y, ladj, N, desc.D, ladj_const, ring_base<C>(smem_raw + size_t(desc.n_consts) * sizeof(T)),
                            [&](auto safe, Tile<C>& t, T (&l)[C::SPT][C::LN], bool& bad) {
                                stages.template apply<decltype(safe)::value>(t, l, bad);
                            });

@@ -17,8 +17,8 @@ void fill_fwd(KernelSet& k) {
     k.fwd = reinterpret_cast<const void*>(&chain_fwd_kernel<CF, false>);
     k.fwd_ladj = reinterpret_cast<const void*>(&chain_fwd_kernel<CF, true>);
     k.fwd_items_per_tile = CF::SB * CF::SPT;
-    k.fwd_ring_bytes = Ring<CF>::BYTES;
-    k.fwd_threads = Ring<CF>::THREADS;
+    k.fwd_ring_bytes = FwdRing<CF>::BYTES;
+    k.fwd_threads = NT;
     k.LN = CF::LN;
 }
 

@@ -23,8 +23,8 @@ void fill(StaticKernel& k) {
     k.items_per_tile = C::SB * C::SPT;
     k.LN = C::LN;
     k.Dp = C::DP;
-    k.ring_bytes = Ring<C>::BYTES;   // + the constants block, added by the launcher
-    k.threads = Ring<C>::THREADS;
+    k.ring_bytes = FwdRing<C>::BYTES;   // + the constants block, added by the launcher
+    k.threads = NT;
 }
 
 bool same(const ChainDesc& d, std::initializer_list<int> codes) {
