@@ -871,6 +871,9 @@ __device__ __forceinline__ unsigned char* ring_base(unsigned char* after_consts)
     return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(after_consts) + 127) & ~uintptr_t(127));
 }
 
+#ifndef ENF_GRAD_SAFE_ONLY
+#define ENF_GRAD_SAFE_ONLY 0
+#endif
 #ifndef ENF_WARP_RING
 #define ENF_WARP_RING 0   // 1: warp-private rings (fwd_tile_loop_w; measured 3 % slower, profiles/README.md), 0: one ring per CTA
 #endif
@@ -1025,7 +1028,11 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
             }
             return bad;
         };
+#if ENF_GRAD_SAFE_ONLY
+        forward(std::true_type{});    // per-element logs only: more MUFU work (not the bottleneck here), half the forward code
+#else
         if (__any_sync(0xffffffffu, forward(std::false_type{}))) forward(std::true_type{});
+#endif
 #pragma unroll
         for (int u = 0; u < C::SPT; ++u) {
             T sy = T(0);
