@@ -244,8 +244,9 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
 }
 
 // sums[(D+1)*(D+1)] = [[S, m], [m^T, N]] (row-major, float64, fixed summation order), sums[(D+1)^2] = N
+// ND: row count the moments kernel ran with (D = 64 runs the 128-row kernel, rows 64.. are TMA zero fill)
 __global__ void moments_reduce_kernel(const float* __restrict__ part_s, const double* __restrict__ part_m, int n_cta,
-                                      int reps, int D, int64_t N, double* __restrict__ sums) {
+                                      int reps, int D, int ND, int64_t N, double* __restrict__ sums) {
     const int D1 = D + 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx == 0) {
@@ -256,14 +257,14 @@ __global__ void moments_reduce_kernel(const float* __restrict__ part_s, const do
         const int a = idx / D, b = idx % D;
         double s = 0.0;
         for (int c = 0; c < n_cta; ++c) {
-            const float* p = part_s + size_t(c) * D * D;
-            s += 0.5 * (double(p[size_t(a) * D + b]) + double(p[size_t(b) * D + a]));
+            const float* p = part_s + size_t(c) * ND * ND;
+            s += 0.5 * (double(p[size_t(a) * ND + b]) + double(p[size_t(b) * ND + a]));
         }
         sums[size_t(a) * D1 + b] = s;
     } else if (idx < D * D + D) {
         const int a = idx - D * D;
         double s = 0.0;
-        for (int c = 0; c < n_cta * reps; ++c) s += part_m[size_t(c) * D + a];
+        for (int c = 0; c < n_cta * reps; ++c) s += part_m[size_t(c) * ND + a];
         sums[size_t(a) * D1 + D] = s;
         sums[size_t(D) * D1 + a] = s;
     }
@@ -514,18 +515,20 @@ __global__ void __launch_bounds__(256) moments_update_kernel(const __grid_consta
 
 }  // namespace
 
-bool moments_supported(int dtype, int D) { return dtype == 0 && (D == 128 || D == 256); }
+bool moments_supported(int dtype, int D) { return dtype == 0 && (D == 64 || D == 128 || D == 256); }
 
 size_t moments_partial_bytes(int D, int sm_count) {
-    return size_t(sm_count) * D * D * sizeof(float) + size_t(sm_count) * 4 * D * sizeof(double);
+    const int ND = D < 128 ? 128 : D;
+    return size_t(sm_count) * ND * ND * sizeof(float) + size_t(sm_count) * 4 * ND * sizeof(double);
 }
 
 // d_part: moments_partial_bytes(D, sm_count) bytes of scratch; d_sums: (D+1)^2 + 1 doubles
 cudaError_t launch_moments(int D, const void* x, int64_t N, void* d_part, double* d_sums, int sm_count, cudaStream_t st) {
+    const int ND = D < 128 ? 128 : D;   // D = 64: the 128-row kernel; row groups 2, 3 lie outside the tensor map -> zero fill
     float* part_s = static_cast<float*>(d_part);
-    double* part_m = reinterpret_cast<double*>(part_s + size_t(sm_count) * D * D);
+    double* part_m = reinterpret_cast<double*>(part_s + size_t(sm_count) * ND * ND);
     const int64_t total = (N + MO_KC - 1) / MO_KC;
-    int n_cta = 0, reps = MO_SPLIT_THREADS / (D / 4);
+    int n_cta = 0, reps = MO_SPLIT_THREADS / (ND / 4);
     if (N > 0) {
         CUtensorMap mx;
         if (!make_map(&mx, x, uint64_t(N), uint64_t(D), MO_KC, 32, true)) return cudaErrorInvalidValue;
@@ -545,15 +548,15 @@ cudaError_t launch_moments(int D, const void* x, int64_t N, void* d_part, double
         }                                                                                                          \
         moments_kernel<ND><<<n_cta, MO_THREADS, smem, st>>>(mx, part_s, part_m, N, per);                           \
     }
-        if (D == 256) ENF_MOMENTS_LAUNCH(256)
-        else if (D == 128) ENF_MOMENTS_LAUNCH(128)
+        if (ND == 256) ENF_MOMENTS_LAUNCH(256)
+        else if (ND == 128) ENF_MOMENTS_LAUNCH(128)
         else return cudaErrorInvalidValue;
 #undef ENF_MOMENTS_LAUNCH
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     const int n = D * D + D;
-    moments_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part_s, part_m, n_cta, reps, D, N, d_sums);
+    moments_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(part_s, part_m, n_cta, reps, D, ND, N, d_sums);
     return cudaGetLastError();
 }
 

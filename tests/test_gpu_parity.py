@@ -377,6 +377,7 @@ def test_device_side_fit_loop_matches_host_loop(ctx, dtype):
 # ---- loss / gradients of Householder+ScaleShift chains at large D from tensor-core second moments
 @pytest.mark.gpu
 @pytest.mark.parametrize("spec,D,N", [
+    (["hh9", "ss"], 64, 2501),           # D = 64 runs the 128-row kernel (upper row groups are TMA zero fill)
     (["hh8", "ss"], 128, 3001),          # ragged: not a multiple of the 32-sample stage
     (["ss", "hh12", "ss"], 128, 40000),  # several TMEM flush periods per CTA
     (["hh64", "ss"], 256, 4100),         # C4 chain
