@@ -16,8 +16,8 @@
 // The tensor core truncates when it adds into the f32 accumulator, so TMEM is drained into a per-CTA f32
 // partial in global memory (L2-resident) every MO_FLUSH_STAGES stages; partials are summed in f64.
 //
-// Warp roles (448 threads, one CTA per SM): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
-// warps 2-5 hi/lo split + row sums (m), warps 6-13 TMEM drain.
+// Warp roles (576 threads, one CTA per SM): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
+// warps 2-9 hi/lo split + row sums (m), warps 10-17 TMEM drain.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -31,8 +31,8 @@ namespace enf {
 namespace {
 
 constexpr int MO_KC = 32;             // samples per pipeline stage = 4 UMMA k-steps (K = 8 for tf32)
-constexpr int MO_THREADS = 448;     // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-13 drain
-constexpr int MO_SPLIT_THREADS = 128;
+constexpr int MO_THREADS = 576;     // warp 0 TMA, warp 1 MMA, warps 2-9 split, warps 10-17 drain
+constexpr int MO_SPLIT_THREADS = 256;
 constexpr int MO_EPI_WARPS = 8;     // two warps per TMEM lane quarter, each drains half of the columns
 #ifndef ENF_MO_FLUSH_STAGES
 #define ENF_MO_FLUSH_STAGES 16        // 512 samples (128 truncating accumulations) per TMEM drain
@@ -49,7 +49,8 @@ struct MomSmem {
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;
     static constexpr int NH = ND / 128;                 // 128-row halves of the accumulator (UMMA M = 128)
-    static constexpr uint32_t TMEM_COLS = uint32_t(NH) * ND;   // 512 at ND = 256, 128 at ND = 128
+    static constexpr int NBUF = ND == 256 ? 1 : 2;      // accumulators: at ND = 128 the drain of one overlaps the MMAs into the other
+    static constexpr uint32_t TMEM_COLS = uint32_t(NBUF) * NH * ND;   // 512 at ND = 256, 256 at ND = 128
     static constexpr int REPS = MO_SPLIT_THREADS / (ND / 4);   // splitter threads that share the same 4 rows
 };
 
@@ -85,11 +86,11 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // TMA landed              (1 + tx)
-    uint64_t* split = full + S::STAGES;                                // xh / 2xl written        (4 warps)
+    uint64_t* split = full + S::STAGES;                                // xh / 2xl written        (8 warps)
     uint64_t* empty = split + S::STAGES;                               // MMAs of the stage done  (tcgen05.commit)
-    uint64_t* acc_full = empty + S::STAGES;                            // flush period accumulated
-    uint64_t* acc_empty = acc_full + 1;                                // TMEM drained            (4 warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* acc_full = empty + S::STAGES;                            // [NBUF] flush period accumulated
+    uint64_t* acc_empty = acc_full + S::NBUF;                          // [NBUF] TMEM drained     (8 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + S::NBUF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t total_stages = (N + MO_KC - 1) / MO_KC;
@@ -104,8 +105,10 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
             mbar_init(&split[s], MO_SPLIT_THREADS / 32);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, MO_EPI_WARPS);
+        for (int b = 0; b < S::NBUF; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], MO_EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -134,13 +137,12 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
     } else if (warp == 1) {
         // ===== MMA issuer: P[h] += Xh[h] Xh^T + Xh[h] (2 Xl)^T, both operands MN-major =====
         constexpr uint32_t idesc = make_idesc_tf32(128, ND) | (1u << 15) | (1u << 16);
-        int nflush = 0;
         for (int it = 0; it < my_stages; ++it) {
             const int s = it % S::STAGES;
             const uint32_t ph = uint32_t(it / S::STAGES) & 1u;
-            const int fs = it % MO_FLUSH_STAGES;
-            if (fs == 0 && it > 0) {
-                mbar_wait(acc_empty, uint32_t(nflush - 1) & 1u);     // the previous period has been drained
+            const int fs = it % MO_FLUSH_STAGES, period = it / MO_FLUSH_STAGES, buf = period % S::NBUF;
+            if (fs == 0 && period >= S::NBUF) {
+                mbar_wait(&acc_empty[buf], uint32_t(period / S::NBUF - 1) & 1u);   // this accumulator has been drained
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             mbar_wait(&full[s], ph);
@@ -149,6 +151,7 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
             const bool last = (fs == MO_FLUSH_STAGES - 1) || (it == my_stages - 1);
             if (lane == 0) {
                 const uint32_t xh = smem_u32(smem + size_t(s) * S::STAGE_BYTES), xl = xh + S::X_BYTES;
+                const uint32_t acc = tmem_base + uint32_t(buf * S::NH * ND);
 #pragma unroll
                 for (int j = 0; j < MO_KC / 8; ++j) {
                     const uint64_t dbh = make_desc_mn_sw128(xh + j * 1024, S::GROUP_BYTES);
@@ -156,17 +159,16 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
 #pragma unroll
                     for (int h = 0; h < S::NH; ++h) {
                         const uint64_t da = make_desc_mn_sw128(xh + h * 4 * S::GROUP_BYTES + j * 1024, S::GROUP_BYTES);
-                        umma_tf32(tmem_base + uint32_t(h * ND), da, dbh, idesc, (fs | j) != 0);
-                        umma_tf32(tmem_base + uint32_t(h * ND), da, dbl, idesc, 1);
+                        umma_tf32(acc + uint32_t(h * ND), da, dbh, idesc, (fs | j) != 0);
+                        umma_tf32(acc + uint32_t(h * ND), da, dbl, idesc, 1);
                     }
                 }
                 umma_commit(&empty[s]);
-                if (last) umma_commit(acc_full);
+                if (last) umma_commit(&acc_full[buf]);
             }
-            if (last) ++nflush;
             __syncwarp();
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + MO_SPLIT_THREADS / 32) {
         // ===== splitters: x -> xh (in place), 2 (x - xh) (second buffer); row sums for m =====
         constexpr int PAIRS = ND / 4;                                  // (row group, 16-byte chunk) pairs
         const int t = threadIdx.x - 64;
@@ -207,12 +209,13 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
     } else {
         // ===== drain: TMEM -> registers -> this CTA's partial P in global memory (store, then red.add) =====
         const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
-        const int chalf = (warp - 6) >> 2;                             // which half of the 32-column chunks
+        const int chalf = (warp - 2 - MO_SPLIT_THREADS / 32) >> 2;     // which half of the 32-column chunks
         constexpr int NCC = ND / 32 / 2;                               // chunks per warp and accumulator half
         const int nfl = (my_stages + MO_FLUSH_STAGES - 1) / MO_FLUSH_STAGES;
         float* mine = part_s + size_t(blockIdx.x) * ND * ND;
         for (int f = 0; f < nfl; ++f) {
-            mbar_wait(acc_full, uint32_t(f) & 1u);
+            const int buf = f % S::NBUF;
+            mbar_wait(&acc_full[buf], uint32_t(f / S::NBUF) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int h = 0; h < S::NH; ++h) {
@@ -222,7 +225,7 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
 #pragma unroll 1
                 for (int cc = chalf * NCC; cc < (chalf + 1) * NCC; ++cc) {
                     float v[32];
-                    tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(h * ND + cc * 32), v);
+                    tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * S::NH * ND + h * ND + cc * 32), v);
                     float* dst = colp + size_t(cc * 32) * ND;
                     if (f == 0) {
 #pragma unroll
@@ -235,7 +238,7 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -519,7 +522,7 @@ bool moments_supported(int dtype, int D) { return dtype == 0 && (D == 64 || D ==
 
 size_t moments_partial_bytes(int D, int sm_count) {
     const int ND = D < 128 ? 128 : D;
-    return size_t(sm_count) * ND * ND * sizeof(float) + size_t(sm_count) * 4 * ND * sizeof(double);
+    return size_t(sm_count) * ND * ND * sizeof(float) + size_t(sm_count) * 8 * ND * sizeof(double);
 }
 
 // d_part: moments_partial_bytes(D, sm_count) bytes of scratch; d_sums: (D+1)^2 + 1 doubles
