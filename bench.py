@@ -41,6 +41,15 @@ D_GRAD, N_GRAD_BATCH = 32, 2_500_000   # C5: 2.5e8 samples/GPU, nbatches=100
 SEED = 42
 
 
+def tensor_peak_tf32():
+    """Dense TF32 tensor peak in TFLOP/s: half of the measured cuBLAS bf16 figure (burst), else half of the nominal 2250."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["bf16_tflops"]) / 2, "measured bf16 / 2 (MEASURED_PEAKS.json)"
+    return 1125.0, "nominal bf16 / 2"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -324,6 +333,8 @@ def main():
         extras["c4_d256_k64_tensor"] = {"samples_per_s": n4 * world / (c4_ms * 1e-3), "ms_per_pass": c4_ms, "samples_per_gpu": n4,
                                         "hbm_frac": (2 * 256 + 1) * 4 * n4 / (c4_ms * 1e-3) / 1e9 / hbm_peak,
                                         "tf32_tflops_issued": flops * n4 / (c4_ms * 1e-3) / 1e12,
+                                        "tensor_frac": flops * n4 / (c4_ms * 1e-3) / 1e12 / tensor_peak_tf32()[0],
+                                        "tensor_peak": {"tflops": tensor_peak_tf32()[0], "source": tensor_peak_tf32()[1]},
                                         "path": "tcgen05.mma kind::tf32, 3xTF32 split, y = W x + c folded on the host"}
 
         # C4 gradient: loss + dV, da, db of the same chain from tensor-core second moments
@@ -350,6 +361,7 @@ def main():
             "moments_samples_per_s": n4 * world / (m4_ms * 1e-3), "moments_ms_per_pass": m4_ms, "samples_per_gpu": n4,
             "hbm_frac": 256 * 4 * n4 / (m4_ms * 1e-3) / 1e9 / hbm_peak,
             "tf32_tflops_issued": 2 * 2 * 256 * 256 * n4 / (m4_ms * 1e-3) / 1e12,
+            "tensor_frac": 2 * 2 * 256 * 256 * n4 / (m4_ms * 1e-3) / 1e12 / tensor_peak_tf32()[0],
             "ms_per_step_batch_1e5": g4_s * 1e3, "step_samples_per_s": nb4 * world / g4_s,
             "path": "tcgen05.mma kind::tf32, MN-major operands (TMA 128B/32B-atom swizzle), P = Xh Xh^T + Xh (2Xl)^T, "
                     "float64 chain rule on column-sliced CTAs; step = set_params + moments + chain rule + D2H"

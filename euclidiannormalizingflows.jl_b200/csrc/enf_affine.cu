@@ -15,8 +15,8 @@
 // the host; xl is produced per K-chunk by the four worker warps between the TMA
 // arrival and the MMA issue (layout preserving: same swizzled offset, other buffer).
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
-// elected lane), warps 2-3 = xh/xl split of every K chunk, warps 4-7 = epilogue
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
+// elected lane), warps 2-5 = xh/xl split of every K chunk, warps 6-9 = epilogue
 // (tcgen05.ld -> + c -> swizzled staging box -> TMA store; ladj = const).  Two TMEM
 // accumulators, so the epilogue of tile t overlaps the MMAs of tile t+1.
 #include <cuda.h>
@@ -35,8 +35,11 @@ namespace enf {
 namespace {
 
 constexpr int AF_TILE_M = 128;     // samples per tile (UMMA M)
-constexpr int AF_THREADS = 256;    // warp 0 TMA, warp 1 MMA, warps 2-3 split, warps 4-7 epilogue
-constexpr int AF_SPLITTERS = 64;
+#ifndef ENF_AF_SPLITTERS
+#define ENF_AF_SPLITTERS 128
+#endif
+constexpr int AF_SPLITTERS = ENF_AF_SPLITTERS;               // threads that split x into tf32 hi / lo (warps 2 ..)
+constexpr int AF_THREADS = 64 + AF_SPLITTERS + 128;          // warp 0 TMA, warp 1 MMA, split warps, 4 epilogue warps
 constexpr int AF_EPI_WARPS = 4;
 
 template <int ND, int KC>
@@ -141,7 +144,7 @@ affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 __syncwarp();
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < 2 + AF_SPLITTERS / 32) {
         // ===== splitters: x -> xh (round-to-nearest tf32, in place) and xl = x - xh (second buffer) =====
         const int wt = threadIdx.x - 64;                             // 0..63
         uint32_t it = 0;
@@ -167,7 +170,7 @@ affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     } else {
         // ===== epilogue: TMEM -> registers -> (+ c) -> swizzled staging box -> TMA store =====
         const int quarter = warp & 3;                                // TMEM lane quarter this warp may access
-        unsigned char* stage_out = smem + S::OUT_OFF + size_t(warp - 4) * 2 * S::OUT_BYTES;
+        unsigned char* stage_out = smem + S::OUT_OFF + size_t(warp - 2 - AF_SPLITTERS / 32) * 2 * S::OUT_BYTES;
         uint32_t tcount = 0, nbox = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t buf = tcount & 1;
@@ -369,7 +372,7 @@ affine2_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 }
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < 2 + AF_SPLITTERS / 32) {
         // ===== splitters (both CTAs): local x chunk -> xh (in place) and xl; signal the leader =====
         const int wt = threadIdx.x - 64;
         uint32_t it = 0;
@@ -394,7 +397,7 @@ affine2_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     } else {
         // ===== epilogue (both CTAs): own 128 rows of the accumulator =====
         const int quarter = warp & 3;
-        unsigned char* stage_out = smem + S::OUT_OFF + size_t(warp - 4) * 2 * S::OUT_BYTES;
+        unsigned char* stage_out = smem + S::OUT_OFF + size_t(warp - 2 - AF_SPLITTERS / 32) * 2 * S::OUT_BYTES;
         uint32_t tcount = 0, nbox = 0;
         for (int64_t pt = cluster_id_x(); pt < n_ptiles; pt += ncluster_id_x(), ++tcount) {
             const uint32_t buf = tcount & 1;
