@@ -26,7 +26,7 @@
 
 namespace enf {
 void affine_fold(int D, int n_ops, const int* kinds, const int* Ks, const double* const* params, std::vector<float>& wh,
-                 std::vector<float>& wl, std::vector<float>& bias);
+                 std::vector<float>& wl, std::vector<float>& bias, std::vector<uint16_t>& wb);
 }
 
 using namespace enf;
@@ -158,7 +158,7 @@ struct enf_chain {
     double* h_sums = nullptr;  // pinned, n_raw + 1
     // Householder/ScaleShift-only chains at large D: folded affine map for the tensor-core kernel (enf_affine.cu)
     bool affine = false;
-    float* d_affine = nullptr;  // Wh | Wl | bias
+    float* d_affine = nullptr;  // Wh | Wl | bias | bf16(W) | bf16(W - Wh)
     // ... and their loss/gradient from the batch's second moments (enf_moments.cu): the raw sums are
     // [[S, m], [m^T, N]] ((D+1)^2 doubles) instead of per-op sums
     bool moments = false;
@@ -329,12 +329,14 @@ int ensure_affine(enf_chain* ch) {
             pp.push_back(ch->params.data() + op.poff);
         }
         std::vector<float> wh, wl, bias;
-        affine_fold(D, int(kinds.size()), kinds.data(), Ks.data(), pp.data(), wh, wl, bias);
+        std::vector<uint16_t> wb;
+        affine_fold(D, int(kinds.size()), kinds.data(), Ks.data(), pp.data(), wh, wl, bias, wb);
         const size_t n2 = size_t(D) * D;
         // pageable source: the copies are staged before cudaMemcpyAsync returns, so the vectors may die here
         CU(ctx, cudaMemcpyAsync(ch->d_affine, wh.data(), n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaMemcpyAsync(ch->d_affine + n2, wl.data(), n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaMemcpyAsync(ch->d_affine + 2 * n2, bias.data(), size_t(D) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ch->d_affine + 2 * n2 + D, wb.data(), 2 * n2 * 2, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         ch->affine_dirty = false;
     }
@@ -853,7 +855,7 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
     }
-    if (ch->affine && (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_affine), (2 * size_t(D) * D + D) * sizeof(float))) != cudaSuccess) {
+    if (ch->affine && (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_affine), (3 * size_t(D) * D + D) * sizeof(float))) != cudaSuccess) {
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
     }

@@ -474,3 +474,31 @@ def test_device_side_fit_loop_for_second_moment_chains(ctx):
     v = E.mvnormal_negll_trafo(r_dev["result"], Xd)
     v_own = float(O.mvnormal_negll_trafo(O.compose(*[type_map(O, t) for t in reversed(E.flatten(r_dev["result"]))]), X.astype(np.float64)))
     assert abs(v - v_own) < 1e-5 * (abs(v_own) + 1)
+
+
+@pytest.mark.gpu
+def test_affine_kernel_with_bf16_correction_terms(ctx):
+    """Opt-in variant of the tensor-core forward kernel (ENF_AFFINE_BF16=1: the two correction products of the 3xTF32
+    scheme as bf16 MMAs).  The switch is read once per process, so the check runs in a child process; the error budget
+    of this mode is 2^-20 on top of the accumulation error, hence the slightly wider bound."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "import enf_b200 as E\nfrom chains import both\nfrom oracle import enf_oracle as O\n"
+        "ctx = E.default_context()\n"
+        "for D, spec, N in ((256, ['hh64', 'ss'], 4099), (128, ['ss', 'hh32'], 1000), (64, ['hh8'], 129)):\n"
+        "    fo, fe = both(spec, D, 7, np.float32)\n"
+        "    X = np.random.default_rng(8).standard_normal((D, N)).astype(np.float32)\n"
+        "    Y, L = E.with_logabsdet_jacobian(fe, E.B200Matrix.from_host(X, ctx))\n"
+        "    yr, lr = O.with_logabsdet_jacobian(fo, X.astype(np.float64))\n"
+        "    e = np.max(np.abs(Y.to_host() - yr) / (np.abs(yr) + np.sqrt(np.mean(yr ** 2))))\n"
+        "    assert e < 1.5e-5, (D, spec, e)\n"
+        "    assert np.max(np.abs(L.to_host()[0] - lr)) < 1e-4\n"
+        "print('bf16 ok')\n")
+    env = dict(os.environ, ENF_AFFINE_BF16="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "bf16 ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
