@@ -473,6 +473,16 @@ __device__ __forceinline__ int64_t num_tiles(int64_t N) {
     return (items + per_tile - 1) / per_tile;
 }
 
+template <typename T, int LN>
+__device__ __forceinline__ void store_ladj_vec16(T* dst, const T (&v)[LN]) {
+    if constexpr (sizeof(T) == 4 && LN == 4) __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+    else if constexpr (sizeof(T) == 8 && LN == 2) __stcs(reinterpret_cast<double2*>(dst), make_double2(v[0], v[1]));
+}
+template <typename T, int LN>
+__device__ __forceinline__ void store_ladj_vec8(T* dst, const T (&v)[LN]) {
+    if constexpr (sizeof(T) == 4 && LN == 2) __stcs(reinterpret_cast<float2*>(dst), make_float2(v[0], v[1]));
+}
+
 // per-sample ladj: finish the sum over the lanes of a group, convert from lg units, add the row constants
 template <class C, bool W = false>
 __device__ __forceinline__ void store_ladj(typename C::T* ladj, int64_t tile, typename C::T (&l)[C::SPT][C::LN],
@@ -482,9 +492,20 @@ __device__ __forceinline__ void store_ladj(typename C::T* ladj, int64_t tile, ty
     for (int u = 0; u < C::SPT; ++u) {
         const int64_t s = tile_item<C, W>(tile, u);
         if (C::PACKED) {
+            T vals[C::LN];
 #pragma unroll
-            for (int p = 0; p < C::LN; ++p)
-                if (p < nv[u]) __stcs(ladj + s * C::LN + p, Prim<T>::fma_(l[u][p], Prim<T>::LGU, ladj_const));
+            for (int p = 0; p < C::LN; ++p) vals[p] = Prim<T>::fma_(l[u][p], Prim<T>::LGU, ladj_const);
+            T* dst = ladj + s * C::LN;
+            // the LN values of one vector are consecutive: one 16- or 8-byte store when the row is aligned
+            if (C::LN * sizeof(T) == 16 && nv[u] == C::LN && (reinterpret_cast<uintptr_t>(ladj) & 15u) == 0) {
+                store_ladj_vec16(dst, vals);
+            } else if (C::LN * sizeof(T) == 8 && sizeof(T) == 4 && nv[u] == C::LN && (reinterpret_cast<uintptr_t>(ladj) & 7u) == 0) {
+                store_ladj_vec8(dst, vals);
+            } else {
+#pragma unroll
+                for (int p = 0; p < C::LN; ++p)
+                    if (p < nv[u]) __stcs(dst + p, vals[p]);
+            }
         } else {
             const T tot = group_sum<C>(l[u][0]);
             if (nv[u] && (threadIdx.x & (C::G - 1)) == 0) __stcs(ladj + s, Prim<T>::fma_(tot, Prim<T>::LGU, ladj_const));

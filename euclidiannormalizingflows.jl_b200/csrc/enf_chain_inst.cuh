@@ -10,10 +10,16 @@ namespace {
 #ifndef ENF_FWD_VECS
 #define ENF_FWD_VECS 8   // 16-byte vectors per thread per tile in the forward kernels
 #endif
+#ifndef ENF_FWD_VECS_DIRECT
+#define ENF_FWD_VECS_DIRECT 4   // 8 measured 0.58 instead of 0.74 of the HBM peak at D = 1
+#endif
 
 template <typename T, int LG, int CH, int MODE, int PD>
 void fill_fwd(KernelSet& k) {
-    using CF = Cfg<T, LG, CH, MODE, PD, (CH >= ENF_FWD_VECS ? 1 : ENF_FWD_VECS / CH)>;
+    // the staged (MODE_VEC) tiles carry ENF_FWD_VECS vectors per thread; modes that load straight into registers use
+    // ENF_FWD_VECS_DIRECT
+    constexpr int V = MODE == MODE_VEC ? ENF_FWD_VECS : ENF_FWD_VECS_DIRECT;
+    using CF = Cfg<T, LG, CH, MODE, PD, (CH >= V ? 1 : V / CH)>;
     k.fwd = reinterpret_cast<const void*>(&chain_fwd_kernel<CF, false>);
     k.fwd_ladj = reinterpret_cast<const void*>(&chain_fwd_kernel<CF, true>);
     k.fwd_items_per_tile = CF::SB * CF::SPT;
