@@ -65,6 +65,9 @@ struct enf_ctx {
     // NCCL group
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // peer-memory all-reduce (enf_p2p.cu): every rank's buffer mapped through CUDA IPC; off -> ncclAllReduce
+    bool p2p = false;
+    P2PDesc p2p_desc = {};
 };
 
 namespace {
@@ -645,9 +648,13 @@ extern "C" int enf_init(int device, enf_ctx** out) {
     return ENF_OK;
 }
 
+static void p2p_teardown(enf_ctx* ctx);
+
 extern "C" int enf_destroy(enf_ctx* ctx) {
     if (!ctx) return ENF_OK;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    p2p_teardown(ctx);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < HOST_SLOTS; ++i) {
@@ -1074,6 +1081,99 @@ extern "C" int enf_group_unique_id(void* id_out) {
     return ENF_OK;
 }
 
+// Map every rank's exchange buffer into this process (CUDA IPC handles travel through one ncclAllReduce(sum) of a
+// zero-padded int32 table).  Any failure just leaves ctx->p2p off: the group calls then use ncclAllReduce.
+static int p2p_setup(enf_ctx* ctx) {
+    ctx->p2p = false;
+    const int R = ctx->nranks;
+    if (R < 2 || R > P2P_MAX_RANKS || getenv("ENF_NO_P2P") != nullptr) return ENF_OK;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* local = nullptr;
+    int* d_tab = nullptr;
+    std::vector<int> tab(size_t(R) * 17, 0);           // per rank: 16 ints of handle + 1 "ok" flag
+    bool ok = cudaMalloc(&local, p2p_bytes(R)) == cudaSuccess && cudaMemset(local, 0, p2p_bytes(R)) == cudaSuccess;
+    cudaIpcMemHandle_t h;
+    ok = ok && cudaIpcGetMemHandle(&h, local) == cudaSuccess;
+    if (ok) {
+        std::memcpy(&tab[size_t(ctx->rank) * 17], &h, 64);
+        tab[size_t(ctx->rank) * 17 + 16] = 1;
+    }
+    cudaGetLastError();
+    // the table exchange is collective: every rank takes part even if its own allocation failed
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&d_tab), tab.size() * sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx, g_nccl.AllReduce(d_tab, d_tab, tab.size(), ncclInt32, ncclSum, ctx->comm, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(tab.data(), d_tab, tab.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_tab);
+    for (int r = 0; r < R; ++r) ok = ok && tab[size_t(r) * 17 + 16] == 1;
+    P2PDesc d = {};
+    d.nranks = R;
+    d.rank = ctx->rank;
+    int opened = 0;
+    for (int r = 0; ok && r < R; ++r) {
+        if (r == ctx->rank) { d.peer[r] = local; continue; }
+        cudaIpcMemHandle_t hr;
+        std::memcpy(&hr, &tab[size_t(r) * 17], 64);
+        if (cudaIpcOpenMemHandle(&d.peer[r], hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+        ++opened;
+    }
+    // all ranks must agree: one more tiny all-reduce of the outcome
+    int good = ok ? 1 : 0, *d_good = nullptr;
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&d_good), sizeof(int)));
+    CU(ctx, cudaMemcpyAsync(d_good, &good, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx, g_nccl.AllReduce(d_good, d_good, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(&good, d_good, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_good);
+    cudaGetLastError();
+    if (good == R) {
+        ctx->p2p = true;
+        ctx->p2p_desc = d;
+    } else {
+        for (int r = 0; r < R; ++r)
+            if (r != ctx->rank && d.peer[r]) cudaIpcCloseMemHandle(d.peer[r]);
+        if (local) cudaFree(local);
+        cudaGetLastError();
+    }
+    (void)opened;
+    return ENF_OK;
+}
+
+static void p2p_teardown(enf_ctx* ctx) {
+    if (!ctx->p2p) return;
+    for (int r = 0; r < ctx->nranks; ++r) {
+        if (r == ctx->rank) continue;
+        if (ctx->p2p_desc.peer[r]) cudaIpcCloseMemHandle(ctx->p2p_desc.peer[r]);
+    }
+    cudaFree(ctx->p2p_desc.peer[ctx->rank]);
+    ctx->p2p = false;
+    ctx->p2p_desc = P2PDesc{};
+    cudaGetLastError();
+}
+
+// sum `n` doubles over the group in place: peer-memory kernel when available and small enough, else ncclAllReduce
+static int group_allreduce(enf_ctx* ctx, double* d_vals, size_t n) {
+    if (ctx->p2p && n <= size_t(P2P_SLOT)) {
+        CU(ctx, launch_p2p_allreduce(ctx->p2p_desc, d_vals, int(n), ctx->stream));
+        return ENF_OK;
+    }
+    NC(ctx, g_nccl.AllReduce(d_vals, d_vals, n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    return ENF_OK;
+}
+
+// did a peer fail to show up in one of the peer-memory all-reduces since the last check? (call after a stream sync)
+static int p2p_check(enf_ctx* ctx) {
+    if (!ctx->p2p) return ENF_OK;
+    int err = 0;
+    CU(ctx, cudaMemcpy(&err, static_cast<unsigned char*>(ctx->p2p_desc.peer[ctx->rank]) + P2P_ERR_OFF, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) {
+        CU(ctx, cudaMemset(static_cast<unsigned char*>(ctx->p2p_desc.peer[ctx->rank]) + P2P_ERR_OFF, 0, sizeof(int)));
+        return fail(ctx, ENF_ERR_NCCL, "peer-memory all-reduce timed out waiting for a rank of the group");
+    }
+    return ENF_OK;
+}
+
 extern "C" int enf_group_init(enf_ctx* ctx, int nranks, int rank, const void* id_bytes) {
     if (!ctx || !id_bytes) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, ENF_ERR_INVALID, "bad rank %d of %d", rank, nranks);
@@ -1086,7 +1186,7 @@ extern "C" int enf_group_init(enf_ctx* ctx, int nranks, int rank, const void* id
     NC(ctx, g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
     ctx->nranks = nranks;
     ctx->rank = rank;
-    return ENF_OK;
+    return p2p_setup(ctx);
 }
 
 extern "C" int enf_group_destroy(enf_ctx* ctx) {
@@ -1094,6 +1194,7 @@ extern "C" int enf_group_destroy(enf_ctx* ctx) {
     if (ctx->comm) {
         CU(ctx, cudaSetDevice(ctx->device));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
+        p2p_teardown(ctx);
         NC(ctx, g_nccl.CommDestroy(ctx->comm));
         ctx->comm = nullptr;
     }
@@ -1112,10 +1213,15 @@ extern "C" int enf_negll_grad_group(enf_chain* ch, const void* x, int64_t N_loca
     // append N_local so one all-reduce also yields the global batch size
     ch->h_sums[ch->n_raw] = double(N_local);
     CU(ctx, cudaMemcpyAsync(ch->d_sums + ch->n_raw, ch->h_sums + ch->n_raw, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    NC(ctx, g_nccl.AllReduce(ch->d_sums, ch->d_sums, size_t(ch->n_raw + 1), ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    rc = group_allreduce(ctx, ch->d_sums, size_t(ch->n_raw + 1));
+    if (rc != ENF_OK) return rc;
     if (ch->moments && !host_chain_rule()) return moments_finish_device(ch, flags, negll, grads_host);   // N_global = S^[D][D]
     CU(ctx, cudaMemcpyAsync(ch->h_sums, ch->d_sums, size_t(ch->n_raw + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (std::isnan(ch->h_sums[ch->n_raw])) {      // poisoned by the peer-memory all-reduce: a rank never arrived
+        p2p_check(ctx);
+        return fail(ctx, ENF_ERR_NCCL, "peer-memory all-reduce timed out waiting for a rank of the group");
+    }
     const int64_t N_global = int64_t(std::llround(ch->h_sums[ch->n_raw]));
     return enf_negll_grad_finish(ch, ch->h_sums, N_global, flags, negll, grads_host);
 }
@@ -1341,10 +1447,9 @@ extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, i
             if (use_group) {
                 CUF(launch_reduce(ch->d_partials, blocks, ch->n_raw, ch->d_sums, false, ctx->stream));
                 CUF(cudaMemcpyAsync(ch->d_sums + ch->n_raw, d_counts + b, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-                ncclResult_t r = g_nccl.AllReduce(ch->d_sums, ch->d_sums, size_t(ch->n_raw + 1), ncclDouble, ncclSum, ctx->comm, ctx->stream);
-                if (r != ncclSuccess) {
+                if (group_allreduce(ctx, ch->d_sums, size_t(ch->n_raw + 1)) != ENF_OK) {
                     cleanup();
-                    return fail(ctx, ENF_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+                    return ENF_ERR_NCCL;
                 }
                 CUF(launch_fit_update(ch->dtype, fd, ch->d_sums, nullptr, 0, 0.0, d_lconst, d_params, d_state, eta, epsilon, flags,
                                       d_hist, d_step, ch->d_consts, ctx->stream));
@@ -1396,6 +1501,10 @@ extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, i
     CUF(cudaStreamSynchronize(ctx->stream));
 #undef CUF
     cleanup();
+    if (use_group) {
+        int prc = p2p_check(ctx);
+        if (prc != ENF_OK) return prc;
+    }
     ch->params = pfin;
     export_grads(ch, pfin, params_out);        // same packed layout / dtype conversion as gradients
     return derive_constants(ch);               // host derivation restores everything (incl. the compact-WY factors)

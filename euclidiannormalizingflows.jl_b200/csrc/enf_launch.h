@@ -60,6 +60,18 @@ cudaError_t launch_reduce(const double* partials, int n_blocks, int n_raw, doubl
                           cudaStream_t st);
 
 // affine chains on the tensor cores (enf_affine.cu)
+// peer-memory all-reduce (enf_p2p.cu): layout of a rank's buffer and the descriptor the kernel takes by value
+constexpr int P2P_MAX_RANKS = 16;
+constexpr int P2P_SLOT = 8192;                         // doubles per rank and parity
+constexpr size_t P2P_SEQ_OFF = 0, P2P_ERR_OFF = 8, P2P_FLAG_OFF = 256, P2P_DATA_OFF = 1024;
+constexpr long long P2P_SPIN_LIMIT = 4000000;          // ~1 s of waiting for a peer before giving up
+inline size_t p2p_bytes(int nranks) { return P2P_DATA_OFF + size_t(2) * nranks * P2P_SLOT * sizeof(double); }
+struct P2PDesc {
+    void* peer[P2P_MAX_RANKS];                         // peer[r]: rank r's buffer as mapped in this process
+    int nranks, rank;
+};
+cudaError_t launch_p2p_allreduce(const P2PDesc& d, double* sums, int n, cudaStream_t st);
+
 bool affine_supported(int dtype, int D, const ChainDesc& d);
 // second moments [[S, m], [m^T, N]] of a D x N batch on tensor cores (enf_moments.cu); d_part: scratch of
 // moments_partial_bytes() bytes, d_sums: (D+1)^2 + 1 doubles
