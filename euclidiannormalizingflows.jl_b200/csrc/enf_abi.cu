@@ -1444,7 +1444,13 @@ extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, i
             int blocks = 0;
             CUF(launch_grad(ch->dtype, ks, ch->desc, ch->d_consts, xb, nbt, true, ch->d_partials, ch->max_blocks, &blocks,
                             ctx->sm_count, ctx->stream));
-            if (use_group) {
+            if (use_group && ctx->p2p && size_t(ch->n_raw + 1) <= size_t(P2P_SLOT)) {
+                // sharded batch, small payload: the update kernel sums the partials, exchanges the sums with the other ranks
+                // through NVLink peer memory and applies the step - still two launches per step
+                CUF(launch_fit_update(ch->dtype, fd, ch->d_sums, ch->d_partials, blocks, double(nbt), d_lconst, d_params, d_state,
+                                      eta, epsilon, flags, d_hist, d_step, ch->d_consts, ctx->stream, &ctx->p2p_desc));
+                ctx->launches += 2;
+            } else if (use_group) {
                 CUF(launch_reduce(ch->d_partials, blocks, ch->n_raw, ch->d_sums, false, ctx->stream));
                 CUF(cudaMemcpyAsync(ch->d_sums + ch->n_raw, d_counts + b, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
                 if (group_allreduce(ctx, ch->d_sums, size_t(ch->n_raw + 1)) != ENF_OK) {

@@ -15,6 +15,7 @@
 
 #include "enf_chain.cuh"
 #include "enf_launch.h"
+#include "enf_p2p.cuh"
 
 namespace enf {
 
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256) fit_update_kernel(const __grid_constant__
                                                          double* __restrict__ lconst, double* __restrict__ params,
                                                          double* __restrict__ state, double eta, double eps, int flags,
                                                          double* __restrict__ history, long long* __restrict__ step_ctr,
-                                                         T* __restrict__ consts) {
+                                                         T* __restrict__ consts, const __grid_constant__ P2PDesc p2p) {
     const int D = fd.D;
     __shared__ double s_red[256];
     if (partials != nullptr) {
@@ -165,6 +166,11 @@ __global__ void __launch_bounds__(256) fit_update_kernel(const __grid_constant__
         }
         if (threadIdx.x == 0) sums[fd.n_raw] = count;
         __syncthreads();
+        // sharded batch: sum the raw sums (and the sample count) over the ranks through NVLink peer memory, in this kernel
+        if (p2p.nranks > 1) {
+            p2p_allreduce_block(p2p, sums, fd.n_raw + 1);
+            __syncthreads();
+        }
     }
     const double Nd = sums[fd.n_raw];
     const double LB = -1.0;
@@ -258,15 +264,18 @@ cudaError_t launch_fit_derive(int dtype, const FitDesc& fd, const double* params
     return cudaGetLastError();
 }
 
+// p2p != nullptr (and partials != nullptr): the batch is sharded over the ranks of p2p; the kernel all-reduces the sums itself
 cudaError_t launch_fit_update(int dtype, const FitDesc& fd, double* sums, const double* partials, int n_blocks, double count,
                               double* lconst, double* params, double* state, double eta, double eps, int flags,
-                              double* history, long long* step_ctr, void* consts, cudaStream_t st) {
+                              double* history, long long* step_ctr, void* consts, cudaStream_t st, const P2PDesc* p2p) {
+    P2PDesc none = {};
+    const P2PDesc& pd = p2p ? *p2p : none;
     if (dtype == 0)
         fit_update_kernel<float><<<1, 256, 0, st>>>(fd, sums, partials, n_blocks, count, lconst, params, state, eta, eps, flags,
-                                                    history, step_ctr, static_cast<float*>(consts));
+                                                    history, step_ctr, static_cast<float*>(consts), pd);
     else
         fit_update_kernel<double><<<1, 256, 0, st>>>(fd, sums, partials, n_blocks, count, lconst, params, state, eta, eps, flags,
-                                                     history, step_ctr, static_cast<double*>(consts));
+                                                     history, step_ctr, static_cast<double*>(consts), pd);
     return cudaGetLastError();
 }
 

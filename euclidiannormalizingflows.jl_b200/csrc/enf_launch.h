@@ -106,7 +106,7 @@ cudaError_t launch_fit_derive(int dtype, const FitDesc& fd, const double* params
                               cudaStream_t st);
 cudaError_t launch_fit_update(int dtype, const FitDesc& fd, double* sums, const double* partials, int n_blocks, double count,
                               double* lconst, double* params, double* state, double eta, double eps, int flags,
-                              double* history, long long* step_ctr, void* consts, cudaStream_t st);
+                              double* history, long long* step_ctr, void* consts, cudaStream_t st, const P2PDesc* p2p = nullptr);
 
 // synthetic data (enf_fill.cu)
 cudaError_t launch_fill_normal(int dtype, void* x, int D, int64_t N, int64_t col0, uint64_t seed, cudaStream_t st);
