@@ -129,7 +129,9 @@ int enf_negll(enf_chain* chain, const void* x_dev, int64_t N, double* negll_host
 /* mvnormal_negll_trafograd(trafo, X): src/optimize_whitening.jl:18-22 (Zygote
  * pullback + the rrules of src/householder_trafo.jl:22-124 and
  * src/abstract_trafo.jl:17-33).  grads_host: packed like the params, chain
- * dtype.  Blocking. */
+ * dtype.  Blocking.  Float32 chains of only Householder / ScaleShift ops at
+ * D = 64, 128, 256 take the second-moment path (tensor-core S = X X^T, chain
+ * rule on the moment matrix): x_dev must then be 16-byte aligned. */
 int enf_negll_grad(enf_chain* chain, const void* x_dev, int64_t N, int flags,
                    double* negll_host, void* grads_host);
 
@@ -145,7 +147,11 @@ int enf_negll_grad_finish(enf_chain* chain, const double* sums_host, int64_t N_g
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink ------------------------
  * The only collective on the path is the all-reduce of the loss and the
- * parameter-gradient sums.  libnccl.so.2 is dlopen'ed on first use. */
+ * parameter-gradient sums.  libnccl.so.2 is dlopen'ed on first use.
+ * enf_group_init also maps a small exchange buffer of every rank into every
+ * process (CUDA IPC); sums of up to 64 KB are then all-reduced by one kernel over
+ * NVLink peer memory, larger ones (and every one when the mapping is not
+ * possible or ENF_NO_P2P is set) by ncclAllReduce. */
 #define ENF_UNIQUE_ID_BYTES 128
 int enf_group_unique_id(void* id_out /* ENF_UNIQUE_ID_BYTES */);
 int enf_group_init(enf_ctx* ctx, int nranks, int rank, const void* id);
