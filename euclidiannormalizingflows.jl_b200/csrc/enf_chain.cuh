@@ -261,6 +261,35 @@ __device__ __forceinline__ void hh_reflect(Tile<C>& t, const typename C::T (&vk)
                     t.v[u][0][p * C::PDD + e] = Prim<T>::fma_(-d, vk[0][p * C::PDD + e], t.v[u][0][p * C::PDD + e]);
             }
     } else {
+#if ENF_F32X2
+        if constexpr (sizeof(T) == 4) {
+            // FFMA2: two rows per instruction for the dot product and for the update
+            float d[C::SPT];
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u) {
+                float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q) {
+                    a = fma2(make_float2(vk[q][0], vk[q][1]), make_float2(t.v[u][q][0], t.v[u][q][1]), a);
+                    a = fma2(make_float2(vk[q][2], vk[q][3]), make_float2(t.v[u][q][2], t.v[u][q][3]), a);
+                }
+                d[u] = a.x + a.y;
+            }
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u) d[u] = group_sum<C>(d[u]);
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u) {
+                const float2 nd = make_float2(-d[u], -d[u]);
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q) {
+                    const float2 lo = fma2(nd, make_float2(vk[q][0], vk[q][1]), make_float2(t.v[u][q][0], t.v[u][q][1]));
+                    const float2 hi = fma2(nd, make_float2(vk[q][2], vk[q][3]), make_float2(t.v[u][q][2], t.v[u][q][3]));
+                    t.v[u][q][0] = lo.x; t.v[u][q][1] = lo.y; t.v[u][q][2] = hi.x; t.v[u][q][3] = hi.y;
+                }
+            }
+            return;
+        }
+#endif
         T d[C::SPT];
 #pragma unroll
         for (int u = 0; u < C::SPT; ++u) {

@@ -89,6 +89,17 @@ template <> struct Prim<double> {
     }
 };
 
+// Packed FP32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 issue two FP32 operations per instruction).  The chain kernels
+// are bound by instruction issue and by the XU pipe, not by the FMA pipe, so pairing the FP32 work of adjacent rows
+// halves its share of the issue slots.
+#ifndef ENF_F32X2
+#define ENF_F32X2 1
+#endif
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 ld2(const float* p) { return make_float2(p[0], p[1]); }
+
 // lg(prod_i p[i]).  Fast form (SAFE = false): ONE log of the product; if the product
 // left the safe range (over/underflow), `bad` is raised and the caller recomputes the
 // whole tile with SAFE = true (sum of per-element logs).  No branch on the fast path:
@@ -158,6 +169,45 @@ template <typename T, int GR, bool LADJ, bool SAFE, bool DEFER = false>
 __device__ __forceinline__ void cs_fwd_v(T* v, const T* nb2, const T* Ah, const T* ib2, const T* c, const T* k1,
                                          const T* k2, T& l, bool& bad, T* pn = nullptr, T* pd = nullptr) {
     using P = Prim<T>;
+#if ENF_F32X2
+    if constexpr (sizeof(T) == 4 && GR == 4 && !SAFE) {
+        // two rows per FP32 instruction (same formulas as the scalar loop below)
+        float2 pn2 = make_float2(1.f, 1.f), pd2 = make_float2(1.f, 1.f);
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+            const float2 x = make_float2(v[e], v[e + 1]);
+            const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+            const float2 t = mul2(ld2(nb2 + e), ax);
+            const float2 w = make_float2(P::ex2(t.x), P::ex2(t.y));
+            const float2 ah = ld2(Ah + e);
+            const float2 m = fma2(make_float2(-ah.x, -ah.y), w, ah);
+            const float2 q = fma2(m, m, w);
+            const float2 g = add2(make_float2(P::sqrt_(q.x), P::sqrt_(q.y)), m);
+            const float2 au = fma2(make_float2(P::lg(g.x), P::lg(g.y)), ld2(ib2 + e), ax);
+            const float2 y = add2(make_float2(copysignf(au.x, x.x), copysignf(au.y, x.y)), ld2(c + e));
+            v[e] = y.x;
+            v[e + 1] = y.y;
+            if (LADJ) {
+                const float2 wg = mul2(w, g);
+                const float2 p2 = fma2(g, g, mul2(w, w));
+                pd2 = mul2(pd2, fma2(ld2(k1 + e), wg, p2));
+                pn2 = mul2(pn2, fma2(ld2(k2 + e), wg, p2));
+            }
+        }
+        if (LADJ) {
+            const float nnp = pn2.x * pn2.y, ndp = pd2.x * pd2.y;
+            if (DEFER) {
+                *pn *= nnp;
+                *pd *= ndp;
+            } else {
+                const float L = P::lg(nnp * P::rcp(ndp));
+                bad = bad || !(P::abs_(L) < P::LG_SAFE);
+                l += L;
+            }
+        }
+        return;
+    }
+#endif
     T nn[GR], nd[GR];
 #pragma unroll
     for (int e = 0; e < GR; ++e) {
@@ -220,6 +270,34 @@ template <typename T, int GR, bool LADJ, bool SAFE, bool DEFER = false>
 __device__ __forceinline__ void jo_fwd_v(T* v, const T* il, const T* c0, const T* gamma, const T* delta2, T& l,
                                          bool& bad, T* pn = nullptr) {
     using P = Prim<T>;
+#if ENF_F32X2
+    if constexpr (sizeof(T) == 4 && GR == 4 && !SAFE) {
+        float2 pr2 = make_float2(1.f, 1.f);
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+            const float2 z = fma2(make_float2(v[e], v[e + 1]), ld2(il + e), ld2(c0 + e));
+            const float2 s = fma2(z, z, make_float2(1.f, 1.f));
+            const float2 r = make_float2(P::rsq(s.x), P::rsq(s.y));
+            const float2 t = fma2(s, r, make_float2(fabsf(z.x), fabsf(z.y)));          // |z| + sqrt(1 + z^2)
+            const float2 a = make_float2(copysignf(P::lg(t.x), z.x), copysignf(P::lg(t.y), z.y));
+            const float2 y = fma2(ld2(delta2 + e), a, ld2(gamma + e));
+            v[e] = y.x;
+            v[e + 1] = y.y;
+            if (LADJ) pr2 = mul2(pr2, r);
+        }
+        if (LADJ) {
+            const float prod = pr2.x * pr2.y;
+            if (DEFER) {
+                *pn *= prod;
+            } else {
+                const float L = P::lg(prod);
+                bad = bad || !(P::abs_(L) < P::LG_SAFE);
+                l += L;
+            }
+        }
+        return;
+    }
+#endif
     T f[GR];
 #pragma unroll
     for (int e = 0; e < GR; ++e) {
