@@ -322,8 +322,21 @@ __device__ __forceinline__ void elem_fwd_q(Tile<C>& t, int q, const typename C::
 #pragma unroll
     for (int u = 0; u < C::SPT; ++u) {
         if (KIND == OP_SS) {
+#if ENF_F32X2
+            if constexpr (sizeof(T) == 4) {
 #pragma unroll
-            for (int e = 0; e < VE; ++e) t.v[u][q][e] = Prim<T>::fma_(t.v[u][q][e], k[0][e], k[1][e]);
+                for (int e = 0; e < VE; e += 2) {
+                    const float2 y = fma2(make_float2(t.v[u][q][e], t.v[u][q][e + 1]), make_float2(k[0][e], k[0][e + 1]),
+                                          make_float2(k[1][e], k[1][e + 1]));
+                    t.v[u][q][e] = y.x;
+                    t.v[u][q][e + 1] = y.y;
+                }
+            } else
+#endif
+            {
+#pragma unroll
+                for (int e = 0; e < VE; ++e) t.v[u][q][e] = Prim<T>::fma_(t.v[u][q][e], k[0][e], k[1][e]);
+            }
         } else {
 #pragma unroll
             for (int p = 0; p < VE / GR; ++p) {

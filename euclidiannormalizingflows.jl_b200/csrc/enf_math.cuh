@@ -239,6 +239,41 @@ template <typename T, int GR, bool LADJ, bool SAFE, bool DEFER = false>
 __device__ __forceinline__ void cc_fwd_v(T* v, const T* nb2, const T* A, const T* ib2, const T* c, T& l, bool& bad,
                                          T* pn = nullptr) {
     using P = Prim<T>;
+#if ENF_F32X2
+    if constexpr (sizeof(T) == 4 && GR == 4 && !SAFE) {
+        const float2 m1 = make_float2(-1.f, -1.f), one = make_float2(1.f, 1.f);
+        float2 pn2 = one, ls2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+            const float2 u = fma2(ld2(c + e), m1, make_float2(v[e], v[e + 1]));
+            const float2 au = make_float2(fabsf(u.x), fabsf(u.y));
+            const float2 t = mul2(ld2(nb2 + e), au);
+            const float2 w = make_float2(P::ex2(t.x), P::ex2(t.y));
+            const float2 a = ld2(A + e);
+            const float2 n1 = fma2(a, w, one), n2 = add2(a, w);
+            const float2 L1 = make_float2(P::lg(n1.x), P::lg(n1.y)), L2 = make_float2(P::lg(n2.x), P::lg(n2.y));
+            const float2 y = fma2(fma2(L2, m1, L1), ld2(ib2 + e), au);
+            v[e] = copysignf(y.x, u.x);
+            v[e + 1] = copysignf(y.y, u.y);
+            if (LADJ) {
+                pn2 = mul2(pn2, fma2(w, n1, n2));                  // S = n3 / (n1 n2)
+                ls2 = add2(ls2, add2(L1, L2));
+            }
+        }
+        if (LADJ) {
+            const float prod = pn2.x * pn2.y;
+            l -= ls2.x + ls2.y;
+            if (DEFER) {
+                *pn *= prod;
+            } else {
+                const float L = P::lg(prod);
+                bad = bad || !(P::abs_(L) < P::LG_SAFE);
+                l += L;
+            }
+        }
+        return;
+    }
+#endif
     T n3[GR];
     T ls = T(0);
 #pragma unroll
@@ -323,6 +358,45 @@ template <typename T, int GR, bool LADJ, bool SAFE, bool DEFER = false>
 __device__ __forceinline__ void ji_fwd_v(T* v, const T* k0, const T* k1, const T* lam, const T* xi, T& l, bool& bad,
                                          T* pn = nullptr) {
     using P = Prim<T>;
+#if ENF_F32X2
+    if constexpr (sizeof(T) == 4 && GR == 4 && !SAFE) {
+        const float2 half = make_float2(0.5f, 0.5f), mhalf = make_float2(-0.5f, -0.5f);
+        float2 pc2 = make_float2(1.f, 1.f);
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+            const float2 sa = fma2(make_float2(v[e], v[e + 1]), ld2(k0 + e), ld2(k1 + e));
+            const float2 ex = make_float2(P::ex2(sa.x), P::ex2(sa.y));
+            const float2 ei = make_float2(P::rcp(ex.x), P::rcp(ex.y));
+            const float2 he = mul2(ex, half);
+            float2 sh = fma2(ei, mhalf, he);
+            const float2 ch = fma2(ei, half, he);
+            // (e - 1/e)/2 cancels for small arguments: odd Taylor polynomial in sa (same as Prim<float>::sinhcosh)
+            const float2 s2 = mul2(sa, sa);
+            float2 pl = fma2(s2, make_float2(1.0178086e-7f, 1.0178086e-7f), make_float2(1.5252734e-5f, 1.5252734e-5f));
+            pl = fma2(s2, pl, make_float2(1.3333558e-3f, 1.3333558e-3f));
+            pl = fma2(s2, pl, make_float2(5.5504109e-2f, 5.5504109e-2f));
+            pl = fma2(s2, pl, make_float2(0.69314718f, 0.69314718f));
+            const float2 sp = mul2(sa, pl);
+            sh.x = fabsf(sa.x) < 0.55f ? sp.x : sh.x;
+            sh.y = fabsf(sa.y) < 0.55f ? sp.y : sh.y;
+            const float2 y = fma2(ld2(lam + e), sh, ld2(xi + e));
+            v[e] = y.x;
+            v[e + 1] = y.y;
+            pc2 = mul2(pc2, ch);
+        }
+        if (LADJ) {
+            const float prod = pc2.x * pc2.y;
+            if (DEFER) {
+                *pn *= prod;
+            } else {
+                const float L = P::lg(prod);
+                bad = bad || !(P::abs_(L) < P::LG_SAFE);
+                l += L;
+            }
+        }
+        return;
+    }
+#endif
     T chs[GR];
 #pragma unroll
     for (int e = 0; e < GR; ++e) {
