@@ -998,6 +998,44 @@ __device__ __forceinline__ void bwd_elem(const Tile<C>& xt, const Tile<C>& yt, T
                                          const typename C::T (&c4)[C::VE], const typename C::T (&c5)[C::VE],
                                          typename C::T (&ra)[4][C::VE]) {
     using T = typename C::T;
+#if ENF_F32X2
+    if constexpr (sizeof(T) == 4) {
+        // two rows per FP32 instruction: the same templates instantiated for the pair type F2
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int e = 0; e < C::VE; e += 2) {
+                auto pr = [&](const float (&a)[C::VE]) { return F2(a[e], a[e + 1]); };
+                F2 r[4] = {F2(0.f), F2(0.f), F2(0.f), F2(0.f)};
+                const F2 xin(xt.v[u][q][e], xt.v[u][q][e + 1]), yout(yt.v[u][q][e], yt.v[u][q][e + 1]);
+                const F2 G(gt.v[u][q][e], gt.v[u][q][e + 1]);
+                F2 gx;
+                if (KIND == OP_SS) {
+                    r[0] = G * xin;
+                    r[1] = G;
+                    gx = G * pr(c0);
+                } else if (KIND == OP_CS) {
+                    gx = cs_bwd<F2>(xin, yout, G, pr(c0), pr(c1), pr(c2), pr(c3), pr(c4), pr(c5), r);
+                } else if (KIND == OP_CC) {
+                    gx = cc_bwd<F2>(xin, yout, G, pr(c0), pr(c1), pr(c2), pr(c3), pr(c4), pr(c5), r);
+                } else if (KIND == OP_JO) {
+                    gx = jo_bwd<F2>(xin, yout, G, pr(c0), pr(c1), pr(c4), r);
+                } else {
+                    gx = ji_bwd<F2>(xin, yout, G, pr(c0), pr(c1), pr(c2), pr(c3), pr(c4), pr(c5), r);
+                }
+                gt.v[u][q][e] = gx.v.x;
+                gt.v[u][q][e + 1] = gx.v.y;
+                const float2 mm = make_float2(m[u][C::slot(e)], m[u][C::slot(e + 1)]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 acc = fma2(mm, r[k].v, make_float2(ra[k][e], ra[k][e + 1]));
+                    ra[k][e] = acc.x;
+                    ra[k][e + 1] = acc.y;
+                }
+            }
+        return;
+    }
+#endif
 #pragma unroll
     for (int u = 0; u < C::SPT; ++u)
 #pragma unroll

@@ -49,6 +49,7 @@ template <> struct Prim<float> {
     }
     static __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
     static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float sign_(float x) { return x < 0.f ? -1.f : 1.f; }
     static __device__ __forceinline__ float csign(float mag, float sgn) { return copysignf(mag, sgn); }
     // lg(|z| + sqrt(1+z^2)) * sign(z), given s = 1 + z^2 and r = rsqrt(s)   [asinh(z) / LGU]
     static __device__ __forceinline__ float asinh_lg(float z, float s, float r) {
@@ -81,6 +82,7 @@ template <> struct Prim<double> {
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
     static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+    static __device__ __forceinline__ double sign_(double x) { return x < 0.0 ? -1.0 : 1.0; }
     static __device__ __forceinline__ double csign(double mag, double sgn) { return copysign(mag, sgn); }
     static __device__ __forceinline__ double asinh_lg(double z, double s, double r) { return asinh(z); }
     static __device__ __forceinline__ void sinhcosh(double sa, double& sh, double& ch) {
@@ -412,6 +414,31 @@ __device__ __forceinline__ void ji_fwd_v(T* v, const T* k0, const T* k1, const T
     }
 }
 
+// A pair of float rows as one value: the backward formulas below are written once and instantiated for T = float,
+// double and F2 (two rows per FFMA2 / FMUL2 / FADD2; MUFU per half).
+struct F2 {
+    float2 v;
+    __device__ __forceinline__ F2() {}
+    __device__ __forceinline__ F2(float a) : v(make_float2(a, a)) {}
+    __device__ __forceinline__ F2(float a, float b) : v(make_float2(a, b)) {}
+    __device__ __forceinline__ explicit F2(float2 a) : v(a) {}
+};
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) { return F2(add2(a.v, b.v)); }
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) { return F2(mul2(a.v, b.v)); }
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return F2(fma2(b.v, make_float2(-1.f, -1.f), a.v)); }
+__device__ __forceinline__ F2 operator-(F2 a) { return F2(make_float2(-a.v.x, -a.v.y)); }
+template <>
+struct Prim<F2> {
+    using S = Prim<float>;
+    static constexpr float LGU = S::LGU, INV_LGU = S::INV_LGU;
+    static __device__ __forceinline__ F2 ex2(F2 x) { return F2(S::ex2(x.v.x), S::ex2(x.v.y)); }
+    static __device__ __forceinline__ F2 rcp(F2 x) { return F2(S::rcp(x.v.x), S::rcp(x.v.y)); }
+    static __device__ __forceinline__ F2 rsq(F2 x) { return F2(S::rsq(x.v.x), S::rsq(x.v.y)); }
+    static __device__ __forceinline__ F2 fma_(F2 a, F2 b, F2 c) { return F2(fma2(a.v, b.v, c.v)); }
+    static __device__ __forceinline__ F2 abs_(F2 x) { return F2(fabsf(x.v.x), fabsf(x.v.y)); }
+    static __device__ __forceinline__ F2 sign_(F2 x) { return F2(x.v.x < 0.f ? -1.f : 1.f, x.v.y < 0.f ? -1.f : 1.f); }
+};
+
 // ---------------------------------------------------------------- backward
 // Every *_bwd takes the op's INPUT x, its OUTPUT y (both are at hand in the reverse sweep: y is the
 // input of the next op) and the output cotangent G; it returns the input cotangent and writes the
@@ -456,7 +483,7 @@ __device__ __forceinline__ T cc_bwd(T x, T y, T G, T nb2, T A, T ib2, T c, T a, 
     const T ib = ib2 * P::INV_LGU;
     const T u = x - c;
     const T au = P::abs_(u);
-    const T sg = u < T(0) ? T(-1) : T(1);
+    const T sg = P::sign_(u);
     T s1au, s2au;
     const CcParts<T> k = cc_parts<T>(au, P::ex2(nb2 * au), A, a, b, s1au, s2au);
     const T ya_b = (s1au + s2au - P::abs_(y)) * ib;
@@ -475,7 +502,7 @@ __device__ __forceinline__ T cs_bwd(T x, T y, T G, T nb2, T A, T ib2, T c, T a, 
     const T ib = ib2 * P::INV_LGU;
     const T u = y - c;
     const T au = P::abs_(u);
-    const T sg = x < T(0) ? T(-1) : T(1);
+    const T sg = P::sign_(x);
     T s1au, s2au;
     const CcParts<T> k = cc_parts<T>(au, P::ex2(nb2 * au), A, a, b, s1au, s2au);
     const T Cb = (s1au + s2au - P::abs_(x)) * ib;
