@@ -1192,6 +1192,48 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
                                 }
                                 a2 = P::fma_(pm, qd, a2);
                             }
+                    } else if constexpr (ENF_F32X2 && sizeof(T) == 4) {
+                        // two rows per FFMA2 (same arithmetic as the scalar branch below)
+                        float po[C::SPT], qd[C::SPT];
+#pragma unroll
+                        for (int u = 0; u < C::SPT; ++u) {
+                            float2 ap = make_float2(0.f, 0.f), aq = make_float2(0.f, 0.f);
+#pragma unroll
+                            for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                                for (int e = 0; e < VE; e += 2) {
+                                    const float2 v2 = make_float2(vk[q][e], vk[q][e + 1]);
+                                    ap = fma2(v2, make_float2(zt.v[u][q][e], zt.v[u][q][e + 1]), ap);
+                                    aq = fma2(v2, make_float2(gt.v[u][q][e], gt.v[u][q][e + 1]), aq);
+                                }
+                            po[u] = ap.x + ap.y;
+                            qd[u] = aq.x + aq.y;
+                        }
+#pragma unroll
+                        for (int u = 0; u < C::SPT; ++u) {
+                            po[u] = group_sum<C>(po[u]);
+                            qd[u] = group_sum<C>(qd[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < C::SPT; ++u) {
+                            const float pm = -po[u] * m[u][0], qm = qd[u] * m[u][0];
+                            const float2 npo = make_float2(-po[u], -po[u]), nqd = make_float2(-qd[u], -qd[u]);
+                            const float2 pm2 = make_float2(pm, pm), qm2 = make_float2(qm, qm);
+#pragma unroll
+                            for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                                for (int e = 0; e < VE; e += 2) {
+                                    const float2 v2 = make_float2(vk[q][e], vk[q][e + 1]);
+                                    const float2 g2 = make_float2(gt.v[u][q][e], gt.v[u][q][e + 1]);
+                                    const float2 z2 = fma2(npo, v2, make_float2(zt.v[u][q][e], zt.v[u][q][e + 1]));  // reflection input
+                                    const float2 a2v = fma2(pm2, g2, fma2(qm2, z2, make_float2(a1[q][e], a1[q][e + 1])));
+                                    const float2 gn = fma2(nqd, v2, g2);
+                                    zt.v[u][q][e] = z2.x; zt.v[u][q][e + 1] = z2.y;
+                                    a1[q][e] = a2v.x; a1[q][e + 1] = a2v.y;
+                                    gt.v[u][q][e] = gn.x; gt.v[u][q][e + 1] = gn.y;
+                                }
+                            a2 = P::fma_(pm, qd[u], a2);
+                        }
                     } else {
                         T po[C::SPT], qd[C::SPT];
 #pragma unroll
