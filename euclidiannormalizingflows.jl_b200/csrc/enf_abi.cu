@@ -26,7 +26,7 @@
 
 namespace enf {
 void affine_fold(int D, int n_ops, const int* kinds, const int* Ks, const double* const* params, std::vector<float>& wh,
-                 std::vector<float>& wl, std::vector<float>& bias, std::vector<uint16_t>& wb);
+                 std::vector<float>& wl, std::vector<float>& bias);
 }
 
 using namespace enf;
@@ -161,7 +161,7 @@ struct enf_chain {
     double* h_sums = nullptr;  // pinned, n_raw + 1
     // Householder/ScaleShift-only chains at large D: folded affine map for the tensor-core kernel (enf_affine.cu)
     bool affine = false;
-    float* d_affine = nullptr;  // Wh | Wl | bias | bf16(W) | bf16(W - Wh)
+    float* d_affine = nullptr;  // Wh | Wl | bias
     // ... and their loss/gradient from the batch's second moments (enf_moments.cu): the raw sums are
     // [[S, m], [m^T, N]] ((D+1)^2 doubles) instead of per-op sums
     bool moments = false;
@@ -261,40 +261,18 @@ int derive_constants(enf_chain* ch) {
             }
         }
         if (op.kind == OP_HH) {
-            // V' (K arrays) and the compact-WY factor M = V' T^T (K arrays):  H_K ... H_1 = I - M V'^T, with
-            // T upper triangular, T_jj = 1, T_{1:j-1,j} = -T_{1:j-1,1:j-1} V'^T_{1:j-1} v'_j  (tau = 1 for the
-            // pre-scaled v').  Used by the blocked Householder update of the static kernels.
-            const int K = op.K;
-            std::vector<double> Vp(size_t(D) * K), T(size_t(K) * K, 0.0), M(size_t(D) * K, 0.0);
-            for (int k = 0; k < K; ++k) {
+            // v'_k = v_k sqrt(2 / v_k.v_k): y = x - (v'.x) v' (src/householder_trafo.jl:4-11 without the division)
+            for (int k = 0; k < op.K; ++k) {
                 const double* v = p + size_t(k) * D;
                 double n = 0.0;
                 for (int j = 0; j < D; ++j) n += v[j] * v[j];
                 const double sc = std::sqrt(2.0 / n);
-                for (int j = 0; j < D; ++j) Vp[size_t(k) * D + j] = v[j] * sc;
-            }
-            for (int j = 0; j < K; ++j) {
-                T[size_t(j) * K + j] = 1.0;
-                std::vector<double> w(j, 0.0);
-                for (int i = 0; i < j; ++i)
-                    for (int r = 0; r < D; ++r) w[i] += Vp[size_t(i) * D + r] * Vp[size_t(j) * D + r];
-                for (int i = 0; i < j; ++i) {
-                    double a = 0.0;
-                    for (int m2 = i; m2 < j; ++m2) a += T[size_t(i) * K + m2] * w[m2];
-                    T[size_t(i) * K + j] = -a;
-                }
-            }
-            // Q = H_1 ... H_K = I - V' T V'^T ;  y = H_K ... H_1 x = Q^T x = x - V' T^T (V'^T x) = x - M (V'^T x)
-            for (int k = 0; k < K; ++k)
-                for (int i = 0; i <= k; ++i)            // M[:,i] += T[i][k] ... M = V' T^T : M[:,c] = sum_k V'[:,k] T[c][k]
-                    for (int r = 0; r < D; ++r) M[size_t(i) * D + r] += Vp[size_t(k) * D + r] * T[size_t(i) * K + k];
-            for (int k = 0; k < K; ++k)
                 for (int r = 0; r < Dp; ++r) {
                     const bool real = packed || r < D;
                     const int i = packed ? r % D : r;
-                    set(size_t(dop.coff) + size_t(k) * Dp + r, real ? Vp[size_t(k) * D + i] : 0.0);
-                    set(size_t(dop.coff) + size_t(K + k) * Dp + r, real ? M[size_t(k) * D + i] : 0.0);
+                    set(size_t(dop.coff) + size_t(k) * Dp + r, real ? v[i] * sc : 0.0);
                 }
+            }
         }
     }
     CU(ctx, cudaMemcpyAsync(ch->d_consts, ch->h_consts, size_t(ch->desc.n_consts) * elem_size(ch->dtype),
@@ -332,14 +310,12 @@ int ensure_affine(enf_chain* ch) {
             pp.push_back(ch->params.data() + op.poff);
         }
         std::vector<float> wh, wl, bias;
-        std::vector<uint16_t> wb;
-        affine_fold(D, int(kinds.size()), kinds.data(), Ks.data(), pp.data(), wh, wl, bias, wb);
+        affine_fold(D, int(kinds.size()), kinds.data(), Ks.data(), pp.data(), wh, wl, bias);
         const size_t n2 = size_t(D) * D;
         // pageable source: the copies are staged before cudaMemcpyAsync returns, so the vectors may die here
         CU(ctx, cudaMemcpyAsync(ch->d_affine, wh.data(), n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaMemcpyAsync(ch->d_affine + n2, wl.data(), n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaMemcpyAsync(ch->d_affine + 2 * n2, bias.data(), size_t(D) * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(ch->d_affine + 2 * n2 + D, wb.data(), 2 * n2 * 2, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         ch->affine_dirty = false;
     }
@@ -862,7 +838,7 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
     }
-    if (ch->affine && (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_affine), (3 * size_t(D) * D + D) * sizeof(float))) != cudaSuccess) {
+    if (ch->affine && (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_affine), (2 * size_t(D) * D + D) * sizeof(float))) != cudaSuccess) {
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
     }
@@ -937,13 +913,6 @@ static int forward_impl(enf_chain* ch, const void* x, int64_t N, void* y, void* 
         int rca = ensure_affine(ch);
         if (rca != ENF_OK) return rca;
         CU(ctx, launch_affine(ch->D, ch->d_affine, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));
-        ctx->launches += 1;
-        return ENF_OK;
-    }
-    StaticKernel sk;
-    if (select_static(ch->dtype, ch->desc, mode, sk)) {
-        CU(ctx, launch_fwd_static(ch->dtype, sk, ch->desc, ch->d_consts, x, y, want_ladj ? ladj : nullptr, N, lc,
-                                  ctx->sm_count, st));
         ctx->launches += 1;
         return ENF_OK;
     }
@@ -1513,5 +1482,5 @@ extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, i
     }
     ch->params = pfin;
     export_grads(ch, pfin, params_out);        // same packed layout / dtype conversion as gradients
-    return derive_constants(ch);               // host derivation restores everything (incl. the compact-WY factors)
+    return derive_constants(ch);
 }

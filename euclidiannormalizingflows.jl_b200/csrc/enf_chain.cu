@@ -142,26 +142,6 @@ cudaError_t launch_fwd(int dtype, const KernelSet& k, const ChainDesc& desc, con
     return cudaLaunchKernel(fn, dim3(grid), dim3(k.fwd_threads), args, smem, st);
 }
 
-cudaError_t launch_fwd_static(int dtype, const StaticKernel& k, const ChainDesc& desc, const void* consts,
-                              const void* x, void* y, void* ladj, int64_t N, double ladj_const, int sm_count,
-                              cudaStream_t st) {
-    if (N <= 0) return cudaSuccess;
-    const void* fn = ladj ? k.fwd_ladj : k.fwd;
-    const size_t smem = fwd_smem_bytes(dtype, desc) + (k.ring_bytes ? k.ring_bytes + 128 : 0);
-    int per_sm = 0;
-    cudaError_t e = prepare_kernel(fn, smem, per_sm, k.threads);
-    if (e != cudaSuccess) return e;
-    const int64_t items = (N + k.LN - 1) / k.LN;
-    const int64_t tiles = (items + k.items_per_tile - 1) / k.items_per_tile;
-    const int64_t cap = int64_t(per_sm) * sm_count;
-    const unsigned grid = unsigned(tiles < cap ? tiles : cap);
-    float lc32 = float(ladj_const);
-    double lc64 = ladj_const;
-    void* args[] = {const_cast<ChainDesc*>(&desc), &consts, &x, &y, &ladj, &N,
-                    dtype == 0 ? static_cast<void*>(&lc32) : static_cast<void*>(&lc64)};
-    return cudaLaunchKernel(fn, dim3(grid), dim3(k.threads), args, smem, st);
-}
-
 cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
                         int64_t N, bool grad, double* partials, int max_blocks, int* blocks_used, int sm_count,
                         cudaStream_t st) {

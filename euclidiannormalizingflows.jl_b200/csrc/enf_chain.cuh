@@ -53,7 +53,7 @@ struct ChainDesc {
 };
 
 __host__ __device__ constexpr int n_consts_of(int kind, int K) {
-    return (kind == OP_CS || kind == OP_CC) ? 9 : kind == OP_JO ? 5 : kind == OP_JI ? 6 : kind == OP_SS ? 2 : 2 * K;   // HH: V' and M = V' T^T
+    return (kind == OP_CS || kind == OP_CC) ? 9 : kind == OP_JO ? 5 : kind == OP_JI ? 6 : kind == OP_SS ? 2 : K;   // HH: the pre-scaled v'_k
 }
 __host__ __device__ constexpr int n_rowslots_of(int kind, int K) {
     return (kind == OP_CS || kind == OP_CC) ? 3 : (kind == OP_JO || kind == OP_JI) ? 4 : kind == OP_SS ? 2 : K;
@@ -380,50 +380,6 @@ __device__ __forceinline__ void elem_fwd_from(const typename C::T* cb, Tile<C>& 
     }
 }
 
-// blocked Householder stack: K reflections as ONE rank-K update  y = x - M (V'^T x)  (compact WY form with
-// M = V' T^T folded on the host).  Same FMA count as K sequential reflections, but the K dot products are
-// independent, so their shuffle reductions overlap instead of forming a chain of K dependent round trips.
-template <class C, int K>
-__device__ __forceinline__ void hh_block(Tile<C>& t, const typename C::T* vb, const typename C::T* mb) {
-    using T = typename C::T;
-    constexpr int VE = C::VE;
-    static_assert(!C::PACKED, "blocked Householder is for the lane-group layouts");
-    T d[C::SPT][K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        T vk[C::CH][VE];
-#pragma unroll
-        for (int q = 0; q < C::CH; ++q) ld16_shared(vb + k * C::DP + const_off<C>(q), vk[q]);
-#pragma unroll
-        for (int u = 0; u < C::SPT; ++u) {
-            T a = T(0);
-#pragma unroll
-            for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                for (int e = 0; e < VE; ++e) a = Prim<T>::fma_(vk[q][e], t.v[u][q][e], a);
-            d[u][k] = a;
-        }
-    }
-#pragma unroll
-    for (int off = C::G / 2; off > 0; off >>= 1)
-#pragma unroll
-        for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-            for (int k = 0; k < K; ++k) d[u][k] += __shfl_xor_sync(0xffffffffu, d[u][k], off);
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        T mk[C::CH][VE];
-#pragma unroll
-        for (int q = 0; q < C::CH; ++q) ld16_shared(mb + k * C::DP + const_off<C>(q), mk[q]);
-#pragma unroll
-        for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-            for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                for (int e = 0; e < VE; ++e) t.v[u][q][e] = Prim<T>::fma_(-d[u][k], mk[q][e], t.v[u][q][e]);
-    }
-}
-
 // interpretive dispatch: the op list is data (ChainDesc), constants come from shared memory
 template <class C, bool LADJ, bool SAFE>
 __device__ __forceinline__ void apply_op_fwd(const DevOp& op, const typename C::T* s_c, Tile<C>& t,
@@ -432,8 +388,6 @@ __device__ __forceinline__ void apply_op_fwd(const DevOp& op, const typename C::
     const T* cb = s_c + op.coff;
     switch (op.kind) {
         case OP_HH:
-            // (the rank-K block update hh_block<> measured 2-5 % slower here than K sequential reflections: the
-            // extra live dot products cost more registers than the overlapped reductions save; profiles/README.md)
 #pragma unroll HH_UNROLL
             for (int k = 0; k < op.K; ++k) {
                 T vk[C::CH][C::VE];
@@ -449,58 +403,6 @@ __device__ __forceinline__ void apply_op_fwd(const DevOp& op, const typename C::
         default: elem_fwd_from<C, OP_JI, LADJ, SAFE>(cb, t, l, bad); break;
     }
 }
-
-// ------------------------------------------------------------------ static chains
-// The same ops with the op list as a template parameter pack (CODE = kind | K << 8):
-// no dispatch, Householder loops unrolled, and every per-row constant of the lane
-// lives in registers for the whole kernel (the lane's rows never change).  Used for
-// the chain shapes in the registry of enf_chain_static.cu; everything else runs
-// the interpretive kernel above.
-template <class C, int CODE, bool LADJ> struct StaticOp {
-    using T = typename C::T;
-    static constexpr int KIND = CODE & 0xff;
-    static constexpr int K = CODE >> 8;
-    const T* cb;   // this op's constants in shared memory
-    __device__ __forceinline__ void load(const T* s_c, const DevOp& op) { cb = s_c + op.coff; }
-    template <bool SAFE>
-    __device__ __forceinline__ void apply(Tile<C>& t, T (&l)[C::SPT][C::LN], bool& bad) const {
-        if (KIND == OP_HH) {
-            if constexpr (K >= 2 && K <= 8 && !C::PACKED) {
-                hh_block<C, K>(t, cb, cb + K * C::DP);   // V' then M = V' T^T
-            } else {
-#pragma unroll 1
-                for (int j = 0; j < K; ++j) {
-                    T vk[C::CH][C::VE];
-#pragma unroll
-                    for (int q = 0; q < C::CH; ++q) ld16_shared(cb + j * C::DP + const_off<C>(q), vk[q]);
-                    hh_reflect<C>(t, vk);
-                }
-            }
-        } else {
-            elem_fwd_from<C, KIND, LADJ, SAFE>(cb, t, l, bad);
-        }
-    }
-};
-
-template <class C, bool LADJ, int... CODES> struct StaticStages;
-template <class C, bool LADJ> struct StaticStages<C, LADJ> {
-    __device__ __forceinline__ void load(const ChainDesc&, const typename C::T*, int) {}
-    template <bool SAFE>
-    __device__ __forceinline__ void apply(Tile<C>&, typename C::T (&)[C::SPT][C::LN], bool&) const {}
-};
-template <class C, bool LADJ, int CODE, int... REST> struct StaticStages<C, LADJ, CODE, REST...> {
-    StaticOp<C, CODE, LADJ> op;
-    StaticStages<C, LADJ, REST...> rest;
-    __device__ __forceinline__ void load(const ChainDesc& d, const typename C::T* s_c, int idx) {
-        op.load(s_c, d.ops[idx]);
-        rest.load(d, s_c, idx + 1);
-    }
-    template <bool SAFE>
-    __device__ __forceinline__ void apply(Tile<C>& t, typename C::T (&l)[C::SPT][C::LN], bool& bad) const {
-        op.template apply<SAFE>(t, l, bad);
-        rest.template apply<SAFE>(t, l, bad);
-    }
-};
 
 template <class C>
 __device__ __forceinline__ void stage_constants(const ChainDesc& desc, const typename C::T* consts, typename C::T* s_c) {
@@ -566,9 +468,6 @@ __device__ __forceinline__ void store_ladj(typename C::T* ladj, int64_t tile, ty
 #define ENF_RING 2   // 2 x 32 KB stages per CTA (8 vectors per thread), 3 CTAs per SM
 #endif
 constexpr int RING = ENF_RING;
-#ifndef ENF_PRODUCER_WARP
-#define ENF_PRODUCER_WARP 0   // 1: dedicated TMA producer warp (+32 threads per CTA); 0: thread 0 also feeds the ring
-#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -608,8 +507,7 @@ struct Ring {
     static constexpr int TILE_SAMPLES = C::SPT * C::SB;
     static constexpr size_t STAGE_BYTES = ON ? size_t(TILE_SAMPLES) * C::DP * sizeof(T) : 0;   // D <= DP
     static constexpr size_t BYTES = ON ? RING * STAGE_BYTES + 128 : 0;                          // + barriers
-    static constexpr int THREADS = (ON && ENF_PRODUCER_WARP) ? NT + 32 : NT;                     // + producer warp
-};
+    };
 
 // issue the bulk copy of tile `tile` into ring slot `slot` (one thread)
 template <class C>
@@ -719,24 +617,6 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         __syncthreads();
-#if ENF_PRODUCER_WARP
-        if (threadIdx.x >= NT) {
-            // producer warp: one lane keeps the ring full; the compute warps never synchronise with
-            // each other, only with the data (warp-specialised, like the TMA warp of a GEMM)
-            if (threadIdx.x == NT) {
-                int k = 0;
-                for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x, ++k) {
-                    const int slot = k % RING;
-                    if (k >= RING) {
-                        const uint32_t parity = uint32_t(k / RING - 1) & 1u;
-                        while (!mbar_try_wait(&empty[slot], parity)) {}
-                    }
-                    ring_issue<C>(x, N, D, tile, stage0, full, slot);
-                }
-            }
-            return;
-        }
-#else
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int i = 0; i < RING; ++i) {
@@ -744,7 +624,6 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
                 if (tl < nt) ring_issue<C>(x, N, D, tl, stage0, full, i);
             }
         }
-#endif
     }
     int k = 0;
     for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x, ++k) {
@@ -756,7 +635,6 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
         if (Ring<C>::ON) {
             const int slot = k % RING;
             const uint32_t parity = uint32_t(k / RING) & 1u;
-#if !ENF_PRODUCER_WARP
             // thread 0 refills the slot every warp finished reading one iteration ago (tile k-1 -> tile k-1+RING):
             // it only ever waits for warps that are more than a whole tile behind
             if (threadIdx.x == 0 && k >= 1) {
@@ -767,7 +645,6 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
                     ring_issue<C>(x, N, D, nxt, stage0, full, ps);
                 }
             }
-#endif
             while (!mbar_try_wait(&full[slot], parity)) {}
             if (full_tile) {
                 ring_read_full<C>(stage0_u32 + uint32_t(slot) * uint32_t(Ring<C>::STAGE_BYTES), D, t);
@@ -808,127 +685,6 @@ __device__ __forceinline__ void fwd_tile_loop(const typename C::T* x, typename C
 }
 
 
-// ------------------------------------------------------------------ warp-private rings (experiment, -DENF_WARP_RING=1)
-// Every WARP streams its own tiles (SPT * 32/G consecutive samples, 4 KB at 8 vectors per thread) through its own
-// RING-deep ring with its own mbarriers: lane 0 issues the bulk copies, the warp waits only for its own data and
-// refills a slot as soon as the warp has read it.  No warp ever waits for another warp, so the warps of a CTA drift
-// apart and their special-function-heavy (CenterStretch, Johnson) and FMA-heavy (Householder) phases interleave
-// instead of hitting the XU pipe and the issue port in lockstep.
-template <class C>
-struct WRing {
-    using T = typename C::T;
-    static constexpr bool ON = (C::MODE == MODE_VEC);
-    static constexpr int NWARP = NT / 32;
-    static constexpr int SBW = 32 / C::G;                         // items per warp row-step
-    static constexpr int TILE_SAMPLES = C::SPT * SBW;
-    static constexpr size_t STAGE_BYTES = ON ? size_t(TILE_SAMPLES) * C::DP * sizeof(T) : 0;
-    static constexpr size_t BYTES = ON ? size_t(NWARP) * RING * STAGE_BYTES + 256 : 0;   // + NWARP * RING barriers
-};
-
-template <class C, bool LADJ, class Apply>
-__device__ __forceinline__ void fwd_tile_loop_w(const typename C::T* x, typename C::T* y, typename C::T* ladj, int64_t N,
-                                                int D, typename C::T ladj_const, unsigned char* ring_smem, Apply&& apply) {
-    using T = typename C::T;
-    using R = WRing<C>;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t items = C::PACKED ? ((N + C::LN - 1) / C::LN) : N;
-    const int64_t nwt = (items + R::TILE_SAMPLES - 1) / R::TILE_SAMPLES;
-    const int64_t gw = int64_t(blockIdx.x) * R::NWARP + warp, stride = int64_t(gridDim.x) * R::NWARP;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_smem + size_t(R::NWARP) * RING * R::STAGE_BYTES) + warp * RING;
-    const uint32_t stage_w = smem_u32(ring_smem) + uint32_t(warp * RING) * uint32_t(R::STAGE_BYTES);
-    auto issue = [&](int64_t wt, int slot) {      // lane 0: bulk copy of warp tile wt into this warp's slot
-        const int64_t first = wt * R::TILE_SAMPLES;
-        int64_t n = N - first;
-        if (n > R::TILE_SAMPLES) n = R::TILE_SAMPLES;
-        const uint32_t bytes = uint32_t(n) * uint32_t(D) * uint32_t(sizeof(T));
-        mbar_expect_tx(&bars[slot], bytes);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         stage_w + uint32_t(slot) * uint32_t(R::STAGE_BYTES)),
-                     "l"(x + first * D), "r"(bytes), "r"(smem_u32(&bars[slot]))
-                     : "memory");
-    };
-    if (R::ON) {
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < RING; ++i) mbar_init(&bars[i], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-            for (int i = 0; i < RING; ++i)
-                if (gw + i * stride < nwt) issue(gw + i * stride, i);
-        }
-        __syncwarp();
-    }
-    const int g = lane & (C::G - 1);
-    int k = 0;
-    for (int64_t wt = gw; wt < nwt; wt += stride, ++k) {
-        Tile<C> t;
-        int nv[C::SPT];
-        T l[C::SPT][C::LN];
-        const bool full_tile = R::ON && (wt + 1) * R::TILE_SAMPLES <= N;
-        if (R::ON) {
-            const int slot = k % RING;
-            while (!mbar_try_wait(&bars[slot], uint32_t(k / RING) & 1u)) {}
-            const uint32_t base = stage_w + uint32_t(slot) * uint32_t(R::STAGE_BYTES) +
-                                  uint32_t(((lane >> C::LG) * D + g * C::VE) * int(sizeof(T)));
-            const uint32_t ustride = uint32_t(R::SBW * D * int(sizeof(T)));
-#pragma unroll
-            for (int u = 0; u < C::SPT; ++u) {
-                nv[u] = (full_tile || tile_item<C, true>(wt, u) < N) ? 1 : 0;
-#pragma unroll
-                for (int q = 0; q < C::CH; ++q) {
-                    if (nv[u] && (q * C::G + g) * C::VE < D) lds16(base + u * ustride + uint32_t(q * C::G * C::VE * int(sizeof(T))), t.v[u][q]);
-                    else {
-#pragma unroll
-                        for (int e = 0; e < C::VE; ++e) t.v[u][q][e] = T(0);
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0 && wt + RING * stride < nwt) issue(wt + RING * stride, slot);   // the slot is free again
-        } else {
-            load_tile<C, true>(x, N, D, wt, t, nv);
-        }
-#pragma unroll
-        for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-            for (int p = 0; p < C::LN; ++p) l[u][p] = T(0);
-        bool bad = false;
-        apply(std::false_type{}, t, l, bad);
-        if (LADJ && __any_sync(0xffffffffu, bad)) {
-            // a Jacobian-factor product left the float range somewhere in this warp: redo the tile
-            // with per-element logs (x is still intact: the outputs have not been stored yet)
-            load_tile<C, true>(x, N, D, wt, t, nv);
-#pragma unroll
-            for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                for (int p = 0; p < C::LN; ++p) l[u][p] = T(0);
-            apply(std::true_type{}, t, l, bad);
-        }
-        if (full_tile) {
-            T* yb = y + tile_item<C, true>(wt, 0) * D + g * C::VE;
-            const int ustride = R::SBW * D;
-#pragma unroll
-            for (int u = 0; u < C::SPT; ++u) {
-#pragma unroll
-                for (int q = 0; q < C::CH; ++q)
-                    if ((q * C::G + g) * C::VE < D) st16_stream(yb + u * ustride + q * C::G * C::VE, t.v[u][q]);
-            }
-            if (LADJ) {
-                T* lb = ladj + tile_item<C, true>(wt, 0);
-#pragma unroll
-                for (int u = 0; u < C::SPT; ++u) {
-                    const T tot = group_sum<C>(l[u][0]);
-                    if (g == 0) __stcs(lb + u * R::SBW, Prim<T>::fma_(tot, Prim<T>::LGU, ladj_const));
-                }
-            }
-        } else {
-            store_tile<C, true>(y, D, wt, t, nv);
-            if (LADJ) store_ladj<C, true>(ladj, wt, l, nv, ladj_const);
-        }
-    }
-}
-
 template <class C>
 __device__ __forceinline__ unsigned char* ring_base(unsigned char* after_consts) {
     return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(after_consts) + 127) & ~uintptr_t(127));
@@ -937,23 +693,15 @@ __device__ __forceinline__ unsigned char* ring_base(unsigned char* after_consts)
 #ifndef ENF_GRAD_SAFE_ONLY
 #define ENF_GRAD_SAFE_ONLY 0
 #endif
-#ifndef ENF_WARP_RING
-#define ENF_WARP_RING 0   // 1: warp-private rings (fwd_tile_loop_w; measured 3 % slower, profiles/README.md), 0: one ring per CTA
-#endif
-#if ENF_WARP_RING
-template <class C> using FwdRing = WRing<C>;
-#define ENF_FWD_LOOP fwd_tile_loop_w
-#else
 template <class C> using FwdRing = Ring<C>;
 #define ENF_FWD_LOOP fwd_tile_loop
-#endif
 
 // F1/F2 of SURVEY §2.3: (f::Trafo)(x) and with_logabsdet_jacobian(f, x) for a whole chain.
 #ifndef ENF_FWD_MIN_CTAS
 #define ENF_FWD_MIN_CTAS 3
 #endif
 template <class C, bool LADJ>
-__global__ void __launch_bounds__(NT + 32 * ENF_PRODUCER_WARP, ENF_FWD_MIN_CTAS) chain_fwd_kernel(const __grid_constant__ ChainDesc desc,
+__global__ void __launch_bounds__(NT, ENF_FWD_MIN_CTAS) chain_fwd_kernel(const __grid_constant__ ChainDesc desc,
                                                                          const typename C::T* __restrict__ consts,
                                                                          const typename C::T* x, typename C::T* y,
                                                                          typename C::T* ladj, int64_t N,
@@ -966,25 +714,6 @@ __global__ void __launch_bounds__(NT + 32 * ENF_PRODUCER_WARP, ENF_FWD_MIN_CTAS)
                            [&](auto safe, Tile<C>& t, T (&l)[C::SPT][C::LN], bool& bad) {
                                constexpr bool SAFE = decltype(safe)::value;
                                for (int o = 0; o < desc.n_ops; ++o) apply_op_fwd<C, LADJ, SAFE>(desc.ops[o], s_c, t, l, bad);
-                           });
-}
-
-// forward (+ ladj) for a chain known at compile time
-template <class C, bool LADJ, int... CODES>
-__global__ void __launch_bounds__(NT + 32 * ENF_PRODUCER_WARP, 2) chain_fwd_static_kernel(const __grid_constant__ ChainDesc desc,
-                                                                 const typename C::T* __restrict__ consts,
-                                                                 const typename C::T* x, typename C::T* y,
-                                                                 typename C::T* ladj, int64_t N,
-                                                                 typename C::T ladj_const) {
-    using T = typename C::T;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T* s_c = reinterpret_cast<T*>(smem_raw);
-    stage_constants<C>(desc, consts, s_c);
-    StaticStages<C, LADJ, CODES...> stages;
-    stages.load(desc, s_c, 0);
-    ENF_FWD_LOOP<C, LADJ>(x, y, ladj, N, desc.D, ladj_const, ring_base<C>(smem_raw + size_t(desc.n_consts) * sizeof(T)),
-                           [&](auto safe, Tile<C>& t, T (&l)[C::SPT][C::LN], bool& bad) {
-                               stages.template apply<decltype(safe)::value>(t, l, bad);
                            });
 }
 

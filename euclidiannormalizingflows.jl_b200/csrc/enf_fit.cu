@@ -57,7 +57,6 @@ __device__ void fit_derive(const FitDesc& fd, const double* __restrict__ params,
                     const bool real = fd.packed || r < D;
                     const int i = fd.packed ? r % D : r;
                     put(cb, size_t(k) * Dp + r, real ? v[i] * sc : 0.0);
-                    put(cb, size_t(op.K + k) * Dp + r, 0.0);   // compact-WY factor: host-derived only (static kernels)
                 }
             }
             continue;

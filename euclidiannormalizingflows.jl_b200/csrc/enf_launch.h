@@ -28,20 +28,8 @@ struct KernelSet {
     int LN = 1;  // samples per item (packed modes)
     int G = 1, CH = 1, VE = 4;
     size_t fwd_ring_bytes = 0;  // TMA input ring of the forward kernels (MODE_VEC)
-    int fwd_threads = 256;      // CTA size of the forward kernels (+1 producer warp with the ring)
+    int fwd_threads = 256;      // CTA size of the forward kernels
 };
-
-// A chain compiled as a static op sequence (enf_chain_static.cu)
-struct StaticKernel {
-    const void* fwd = nullptr;
-    const void* fwd_ladj = nullptr;
-    int items_per_tile = 0;
-    int LN = 1;
-    int Dp = 0;
-    size_t ring_bytes = 0;
-    int threads = 256;
-};
-bool select_static(int dtype, const ChainDesc& d, int mode, StaticKernel& k);
 
 bool make_plan(int dtype, int D, Plan& plan);
 bool select_kernels(int dtype, const Plan& plan, int mode, KernelSet& k);
@@ -50,9 +38,6 @@ size_t grad_smem_bytes(int dtype, const ChainDesc& d, const KernelSet& k, bool g
 
 cudaError_t launch_fwd(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
                        void* y, void* ladj, int64_t N, double ladj_const, int sm_count, cudaStream_t st);
-cudaError_t launch_fwd_static(int dtype, const StaticKernel& k, const ChainDesc& desc, const void* consts,
-                              const void* x, void* y, void* ladj, int64_t N, double ladj_const, int sm_count,
-                              cudaStream_t st);
 cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
                         int64_t N, bool grad, double* partials, int max_blocks, int* blocks_used, int sm_count,
                         cudaStream_t st);

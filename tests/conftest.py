@@ -46,7 +46,22 @@ def rel_err(got, ref, floor=0.0):
     return float(np.max(np.abs(got - ref) / (np.abs(ref) + scale)))
 
 
+def strict_rel_err(got, ref):
+    """Plain element-wise relative error max |got - ref| / |ref| over the elements with |ref| > RMS(ref):
+    the un-softened companion of rel_err (it ignores only the elements near zero, where a relative error is
+    ill-posed).  Reported in every assertion message; the Float32 budget is checked on rel_err."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    if ref.size == 0:
+        return 0.0
+    m = np.abs(ref) > np.sqrt(np.mean(ref * ref))
+    if not m.any():
+        return 0.0
+    return float(np.max(np.abs(got - ref)[m] / np.abs(ref)[m]))
+
+
 def assert_close(got, ref, dtype, what="", factor=1.0, floor=0.0):
     tol = TOL[np.dtype(dtype)] * factor
     e = rel_err(got, ref, floor)
-    assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e}"
+    assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e} (plain relative error on |ref| > RMS: {strict_rel_err(got, ref):.3e})"
+    return e

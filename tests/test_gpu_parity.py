@@ -165,7 +165,7 @@ def test_negll_and_grad(ctx, dtype, spec, D):
         for (k, a), (_, b) in zip(got, ref):
             assert a.dtype == dtype
             b = b.reshape(a.shape)
-            assert_close(a, b, dtype, f"grad {k} {spec}", factor=4.0 if dtype == np.float32 else 50.0)
+            assert_close(a, b, dtype, f"grad {k} {spec}")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -185,7 +185,7 @@ def test_grad_reproducible_and_ragged(ctx, dtype):
         v_ref, g_ref = O.mvnormal_negll_trafograd(fo, X.astype(np.float64))
         assert abs(v1 - v_ref) <= (1e-5 if dtype == np.float32 else 1e-12) * (abs(v_ref) + 1)
         for (k, a), (_, b) in zip(flat_grads(g1, fe), flat_grads(g_ref, fo)):
-            assert_close(a, b.reshape(a.shape), dtype, f"grad {k} N={N}", factor=4.0 if dtype == np.float32 else 50.0)
+            assert_close(a, b.reshape(a.shape), dtype, f"grad {k} N={N}")
 
 
 def test_optimize_whitening_matches_oracle(ctx):
@@ -260,7 +260,9 @@ def test_against_committed_golden_fixtures(ctx, dtype, name):
         assert abs(vz - float(z["negll_zygote_primal"])) <= 1e-12 * (abs(vz) + 1)
         keys = sorted(k for k in z.files if k.startswith("grad_"))
         for k, (_, a) in zip(keys, flat_grads(g, fe)):
-            assert_close(a, z[k].reshape(a.shape), dtype, f"golden {k} {name}", factor=50.0, floor=1e-3)
+            # floor: the gradient of an OUTERMOST Householder stack is mathematically zero (|Hy| = |y|), the fixture
+            # holds rounding noise there; everything else is measured at the stated tolerance
+            assert_close(a, z[k].reshape(a.shape), dtype, f"golden {k} {name}", floor=1e-3)
         X2, L2 = E.with_logabsdet_jacobian(E.inverse(fe), Y)
         assert_close(X2.to_host(), z["X"], dtype, "golden roundtrip", factor=3000)
 
@@ -398,7 +400,7 @@ def test_affine_chain_grad_from_tensor_core_moments(ctx, spec, D, N):
         got, ref = flat_grads(g, fe), flat_grads(g_ref, fo)
         assert [k for k, _ in got] == [k for k, _ in ref]
         for (k, a), (_, b) in zip(got, ref):
-            assert_close(a, b.reshape(a.shape), np.float32, f"grad {k} {spec}", factor=4.0)
+            assert_close(a, b.reshape(a.shape), np.float32, f"grad {k} {spec}")
     # same call twice -> identical result (fixed-order reductions)
     _, g2 = E.mvnormal_negll_trafograd(fe, Xd)
     for (_, a), (_, b) in zip(flat_grads(g, fe), flat_grads(g2, fe)):
@@ -476,29 +478,103 @@ def test_device_side_fit_loop_for_second_moment_chains(ctx):
     assert abs(v - v_own) < 1e-5 * (abs(v_own) + 1)
 
 
-@pytest.mark.gpu
-def test_affine_kernel_with_bf16_correction_terms(ctx):
-    """Opt-in variant of the tensor-core forward kernel (ENF_AFFINE_BF16=1: the two correction products of the 3xTF32
-    scheme as bf16 MMAs).  The switch is read once per process, so the check runs in a child process; the error budget
-    of this mode is 2^-20 on top of the accumulation error, hence the slightly wider bound."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = (
-        "import sys, numpy as np\n"
-        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
-        "import enf_b200 as E\nfrom chains import both\nfrom oracle import enf_oracle as O\n"
-        "ctx = E.default_context()\n"
-        "for D, spec, N in ((256, ['hh64', 'ss'], 4099), (128, ['ss', 'hh32'], 1000), (64, ['hh8'], 129)):\n"
-        "    fo, fe = both(spec, D, 7, np.float32)\n"
-        "    X = np.random.default_rng(8).standard_normal((D, N)).astype(np.float32)\n"
-        "    Y, L = E.with_logabsdet_jacobian(fe, E.B200Matrix.from_host(X, ctx))\n"
-        "    yr, lr = O.with_logabsdet_jacobian(fo, X.astype(np.float64))\n"
-        "    e = np.max(np.abs(Y.to_host() - yr) / (np.abs(yr) + np.sqrt(np.mean(yr ** 2))))\n"
-        "    assert e < 1.5e-5, (D, spec, e)\n"
-        "    assert np.max(np.abs(L.to_host()[0] - lr)) < 1e-4\n"
-        "print('bf16 ok')\n")
-    env = dict(os.environ, ENF_AFFINE_BF16="1")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
-    assert r.returncode == 0 and "bf16 ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+# ---- round 2: literal-Float32 reference, deep accumulation, synthetic-data generator
+@pytest.mark.parametrize("spec,D", [
+    (["cs", "hhv", "ss"], 2), (["jo", "cs"], 1), (["ss", "jo"], 1), (["hh4", "jo", "cs"], 16),
+    (["cc", "jo", "hh4", "ss"], 32), (["cs", "jo", "hh4"], 16), (["ji", "cc"], 8),
+])
+def test_float32_against_the_literal_float32_reference(ctx, spec, D):
+    """The reference computes Float32 inputs in Float32 (`float(promote_type(...))`, src/center_stretch.jl:5,
+    src/johnson_trafo.jl:30).  Compare the CUDA Float32 path with the oracle evaluated literally in Float32
+    (all-float32 numpy arithmetic) AND with the float64 oracle, on the columns where the literal Float32 formula is
+    finite; all three pairwise distances are printed (run with -s) and the CUDA-vs-literal one is held to 1e-5.
+    Measured on B200 (tools/parity_report.py, N = 1e5): cuda-vs-literal <= 6.4e-6 (y), 1.5e-6 (ladj); the literal
+    Float32 evaluation itself is 1.2e-7 ... 4.4e-6 from float64."""
+    import enf_b200 as E
+    N = 50_000
+    fo, fe = both(spec, D, 5, np.float32)                     # float32-rounded parameters in both
+    X = _data(D, N, 6, np.float32)
+    with np.errstate(all="ignore"):
+        y32, l32 = O.with_logabsdet_jacobian(fo, X)           # literal: every operation rounds to Float32
+    assert y32.dtype == np.float32 and l32.dtype == np.float32
+    y64, l64 = O.with_logabsdet_jacobian(fo, X.astype(np.float64))
+    Y, L = E.with_logabsdet_jacobian(fe, E.B200Matrix.from_host(X, ctx))
+    y, l = Y.to_host(), L.to_host()[0]
+    fin = np.isfinite(y32).all(0) & np.isfinite(l32)
+    assert fin.mean() > 0.99
+    print(f"\n{spec} D={D}: y cuda-vs-literal32 {rel_err(y[:, fin], y32[:, fin]):.2e}  cuda-vs-f64 {rel_err(y, y64):.2e}  "
+          f"literal32-vs-f64 {rel_err(y32[:, fin], y64[:, fin]):.2e} | ladj {rel_err(l[fin], l32[fin]):.2e} "
+          f"{rel_err(l, l64):.2e} {rel_err(l32[fin], l64[fin]):.2e}")
+    assert_close(y[:, fin], y32[:, fin], np.float32, f"y vs literal Float32 {spec}")
+    assert_close(l[fin], l32[fin], np.float32, f"ladj vs literal Float32 {spec}")
+    assert np.isfinite(y).all() and np.isfinite(l).all()       # finite also where the literal Float32 formula is not
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("spec,D", [(["cc", "jo", "hh4", "ss"], 32), (["hh4", "jo", "cs"], 16), (["ss", "jo"], 1)])
+def test_gradient_parity_with_many_tiles_per_cta(ctx, dtype, spec, D):
+    """N large enough that every CTA of the gradient kernel visits many tiles (the grid is capped at a few CTAs
+    per SM): per-thread Float32 accumulation depth grows with N / grid.  Held to the stated tolerance."""
+    import enf_b200 as E
+    N = 1_200_003 if D <= 16 else 600_001
+    fo, fe = both(spec, D, 21, dtype)
+    X = _data(D, N, 23, dtype, spread=1.2)
+    v_ref, g_ref = O.mvnormal_negll_trafograd(fo, X.astype(np.float64))
+    v, g = E.mvnormal_negll_trafograd(fe, E.B200Matrix.from_host(X, ctx))
+    assert abs(v - v_ref) <= (1e-5 if dtype == np.float32 else 1e-12) * (abs(v_ref) + 1)
+    for (k, a), (_, b) in zip(flat_grads(g, fe), flat_grads(g_ref, fo)):
+        assert_close(a, b.reshape(a.shape), dtype, f"grad {k} {spec} N={N}")
+
+
+def _philox4x32_10(ctr, seed):
+    """numpy twin of csrc/enf_fill.cu: Philox4x32-10, counter = (lo32, hi32, 0, 0) of the global element index,
+    key = (lo32, hi32) of the seed."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+    ctr = np.asarray(ctr, dtype=np.uint64)
+    c = [(ctr & np.uint64(0xFFFFFFFF)).astype(np.uint32), (ctr >> np.uint64(32)).astype(np.uint32),
+         np.zeros(ctr.shape, np.uint32), np.zeros(ctr.shape, np.uint32)]
+    k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32)
+    for _ in range(10):
+        p0 = M0 * c[0].astype(np.uint64)
+        p1 = M1 * c[2].astype(np.uint64)
+        hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        with np.errstate(over="ignore"):
+            k0, k1 = np.uint32(k0 + W0), np.uint32(k1 + W1)
+    return c
+
+
+def _fill_normal_twin(D, N, col0, seed):
+    idx = np.arange(D * N, dtype=np.uint64) + np.uint64(col0 * D)
+    r = _philox4x32_10(idx, seed)
+    two64 = 18446744073709551616.0
+    u1 = (r[0].astype(np.float64) * 4294967296.0 + r[2].astype(np.float64) + 0.5) / two64
+    u2 = (r[1].astype(np.float64) * 4294967296.0 + r[3].astype(np.float64) + 0.5) / two64
+    return (np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)).reshape(N, D).T      # D x N, column-major memory
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fill_normal_matches_numpy_philox_twin(ctx, dtype):
+    """enf_fill_normal (counter-based Philox4x32-10 keyed by (seed, global element index) + Box-Muller):
+    (i) equals a numpy restatement of the same generator, (ii) element (i, j) does not depend on `col0` sharding,
+    (iii) also beyond 2^32 elements (64-bit counters), (iv) moments of N(0,1)."""
+    import enf_b200 as E
+    D, N, seed = 16, 40_000, 42
+    ref = _fill_normal_twin(D, N, 0, seed)
+    got = E.B200Matrix.randn(D, N, dtype, seed=seed, col0=0, ctx=ctx).to_host()
+    tol = 2e-6 if dtype == np.float32 else 1e-13      # float32: logf/cospif of the rounded uniforms
+    assert np.max(np.abs(got - ref) / (np.abs(ref) + 1)) < tol
+    # sharding: columns [col0, col0 + n) generated on their own are the same bits as inside the whole matrix
+    for col0, n in ((1, 100), (12_345, 5000), (39_999, 1)):
+        part = E.B200Matrix.randn(D, n, dtype, seed=seed, col0=col0, ctx=ctx).to_host()
+        np.testing.assert_array_equal(part, got[:, col0:col0 + n])
+    # 64-bit element counters: a shard that starts beyond 2^32 elements
+    far = (1 << 32) // D + 7
+    part = E.B200Matrix.randn(D, 64, dtype, seed=seed, col0=far, ctx=ctx).to_host()
+    assert np.max(np.abs(part - _fill_normal_twin(D, 64, far, seed)) / (np.abs(_fill_normal_twin(D, 64, far, seed)) + 1)) < tol
+    # another seed gives other data; moments are those of N(0,1)
+    other = E.B200Matrix.randn(D, N, dtype, seed=seed + 1, col0=0, ctx=ctx).to_host()
+    assert np.abs(other - got).mean() > 0.5
+    big = E.B200Matrix.randn(4, 1_000_000, dtype, seed=7, ctx=ctx).to_host().astype(np.float64)
+    assert abs(big.mean()) < 4e-3 and abs(big.std() - 1) < 4e-3 and abs((big ** 3).mean()) < 2e-2 and abs((big ** 4).mean() - 3) < 5e-2
