@@ -478,14 +478,14 @@ void finish(const enf_chain* ch, const double* sums, int64_t N, int flags, doubl
         for (int i = 0; i < D; ++i) {
             const double r0 = row_sum(0, i), r1 = row_sum(1, i);
             switch (op.kind) {
-                case OP_CS: {
+                case OP_CS: {      // raw sums: dc, -da, -b db (enf_math.cuh: cs_bwd)
                     const double r2 = row_sum(2, i);
-                    g[i] = r1 / Nd; g[D + i] = r2 / Nd; g[2 * D + i] = r0 / Nd;
+                    g[i] = -r1 / Nd; g[D + i] = -r2 / (p[D + i] * Nd); g[2 * D + i] = r0 / Nd;
                     break;
                 }
-                case OP_CC: {
+                case OP_CC: {      // raw sums: -dc, da, b db (enf_math.cuh: cc_bwd)
                     const double r2 = row_sum(2, i);
-                    g[i] = r1 / Nd; g[D + i] = r2 / Nd; g[2 * D + i] = -r0 / Nd;
+                    g[i] = r1 / Nd; g[D + i] = r2 / (p[D + i] * Nd); g[2 * D + i] = -r0 / Nd;
                     break;
                 }
                 case OP_JO: {
@@ -751,6 +751,43 @@ extern "C" int enf_fill_normal(enf_ctx* ctx, int dtype, void* x, int D, int64_t 
 }
 
 // ------------------------------------------------------------------ chains
+// Parameter domain of the kernels.  CenterStretch / CenterContract are evaluated with w = e^{-b|x|} and ln2/b, i.e. for
+// b > 0: the reference itself writes exp(abs(b*x)) and sign(x) (src/center_stretch.jl:6-7), which is the b > 0 branch of
+// the inverse; b <= 0 is rejected instead of silently returning another branch.  Johnson needs delta, lambda != 0
+// (src/johnson_trafo.jl:29-42 divides by both), ScaleShift a != 0 (log|a|, 1/a), Householder v != 0.
+static int validate_params(enf_chain* ch) {
+    const int D = ch->D;
+    for (size_t o = 0; o < ch->ops.size(); ++o) {
+        const HostOp& op = ch->ops[o];
+        const double* p = ch->params.data() + op.poff;
+        for (size_t i = 0; i < op.nparams; ++i)
+            if (!std::isfinite(p[i])) return fail(ch->ctx, ENF_ERR_INVALID, "op %zu: parameter %zu is not finite", o, i);
+        switch (op.kind) {
+            case OP_CS: case OP_CC:
+                for (int i = 0; i < D; ++i)
+                    if (!(p[D + i] > 0.0))
+                        return fail(ch->ctx, ENF_ERR_INVALID, "op %zu: CenterStretch/CenterContract need b > 0 (b[%d] = %g)", o, i, p[D + i]);
+                break;
+            case OP_JO: case OP_JI:
+                for (int i = 0; i < D; ++i)
+                    if (p[D + i] == 0.0 || p[3 * D + i] == 0.0)
+                        return fail(ch->ctx, ENF_ERR_INVALID, "op %zu: JohnsonTrafo needs delta != 0 and lambda != 0 (row %d)", o, i);
+                break;
+            case OP_SS:
+                for (int i = 0; i < D; ++i)
+                    if (p[i] == 0.0) return fail(ch->ctx, ENF_ERR_INVALID, "op %zu: ScaleShiftTrafo needs a != 0 (row %d)", o, i);
+                break;
+            default:
+                for (int k = 0; k < op.K; ++k) {
+                    double n = 0.0;
+                    for (int i = 0; i < D; ++i) n += p[size_t(k) * D + i] * p[size_t(k) * D + i];
+                    if (!(n > 0.0)) return fail(ch->ctx, ENF_ERR_INVALID, "op %zu: Householder vector %d is zero", o, k);
+                }
+        }
+    }
+    return ENF_OK;
+}
+
 extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const enf_op* ops, enf_chain** out) {
     if (!ctx || !ops || !out) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
     *out = nullptr;
@@ -842,7 +879,8 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
     }
-    int rc = derive_constants(ch);
+    int rc = validate_params(ch);
+    if (rc == ENF_OK) rc = derive_constants(ch);
     if (rc != ENF_OK) { enf_chain_destroy(ch); return rc; }
     *out = ch;
     return ENF_OK;
@@ -851,9 +889,12 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
 extern "C" int enf_chain_set_params(enf_chain* ch, const void* packed) {
     if (!ch || !packed) return fail(ch ? ch->ctx : nullptr, ENF_ERR_INVALID, "NULL argument");
     CU(ch->ctx, cudaSetDevice(ch->ctx->device));
+    std::vector<double> old = ch->params;
     for (size_t i = 0; i < ch->n_params; ++i)
         ch->params[i] = ch->dtype == ENF_F32 ? double(static_cast<const float*>(packed)[i])
                                               : static_cast<const double*>(packed)[i];
+    int rc = validate_params(ch);
+    if (rc != ENF_OK) { ch->params = old; return rc; }     // the chain keeps its previous parameters
     return derive_constants(ch);
 }
 
@@ -1184,11 +1225,15 @@ extern "C" int enf_negll_grad_group(enf_chain* ch, const void* x, int64_t N_loca
     CU(ctx, cudaMemcpyAsync(ch->d_sums + ch->n_raw, ch->h_sums + ch->n_raw, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     rc = group_allreduce(ctx, ch->d_sums, size_t(ch->n_raw + 1));
     if (rc != ENF_OK) return rc;
-    if (ch->moments && !host_chain_rule()) return moments_finish_device(ch, flags, negll, grads_host);   // N_global = S^[D][D]
+    if (ch->moments && !host_chain_rule()) {                 // N_global = S^[D][D]
+        rc = moments_finish_device(ch, flags, negll, grads_host);        // synchronises the stream
+        if (rc != ENF_OK) return rc;
+        return p2p_check(ctx);                                           // a rank that never arrived fails every rank
+    }
     CU(ctx, cudaMemcpyAsync(ch->h_sums, ch->d_sums, size_t(ch->n_raw + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if (std::isnan(ch->h_sums[ch->n_raw])) {      // poisoned by the peer-memory all-reduce: a rank never arrived
-        p2p_check(ctx);
+    if (std::isnan(ch->h_sums[ch->n_raw])) {      // poisoned by the peer-memory all-reduce: some rank never arrived (sticky on all ranks)
+        p2p_check(ctx);                           // clears the flag
         return fail(ctx, ENF_ERR_NCCL, "peer-memory all-reduce timed out waiting for a rank of the group");
     }
     const int64_t N_global = int64_t(std::llround(ch->h_sums[ch->n_raw]));
@@ -1199,15 +1244,17 @@ extern "C" int enf_negll_grad_group(enf_chain* ch, const void* x, int64_t N_loca
 // the same in every epoch (src/optimize_whitening.jl:31-38), and the loss depends on a batch only through its moment
 // matrix, so ONE pass over the data computes [[S, m], [m^T, N]] of every batch; after that a step is two launches
 // (chain-rule cluster kernel + optimizer kernel) whose cost does not depend on the number of samples.
-static int optimize_whitening_moments(enf_chain* ch, const void* x, int64_t N, int64_t batchsize, int64_t nb, int64_t nepochs,
-                                      double eta, double epsilon, int flags, int use_group, int fresh_state,
+static int optimize_whitening_moments(enf_chain* ch, const void* x, const std::vector<int64_t>& starts, const std::vector<int64_t>& counts,
+                                      int64_t nepochs, double eta, double epsilon, int flags, int use_group, int fresh_state,
                                       double* state_inout, void* params_out, double* history_out) {
     enf_ctx* ctx = ch->ctx;
     const size_t P = ch->n_params, stride = size_t(ch->n_raw) + 1;
+    const int64_t nb = int64_t(counts.size());
     const int64_t n_steps = nb * nepochs;
-    if (!aligned16(x) || (batchsize * ch->D * 4) % 16 != 0)
-        return fail(ctx, ENF_ERR_INVALID, "second-moment chains need 16-byte aligned batches (D=%d, batch size %lld)", ch->D,
-                    static_cast<long long>(batchsize));
+    for (int64_t b = 0; b < nb; ++b)
+        if (counts[size_t(b)] > 0 && (!aligned16(x) || (starts[size_t(b)] * ch->D * 4) % 16 != 0))
+            return fail(ctx, ENF_ERR_INVALID, "second-moment chains need 16-byte aligned batches (D=%d, batch %lld starts at column %lld)",
+                        ch->D, static_cast<long long>(b), static_cast<long long>(starts[size_t(b)]));
     std::vector<int> kinds, Ks, poffs;
     for (const HostOp& op : ch->ops) {
         kinds.push_back(op.kind);
@@ -1255,7 +1302,11 @@ static int optimize_whitening_moments(enf_chain* ch, const void* x, int64_t N, i
     CUF(cudaStreamSynchronize(ctx->stream));
     // the one pass over the data
     for (int64_t b = 0; b < nb; ++b) {
-        const int64_t start = b * batchsize, nbt = std::min(batchsize, N - start);
+        const int64_t start = starts[size_t(b)], nbt = counts[size_t(b)];
+        if (nbt == 0) {      // this rank holds no column of the batch (sharded batches): its moments are zero
+            CUF(cudaMemsetAsync(d_all + size_t(b) * stride, 0, stride * sizeof(double), ctx->stream));
+            continue;
+        }
         const char* xb = static_cast<const char*>(x) + size_t(start) * size_t(ch->D) * 4;
         CUF(launch_moments(ch->D, xb, nbt, ch->d_partials, d_all + size_t(b) * stride, ctx->sm_count, ctx->stream));
         ctx->launches += 2;
@@ -1318,27 +1369,56 @@ static int optimize_whitening_moments(enf_chain* ch, const void* x, int64_t N, i
     cleanup();
     ch->params = pfin;
     export_grads(ch, pfin, params_out);
+    int rcv = validate_params(ch);
+    if (rcv != ENF_OK) return rcv;
     return derive_constants(ch);
 }
 
 // ------------------------------------------------------------------ device-side fit loop
-extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, int64_t nbatches, int64_t nepochs,
-                                      double eta, double epsilon, int flags, int use_group, int fresh_state,
-                                      double* state_inout, void* params_out, double* history_out, int64_t* n_steps_out) {
+// every rank of a group must run the same number of steps with the same number of collectives: compare the batch
+// count over the ranks before anything is launched (max and -min in one all-reduce) and fail on EVERY rank otherwise
+static int group_check_same(enf_ctx* ctx, int64_t value, const char* what) {
+    long long h[2] = {static_cast<long long>(value), -static_cast<long long>(value)};
+    long long* d = nullptr;
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&d), sizeof h));
+    CU(ctx, cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    ncclResult_t r = g_nccl.AllReduce(d, d, 2, ncclInt64, ncclMax, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) { cudaFree(d); return fail(ctx, ENF_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r)); }
+    CU(ctx, cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    if (h[0] != -h[1])
+        return fail(ctx, ENF_ERR_INVALID, "the ranks of the group disagree on %s (%lld ... %lld); pass explicit per-batch column "
+                    "counts (enf_optimize_whitening_batches)", what, -h[1], h[0]);
+    return ENF_OK;
+}
+
+extern "C" int enf_optimize_whitening_batches(enf_chain* ch, const void* x, int64_t n_batches, const int64_t* local_counts,
+                                              int64_t nepochs, double eta, double epsilon, int flags, int use_group, int fresh_state,
+                                              double* state_inout, void* params_out, double* history_out, int64_t* n_steps_out) {
     if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
     enf_ctx* ctx = ch->ctx;
-    if (!x || !state_inout || !params_out || !history_out) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
-    if (N < 1 || nbatches < 1 || nepochs < 0) return fail(ctx, ENF_ERR_INVALID, "bad N / nbatches / nepochs");
+    if (!x || !local_counts || !state_inout || !params_out || !history_out) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    if (n_batches < 1 || nepochs < 0) return fail(ctx, ENF_ERR_INVALID, "bad number of batches / epochs");
     if (use_group && !ctx->comm) return fail(ctx, ENF_ERR_INVALID, "enf_group_init has not been called on this context");
     CU(ctx, cudaSetDevice(ctx->device));
-    // src/optimize_whitening.jl:31: batchsize = round(Int, length(smpls) / nbatches)  (ties to even)
-    const int64_t batchsize = int64_t(std::nearbyint(double(N) / double(nbatches)));
-    if (batchsize < 1) return fail(ctx, ENF_ERR_INVALID, "nbatches exceeds the number of samples");
-    const int64_t nb = (N + batchsize - 1) / batchsize;
+    const int64_t nb = n_batches;
+    std::vector<int64_t> starts(static_cast<size_t>(nb)), cnts(local_counts, local_counts + nb);
+    int64_t N = 0;
+    for (int64_t b = 0; b < nb; ++b) {
+        if (cnts[size_t(b)] < 0 || (cnts[size_t(b)] == 0 && !use_group))
+            return fail(ctx, ENF_ERR_INVALID, "batch %lld has %lld columns", static_cast<long long>(b), static_cast<long long>(cnts[size_t(b)]));
+        starts[size_t(b)] = N;
+        N += cnts[size_t(b)];
+    }
+    if (use_group) {
+        int rcg = group_check_same(ctx, nb, "the number of batches");
+        if (rcg != ENF_OK) return rcg;
+    }
     const int64_t n_steps = nb * nepochs;
     if (n_steps_out) *n_steps_out = n_steps;
     if (ch->moments)
-        return optimize_whitening_moments(ch, x, N, batchsize, nb, nepochs, eta, epsilon, flags, use_group, fresh_state,
+        return optimize_whitening_moments(ch, x, starts, cnts, nepochs, eta, epsilon, flags, use_group, fresh_state,
                                           state_inout, params_out, history_out);
     const size_t P = ch->n_params;
     const size_t es = elem_size(ch->dtype);
@@ -1369,7 +1449,7 @@ extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, i
     long long* d_step = nullptr;
     std::vector<double> counts(static_cast<size_t>(nb), 0.0);
     std::vector<double> st0(P, 0.0);
-    for (int64_t b = 0; b < nb; ++b) counts[size_t(b)] = double(std::min(batchsize, N - b * batchsize));
+    for (int64_t b = 0; b < nb; ++b) counts[size_t(b)] = double(cnts[size_t(b)]);
     for (size_t i = 0; i < P; ++i) st0[i] = fresh_state ? epsilon : state_inout[i];
     auto cleanup = [&]() {
         if (d_params) cudaFree(d_params);
@@ -1406,7 +1486,7 @@ extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, i
     // one epoch = nb steps of (derive, grad, reduce, count, [all-reduce], update); identical every epoch
     auto enqueue_epoch = [&]() -> int {
         for (int64_t b = 0; b < nb; ++b) {
-            const int64_t start = b * batchsize, nbt = std::min(batchsize, N - start);
+            const int64_t start = starts[size_t(b)], nbt = cnts[size_t(b)];
             const char* xb = static_cast<const char*>(x) + size_t(start) * size_t(ch->D) * es;
             KernelSet ks;
             select_kernels(ch->dtype, ch->plan, pick_mode(ch, xb, nullptr), ks);
@@ -1482,5 +1562,24 @@ extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, i
     }
     ch->params = pfin;
     export_grads(ch, pfin, params_out);        // same packed layout / dtype conversion as gradients
+    int rcv = validate_params(ch);             // the optimizer may have stepped a parameter out of the trafo's domain
+    if (rcv != ENF_OK) return rcv;
     return derive_constants(ch);
+}
+
+// src/optimize_whitening.jl:31-32: batchsize = round(Int, length(smpls) / nbatches) (ties to even), contiguous column
+// ranges in fixed order, the last one possibly short
+extern "C" int enf_optimize_whitening(enf_chain* ch, const void* x, int64_t N, int64_t nbatches, int64_t nepochs,
+                                      double eta, double epsilon, int flags, int use_group, int fresh_state,
+                                      double* state_inout, void* params_out, double* history_out, int64_t* n_steps_out) {
+    if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
+    enf_ctx* ctx = ch->ctx;
+    if (N < 1 || nbatches < 1 || nepochs < 0) return fail(ctx, ENF_ERR_INVALID, "bad N / nbatches / nepochs");
+    const int64_t batchsize = int64_t(std::nearbyint(double(N) / double(nbatches)));
+    if (batchsize < 1) return fail(ctx, ENF_ERR_INVALID, "nbatches exceeds the number of samples");
+    const int64_t nb = (N + batchsize - 1) / batchsize;
+    std::vector<int64_t> counts(static_cast<size_t>(nb));
+    for (int64_t b = 0; b < nb; ++b) counts[size_t(b)] = std::min(batchsize, N - b * batchsize);
+    return enf_optimize_whitening_batches(ch, x, nb, counts.data(), nepochs, eta, epsilon, flags, use_group, fresh_state,
+                                          state_inout, params_out, history_out, n_steps_out);
 }

@@ -59,6 +59,8 @@ __host__ __device__ constexpr int n_rowslots_of(int kind, int K) {
     return (kind == OP_CS || kind == OP_CC) ? 3 : (kind == OP_JO || kind == OP_JI) ? 4 : kind == OP_SS ? 2 : K;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
 // ------------------------------------------------------------------ 16-byte accessors
 template <typename T> struct Vec;
 template <> struct Vec<float> { static constexpr int VE = 4; };
@@ -100,14 +102,32 @@ __device__ __forceinline__ void lds16(uint32_t a, float (&o)[4]) {
 __device__ __forceinline__ void lds16(uint32_t a, double (&o)[2]) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(a));
 }
+__device__ __forceinline__ void sts16(uint32_t a, const float (&o)[4]) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t a, const double (&o)[2]) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(o[0]), "d"(o[1]) : "memory");
+}
 // 16-byte read-modify-write of a per-thread accumulator vector in shared memory
 template <typename T, int VE>
-__device__ __forceinline__ void acc16_shared(T* p, const T (&a)[VE]) {
+__device__ __forceinline__ void acc16_shared(uint32_t p, const T (&a)[VE]) {   // p: 32-bit shared-window address
     T cur[VE];
-    ld16_shared(p, cur);
+    lds16(p, cur);
+#if ENF_F32X2
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int e = 0; e < VE; e += 2) {
+            const float2 s2 = add2(make_float2(cur[e], cur[e + 1]), make_float2(a[e], a[e + 1]));
+            cur[e] = s2.x;
+            cur[e + 1] = s2.y;
+        }
+        sts16(p, cur);
+        return;
+    }
+#endif
 #pragma unroll
     for (int e = 0; e < VE; ++e) cur[e] += a[e];
-    st16_shared(p, cur);
+    sts16(p, cur);
 }
 
 // ------------------------------------------------------------------ configuration
@@ -222,6 +242,24 @@ __device__ __forceinline__ T group_sum(T v) {
     return v;
 }
 
+// xor-shuffle sum over the G lanes of a group of a PAIR of values (Float32: one packed add per step)
+template <class C, typename T>
+__device__ __forceinline__ void group_sum2(T& a, T& b) {
+#if ENF_F32X2
+    if constexpr (sizeof(T) == 4) {
+        float2 v = make_float2(a, b);
+#pragma unroll
+        for (int off = C::G / 2; off > 0; off >>= 1)
+            v = add2(v, make_float2(__shfl_xor_sync(0xffffffffu, v.x, off), __shfl_xor_sync(0xffffffffu, v.y, off)));
+        a = v.x;
+        b = v.y;
+        return;
+    }
+#endif
+    a = group_sum<C>(a);
+    b = group_sum<C>(b);
+}
+
 // offset of this lane's constants for vector q inside one length-Dp constant array
 template <class C>
 __device__ __forceinline__ int const_off(int q) {
@@ -275,8 +313,13 @@ __device__ __forceinline__ void hh_reflect(Tile<C>& t, const typename C::T (&vk)
                 }
                 d[u] = a.x + a.y;
             }
+            if constexpr (C::SPT % 2 == 0) {
 #pragma unroll
-            for (int u = 0; u < C::SPT; ++u) d[u] = group_sum<C>(d[u]);
+                for (int u = 0; u < C::SPT; u += 2) group_sum2<C>(d[u], d[u + 1]);   // one packed add per shuffle step and sample pair
+            } else {
+#pragma unroll
+                for (int u = 0; u < C::SPT; ++u) d[u] = group_sum<C>(d[u]);
+            }
 #pragma unroll
             for (int u = 0; u < C::SPT; ++u) {
                 const float2 nd = make_float2(-d[u], -d[u]);
@@ -469,7 +512,6 @@ __device__ __forceinline__ void store_ladj(typename C::T* ladj, int64_t tile, ty
 #endif
 constexpr int RING = ENF_RING;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -718,8 +760,8 @@ __global__ void __launch_bounds__(NT, ENF_FWD_MIN_CTAS) chain_fwd_kernel(const _
 }
 
 // backward of one elementwise op on vector q of a tile: xt = the op's input, yt = its output,
-// gt <- input cotangent, ra[k][e] += m[u] * raw integrand k
-template <class C, int KIND>
+// gt <- input cotangent, ra[k][e] += m[u] * raw integrand k  (FULL: every sample of the tile exists, no mask)
+template <class C, int KIND, bool FULL>
 __device__ __forceinline__ void bwd_elem(const Tile<C>& xt, const Tile<C>& yt, Tile<C>& gt, int q,
                                          const typename C::T (&m)[C::SPT][C::LN],
                                          const typename C::T (&c0)[C::VE], const typename C::T (&c1)[C::VE],
@@ -727,6 +769,7 @@ __device__ __forceinline__ void bwd_elem(const Tile<C>& xt, const Tile<C>& yt, T
                                          const typename C::T (&c4)[C::VE], const typename C::T (&c5)[C::VE],
                                          typename C::T (&ra)[4][C::VE]) {
     using T = typename C::T;
+    constexpr int NR = n_rowslots_of(KIND, 0);
 #if ENF_F32X2
     if constexpr (sizeof(T) == 4) {
         // two rows per FP32 instruction: the same templates instantiated for the pair type F2
@@ -754,10 +797,11 @@ __device__ __forceinline__ void bwd_elem(const Tile<C>& xt, const Tile<C>& yt, T
                 }
                 gt.v[u][q][e] = gx.v.x;
                 gt.v[u][q][e + 1] = gx.v.y;
-                const float2 mm = make_float2(m[u][C::slot(e)], m[u][C::slot(e + 1)]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 acc = fma2(mm, r[k].v, make_float2(ra[k][e], ra[k][e + 1]));
+                for (int k = 0; k < NR; ++k) {
+                    float2 acc;
+                    if (FULL) acc = add2(r[k].v, make_float2(ra[k][e], ra[k][e + 1]));
+                    else acc = fma2(make_float2(m[u][C::slot(e)], m[u][C::slot(e + 1)]), r[k].v, make_float2(ra[k][e], ra[k][e + 1]));
                     ra[k][e] = acc.x;
                     ra[k][e + 1] = acc.y;
                 }
@@ -787,7 +831,7 @@ __device__ __forceinline__ void bwd_elem(const Tile<C>& xt, const Tile<C>& yt, T
             }
             gt.v[u][q][e] = gx;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ra[k][e] = Prim<T>::fma_(m[u][C::slot(e)], r[k], ra[k][e]);
+            for (int k = 0; k < NR; ++k) ra[k][e] = FULL ? ra[k][e] + r[k] : Prim<T>::fma_(m[u][C::slot(e)], r[k], ra[k][e]);
         }
 }
 
@@ -797,8 +841,261 @@ __device__ __forceinline__ void bwd_elem(const Tile<C>& xt, const Tile<C>& yt, T
 // Per CTA it emits `n_raw` float64 partial sums:
 //   [n_rowslots][Dp] per-row raw sums | [n_scalars] | sum_j 1/2 |y_j|^2 | sum_j ladj_j (variable part)
 // which reduce_partials_kernel adds up in a fixed order (bitwise reproducible).
+//
+// Shared memory: constants | saved op inputs [n_save][TV][NT] x 16 B | accumulators [n_rowslots][CH][NT] x 16 B
+// | scalar accumulators [n_scalars][NT].  Every per-thread datum is a 16-byte vector at [..][tid]:
+// LDS.128 / STS.128, conflict-free.
+template <typename T>
+struct GradSmem {
+    const T* c;      // constants
+    uint32_t c32;    //   ... as a 32-bit shared-window address
+    uint32_t save;   // 32-bit shared-window addresses of THIS thread's 16-byte slot [..][tid] (immediate offsets per vector):
+    uint32_t acc;    //   saved inputs of the elementwise ops / per-row raw-sum accumulators
+    T* sc;           // per-thread scalar accumulators
+};
+
+// Forward pass of one tile (saving the input of every elementwise op when GRAD).  FULL: every sample of the tile
+// exists (MODE_VEC): predicate-free loads, no masks.  Returns the range flag of the fast ladj path (!SAFE).
+template <class C, bool GRAD, bool FULL, bool SAFE>
+__device__ __forceinline__ bool grad_fwd_tile(const ChainDesc& desc, const GradSmem<typename C::T>& sm, const typename C::T* x,
+                                              int64_t N, int64_t tile, Tile<C>& zt, typename C::T (&l)[C::SPT][C::LN],
+                                              typename C::T (&m)[C::SPT][C::LN]) {
+    using T = typename C::T;
+    constexpr int VE = C::VE;
+    constexpr int TV = C::SPT * C::CH;
+    const int tid = threadIdx.x;
+    const int D = desc.D;
+    if constexpr (FULL) {
+        const int g = tid & (C::G - 1);
+        const T* xb = x + tile_item<C>(tile, 0) * D + g * VE;
+        const int ustride = C::SB * D;
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int q = 0; q < C::CH; ++q) {
+                if ((q * C::G + g) * VE < D) ld16_stream(xb + u * ustride + q * C::G * VE, zt.v[u][q]);
+                else {
+#pragma unroll
+                    for (int e = 0; e < VE; ++e) zt.v[u][q][e] = T(0);
+                }
+            }
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int p = 0; p < C::LN; ++p) l[u][p] = T(0);
+    } else {
+        int nv[C::SPT];
+        load_tile<C>(x, N, D, tile, zt, nv);
+#pragma unroll
+        for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+            for (int p = 0; p < C::LN; ++p) {
+                m[u][p] = p < nv[u] ? T(1) : T(0);
+                l[u][p] = T(0);
+            }
+    }
+    bool bad = false;
+    for (int o = 0; o < desc.n_ops; ++o) {
+        const DevOp op = desc.ops[o];
+        if (GRAD && op.save >= 0) {
+            const uint32_t sv = sm.save + uint32_t(op.save) * uint32_t(TV * NT * 16);
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q) sts16(sv + uint32_t((u * C::CH + q) * NT * 16), zt.v[u][q]);
+        }
+        apply_op_fwd<C, true, SAFE>(op, sm.c, zt, l, bad);
+    }
+    return bad;
+}
+
+// Reverse pass of one tile: gt = N dL/d(activation), seeded with y (src/optimize_whitening.jl:12); zt holds the
+// chain's output on entry and is walked back to the input.
+template <class C, bool FULL>
+__device__ __forceinline__ void grad_bwd_tile(const ChainDesc& desc, const GradSmem<typename C::T>& sm, Tile<C>& zt,
+                                              const typename C::T (&m)[C::SPT][C::LN]) {
+    using T = typename C::T;
+    using P = Prim<T>;
+    constexpr int VE = C::VE;
+    constexpr int TV = C::SPT * C::CH;
+    constexpr int Dp = C::DP;
+    const int tid = threadIdx.x;
+    const int g = tid & (C::G - 1);
+    Tile<C> gt;
+#pragma unroll
+    for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+        for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+            for (int e = 0; e < VE; ++e) gt.v[u][q][e] = zt.v[u][q][e];
+    for (int o = desc.n_ops - 1; o >= 0; --o) {
+        const DevOp op = desc.ops[o];
+        const uint32_t cb = sm.c32 + uint32_t(op.coff) * uint32_t(sizeof(T));   // this op's constants
+        if (op.kind == OP_HH) {
+            // reverse sweep with recomputation (src/householder_trafo.jl:88-114)
+            for (int k = op.K - 1; k >= 0; --k) {
+                T vk[C::CH][VE];
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q) lds16(cb + uint32_t((k * Dp + const_off<C>(q)) * int(sizeof(T))), vk[q]);
+                const uint32_t acc = sm.acc + uint32_t(op.roff + k) * uint32_t(C::CH * NT * 16);
+                T* sc = sm.sc + size_t(op.soff + k) * NT + tid;
+                T a1[C::CH][VE];
+                T a2 = T(0);
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                    for (int e = 0; e < VE; ++e) a1[q][e] = T(0);
+                if (C::PACKED) {
+#pragma unroll
+                    for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                        for (int p = 0; p < C::LN; ++p) {
+                            T po = T(0), qd = T(0);
+#pragma unroll
+                            for (int e = 0; e < C::PD; ++e) {
+                                po = P::fma_(vk[0][p * C::PD + e], zt.v[u][0][p * C::PD + e], po);
+                                qd = P::fma_(vk[0][p * C::PD + e], gt.v[u][0][p * C::PD + e], qd);
+                            }
+                            const T pm = -po * m[u][p], qm = qd * m[u][p];
+#pragma unroll
+                            for (int e = 0; e < C::PD; ++e) {
+                                const int i = p * C::PD + e;
+                                zt.v[u][0][i] = P::fma_(-po, vk[0][i], zt.v[u][0][i]);
+                                a1[0][i] = P::fma_(pm, gt.v[u][0][i], P::fma_(qm, zt.v[u][0][i], a1[0][i]));
+                                gt.v[u][0][i] = P::fma_(-qd, vk[0][i], gt.v[u][0][i]);
+                            }
+                            a2 = P::fma_(pm, qd, a2);
+                        }
+                } else if constexpr (ENF_F32X2 && sizeof(T) == 4) {
+                    // two rows per FFMA2 (same arithmetic as the scalar branch below)
+                    float po[C::SPT], qd[C::SPT];
+#pragma unroll
+                    for (int u = 0; u < C::SPT; ++u) {
+                        float2 ap = make_float2(0.f, 0.f), aq = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                            for (int e = 0; e < VE; e += 2) {
+                                const float2 v2 = make_float2(vk[q][e], vk[q][e + 1]);
+                                ap = fma2(v2, make_float2(zt.v[u][q][e], zt.v[u][q][e + 1]), ap);
+                                aq = fma2(v2, make_float2(gt.v[u][q][e], gt.v[u][q][e + 1]), aq);
+                            }
+                        const float2 pq = add2(make_float2(ap.x, aq.x), make_float2(ap.y, aq.y));
+                        po[u] = pq.x;
+                        qd[u] = pq.y;
+                    }
+#pragma unroll
+                    for (int u = 0; u < C::SPT; ++u) group_sum2<C>(po[u], qd[u]);
+#pragma unroll
+                    for (int u = 0; u < C::SPT; ++u) {
+                        const float pm = FULL ? -po[u] : -po[u] * m[u][0], qm = FULL ? qd[u] : qd[u] * m[u][0];
+                        const float2 npo = make_float2(-po[u], -po[u]), nqd = make_float2(-qd[u], -qd[u]);
+                        const float2 pm2 = make_float2(pm, pm), qm2 = make_float2(qm, qm);
+#pragma unroll
+                        for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                            for (int e = 0; e < VE; e += 2) {
+                                const float2 v2 = make_float2(vk[q][e], vk[q][e + 1]);
+                                const float2 g2 = make_float2(gt.v[u][q][e], gt.v[u][q][e + 1]);
+                                const float2 z2 = fma2(npo, v2, make_float2(zt.v[u][q][e], zt.v[u][q][e + 1]));  // reflection input
+                                const float2 a2v = fma2(pm2, g2, fma2(qm2, z2, make_float2(a1[q][e], a1[q][e + 1])));
+                                const float2 gn = fma2(nqd, v2, g2);
+                                zt.v[u][q][e] = z2.x; zt.v[u][q][e + 1] = z2.y;
+                                a1[q][e] = a2v.x; a1[q][e + 1] = a2v.y;
+                                gt.v[u][q][e] = gn.x; gt.v[u][q][e + 1] = gn.y;
+                            }
+                        a2 = P::fma_(pm, qd[u], a2);
+                    }
+                } else {
+                    T po[C::SPT], qd[C::SPT];
+#pragma unroll
+                    for (int u = 0; u < C::SPT; ++u) {
+                        po[u] = T(0);
+                        qd[u] = T(0);
+#pragma unroll
+                        for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                            for (int e = 0; e < VE; ++e) {
+                                po[u] = P::fma_(vk[q][e], zt.v[u][q][e], po[u]);
+                                qd[u] = P::fma_(vk[q][e], gt.v[u][q][e], qd[u]);
+                            }
+                    }
+#pragma unroll
+                    for (int u = 0; u < C::SPT; ++u) {
+                        po[u] = group_sum<C>(po[u]);
+                        qd[u] = group_sum<C>(qd[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < C::SPT; ++u) {
+                        const T pm = FULL ? -po[u] : -po[u] * m[u][0], qm = FULL ? qd[u] : qd[u] * m[u][0];
+#pragma unroll
+                        for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                            for (int e = 0; e < VE; ++e) {
+                                zt.v[u][q][e] = P::fma_(-po[u], vk[q][e], zt.v[u][q][e]);  // reflection input
+                                a1[q][e] = P::fma_(pm, gt.v[u][q][e], P::fma_(qm, zt.v[u][q][e], a1[q][e]));
+                                gt.v[u][q][e] = P::fma_(-qd[u], vk[q][e], gt.v[u][q][e]);
+                            }
+                        a2 = P::fma_(pm, qd[u], a2);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q) acc16_shared<T, VE>(acc + uint32_t(q * NT * 16), a1[q]);
+                if (g == 0) *sc += a2;
+            }
+            continue;
+        }
+        // elementwise op: zt holds its output; reload its input, differentiate
+        Tile<C> xt;
+        {
+            const uint32_t sv = sm.save + uint32_t(op.save) * uint32_t(TV * NT * 16);
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u)
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q) lds16(sv + uint32_t((u * C::CH + q) * NT * 16), xt.v[u][q]);
+        }
+#pragma unroll
+        for (int q = 0; q < C::CH; ++q) {
+            const int co = const_off<C>(q);
+            T c0[VE], c1[VE], c2[VE], c3[VE], c4[VE], c5[VE];
+            lds16(cb + uint32_t((0 * Dp + co) * int(sizeof(T))), c0);
+            lds16(cb + uint32_t((1 * Dp + co) * int(sizeof(T))), c1);
+            if (op.kind != OP_SS) {
+                lds16(cb + uint32_t((2 * Dp + co) * int(sizeof(T))), c2);
+                lds16(cb + uint32_t((3 * Dp + co) * int(sizeof(T))), c3);
+                lds16(cb + uint32_t((4 * Dp + co) * int(sizeof(T))), c4);
+            }
+            if (op.kind == OP_CS || op.kind == OP_CC || op.kind == OP_JI) lds16(cb + uint32_t((5 * Dp + co) * int(sizeof(T))), c5);
+            T ra[4][VE];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int e = 0; e < VE; ++e) ra[k][e] = T(0);
+            switch (op.kind) {
+                case OP_SS: bwd_elem<C, OP_SS, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                case OP_CS: bwd_elem<C, OP_CS, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                case OP_CC: bwd_elem<C, OP_CC, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                case OP_JO: bwd_elem<C, OP_JO, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                default: bwd_elem<C, OP_JI, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+            }
+            const int nr = n_rowslots_of(op.kind, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < nr) acc16_shared<T, VE>(sm.acc + uint32_t((op.roff + k) * C::CH + q) * uint32_t(NT * 16), ra[k]);
+        }
+        zt = xt;   // the input of this op is the output of the previous one
+    }
+}
+
+#ifndef ENF_GRAD_FLUSH_TILES
+#define ENF_GRAD_FLUSH_TILES 64   // Float32 per-thread accumulation depth: 64 tiles x SPT samples, then folded into float64
+#endif
+constexpr int GRAD_FLUSH_TILES = ENF_GRAD_FLUSH_TILES;
+#ifndef ENF_GRAD_MIN_CTAS
+#define ENF_GRAD_MIN_CTAS 2
+#endif
 template <class C, bool GRAD>
-__global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ ChainDesc desc,
+__global__ void __launch_bounds__(NT, ENF_GRAD_MIN_CTAS) chain_grad_kernel(const __grid_constant__ ChainDesc desc,
                                                         const typename C::T* __restrict__ consts,
                                                         const typename C::T* __restrict__ x, int64_t N,
                                                         double* __restrict__ partials) {
@@ -806,271 +1103,127 @@ __global__ void __launch_bounds__(NT) chain_grad_kernel(const __grid_constant__ 
     using P = Prim<T>;
     constexpr int VE = C::VE;
     constexpr int TV = C::SPT * C::CH;  // 16-byte vectors per thread per tile
-    // shared memory: constants | saved op inputs [n_save][TV][NT] x 16 B | accumulators [n_rowslots][CH][NT] x 16 B
-    // | scalar accumulators [n_scalars][NT].  Every per-thread datum is a 16-byte vector at [..][tid]:
-    // LDS.128 / STS.128, conflict-free.
+    constexpr bool HOTFULL = (C::MODE == MODE_VEC);   // the hot instantiation has no masks: the (one) ragged tile takes the masked path
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* s_c = reinterpret_cast<T*>(smem_raw);
     const int n_consts_al = (desc.n_consts + 3) & ~3;
+    const int tid = threadIdx.x;
     T* s_save = s_c + n_consts_al;
     T* s_acc = s_save + (GRAD ? size_t(desc.n_save) * TV * NT * VE : 0);
-    T* s_sc = s_acc + (GRAD ? size_t(desc.n_rowslots) * C::CH * NT * VE : 0);
+    GradSmem<T> sm;
+    sm.c = s_c;
+    sm.c32 = smem_u32(s_c);
+    sm.save = smem_u32(s_save) + uint32_t(tid) * 16u;
+    sm.acc = smem_u32(s_acc) + uint32_t(tid) * 16u;
+    sm.sc = s_acc + (GRAD ? size_t(desc.n_rowslots) * C::CH * NT * VE : 0);
     stage_constants<C>(desc, consts, s_c);
-    const int tid = threadIdx.x;
-    const int g = tid & (C::G - 1);
     if (GRAD) {
         const T zero[VE] = {};
         for (int i = 0; i < desc.n_rowslots * C::CH; ++i) st16_shared(s_acc + (size_t(i) * NT + tid) * VE, zero);
-        for (int i = 0; i < desc.n_scalars; ++i) s_sc[size_t(i) * NT + tid] = T(0);
+        for (int i = 0; i < desc.n_scalars; ++i) sm.sc[size_t(i) * NT + tid] = T(0);
     }
-    const int D = desc.D;
     constexpr int Dp = C::DP;
     T loss_y = T(0), loss_l = T(0);
+    double loss_y64 = 0.0, loss_l64 = 0.0;
     const int64_t nt = num_tiles<C>(N);
-    for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-        Tile<C> zt;
-        int nv[C::SPT];
-        T l[C::SPT][C::LN];
-        T m[C::SPT][C::LN];  // 1 for real samples, 0 for the padding of the last tile
-        // ---- forward, saving the input of every elementwise op; fast ladj (one log per lane vector), and
-        // the whole forward again with per-element logs if a factor product left the float range
-        auto forward = [&](auto safe) {
-            constexpr bool SAFE = decltype(safe)::value;
-            load_tile<C>(x, N, D, tile, zt, nv);
-#pragma unroll
-            for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                for (int p = 0; p < C::LN; ++p) {
-                    m[u][p] = p < nv[u] ? T(1) : T(0);
-                    l[u][p] = T(0);
-                }
-            bool bad = false;
-            for (int o = 0; o < desc.n_ops; ++o) {
-                const DevOp op = desc.ops[o];
-                if (GRAD && op.save >= 0) {
-                    T* sv = s_save + (size_t(op.save) * TV * NT + tid) * VE;
-#pragma unroll
-                    for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                        for (int q = 0; q < C::CH; ++q) st16_shared(sv + size_t(u * C::CH + q) * NT * VE, zt.v[u][q]);
-                }
-                apply_op_fwd<C, true, SAFE>(op, s_c, zt, l, bad);
-            }
-            return bad;
-        };
-#if ENF_GRAD_SAFE_ONLY
-        forward(std::true_type{});    // per-element logs only: more MUFU work (not the bottleneck here), half the forward code
-#else
-        if (__any_sync(0xffffffffu, forward(std::false_type{}))) forward(std::true_type{});
-#endif
-#pragma unroll
-        for (int u = 0; u < C::SPT; ++u) {
-            T sy = T(0);
-#pragma unroll
-            for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                for (int e = 0; e < VE; ++e) sy = P::fma_(m[u][C::slot(e)] * zt.v[u][q][e], zt.v[u][q][e], sy);
-            loss_y = P::fma_(T(0.5), sy, loss_y);
-#pragma unroll
-            for (int p = 0; p < C::LN; ++p) loss_l = P::fma_(m[u][p], l[u][p], loss_l);
-        }
-        if constexpr (!GRAD) continue;
-        // ---- backward: gt = N dL/d(activation), seeded with y (src/optimize_whitening.jl:12)
-        Tile<C> gt;
-#pragma unroll
-        for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-            for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                for (int e = 0; e < VE; ++e) gt.v[u][q][e] = zt.v[u][q][e];
-        for (int o = desc.n_ops - 1; o >= 0; --o) {
-            const DevOp op = desc.ops[o];
-            const T* cb = s_c + op.coff;
-            if (op.kind == OP_HH) {
-                // reverse sweep with recomputation (src/householder_trafo.jl:88-114)
-                for (int k = op.K - 1; k >= 0; --k) {
-                    T vk[C::CH][VE];
-#pragma unroll
-                    for (int q = 0; q < C::CH; ++q) ld16_shared(cb + k * Dp + const_off<C>(q), vk[q]);
-                    T* acc = s_acc + (size_t(op.roff + k) * C::CH * NT + tid) * VE;
-                    T* sc = s_sc + size_t(op.soff + k) * NT + tid;
-                    T a1[C::CH][VE];
-                    T a2 = T(0);
-#pragma unroll
-                    for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                        for (int e = 0; e < VE; ++e) a1[q][e] = T(0);
-                    if (C::PACKED) {
-#pragma unroll
-                        for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                            for (int p = 0; p < C::LN; ++p) {
-                                T po = T(0), qd = T(0);
-#pragma unroll
-                                for (int e = 0; e < C::PD; ++e) {
-                                    po = P::fma_(vk[0][p * C::PD + e], zt.v[u][0][p * C::PD + e], po);
-                                    qd = P::fma_(vk[0][p * C::PD + e], gt.v[u][0][p * C::PD + e], qd);
-                                }
-                                const T pm = -po * m[u][p], qm = qd * m[u][p];
-#pragma unroll
-                                for (int e = 0; e < C::PD; ++e) {
-                                    const int i = p * C::PD + e;
-                                    zt.v[u][0][i] = P::fma_(-po, vk[0][i], zt.v[u][0][i]);
-                                    a1[0][i] = P::fma_(pm, gt.v[u][0][i], P::fma_(qm, zt.v[u][0][i], a1[0][i]));
-                                    gt.v[u][0][i] = P::fma_(-qd, vk[0][i], gt.v[u][0][i]);
-                                }
-                                a2 = P::fma_(pm, qd, a2);
-                            }
-                    } else if constexpr (ENF_F32X2 && sizeof(T) == 4) {
-                        // two rows per FFMA2 (same arithmetic as the scalar branch below)
-                        float po[C::SPT], qd[C::SPT];
-#pragma unroll
-                        for (int u = 0; u < C::SPT; ++u) {
-                            float2 ap = make_float2(0.f, 0.f), aq = make_float2(0.f, 0.f);
-#pragma unroll
-                            for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                                for (int e = 0; e < VE; e += 2) {
-                                    const float2 v2 = make_float2(vk[q][e], vk[q][e + 1]);
-                                    ap = fma2(v2, make_float2(zt.v[u][q][e], zt.v[u][q][e + 1]), ap);
-                                    aq = fma2(v2, make_float2(gt.v[u][q][e], gt.v[u][q][e + 1]), aq);
-                                }
-                            po[u] = ap.x + ap.y;
-                            qd[u] = aq.x + aq.y;
-                        }
-#pragma unroll
-                        for (int u = 0; u < C::SPT; ++u) {
-                            po[u] = group_sum<C>(po[u]);
-                            qd[u] = group_sum<C>(qd[u]);
-                        }
-#pragma unroll
-                        for (int u = 0; u < C::SPT; ++u) {
-                            const float pm = -po[u] * m[u][0], qm = qd[u] * m[u][0];
-                            const float2 npo = make_float2(-po[u], -po[u]), nqd = make_float2(-qd[u], -qd[u]);
-                            const float2 pm2 = make_float2(pm, pm), qm2 = make_float2(qm, qm);
-#pragma unroll
-                            for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                                for (int e = 0; e < VE; e += 2) {
-                                    const float2 v2 = make_float2(vk[q][e], vk[q][e + 1]);
-                                    const float2 g2 = make_float2(gt.v[u][q][e], gt.v[u][q][e + 1]);
-                                    const float2 z2 = fma2(npo, v2, make_float2(zt.v[u][q][e], zt.v[u][q][e + 1]));  // reflection input
-                                    const float2 a2v = fma2(pm2, g2, fma2(qm2, z2, make_float2(a1[q][e], a1[q][e + 1])));
-                                    const float2 gn = fma2(nqd, v2, g2);
-                                    zt.v[u][q][e] = z2.x; zt.v[u][q][e + 1] = z2.y;
-                                    a1[q][e] = a2v.x; a1[q][e + 1] = a2v.y;
-                                    gt.v[u][q][e] = gn.x; gt.v[u][q][e + 1] = gn.y;
-                                }
-                            a2 = P::fma_(pm, qd[u], a2);
-                        }
-                    } else {
-                        T po[C::SPT], qd[C::SPT];
-#pragma unroll
-                        for (int u = 0; u < C::SPT; ++u) {
-                            po[u] = T(0);
-                            qd[u] = T(0);
-#pragma unroll
-                            for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                                for (int e = 0; e < VE; ++e) {
-                                    po[u] = P::fma_(vk[q][e], zt.v[u][q][e], po[u]);
-                                    qd[u] = P::fma_(vk[q][e], gt.v[u][q][e], qd[u]);
-                                }
-                        }
-#pragma unroll
-                        for (int u = 0; u < C::SPT; ++u) {
-                            po[u] = group_sum<C>(po[u]);
-                            qd[u] = group_sum<C>(qd[u]);
-                        }
-#pragma unroll
-                        for (int u = 0; u < C::SPT; ++u) {
-                            const T pm = -po[u] * m[u][0], qm = qd[u] * m[u][0];
-#pragma unroll
-                            for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-                                for (int e = 0; e < VE; ++e) {
-                                    zt.v[u][q][e] = P::fma_(-po[u], vk[q][e], zt.v[u][q][e]);  // reflection input
-                                    a1[q][e] = P::fma_(pm, gt.v[u][q][e], P::fma_(qm, zt.v[u][q][e], a1[q][e]));
-                                    gt.v[u][q][e] = P::fma_(-qd[u], vk[q][e], gt.v[u][q][e]);
-                                }
-                            a2 = P::fma_(pm, qd[u], a2);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < C::CH; ++q) acc16_shared<T, VE>(acc + size_t(q) * NT * VE, a1[q]);
-                    if (g == 0) *sc += a2;
-                }
-                continue;
-            }
-            // elementwise op: zt holds its output; reload its input, differentiate
-            Tile<C> xt;
-            {
-                const T* sv = s_save + (size_t(op.save) * TV * NT + tid) * VE;
-#pragma unroll
-                for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-                    for (int q = 0; q < C::CH; ++q) ld16_shared(sv + size_t(u * C::CH + q) * NT * VE, xt.v[u][q]);
-            }
-#pragma unroll
-            for (int q = 0; q < C::CH; ++q) {
-                const int co = const_off<C>(q);
-                T c0[VE], c1[VE], c2[VE], c3[VE], c4[VE], c5[VE];
-                ld16_shared(cb + 0 * Dp + co, c0);
-                ld16_shared(cb + 1 * Dp + co, c1);
-                if (op.kind != OP_SS) {
-                    ld16_shared(cb + 2 * Dp + co, c2);
-                    ld16_shared(cb + 3 * Dp + co, c3);
-                }
-                if (op.kind != OP_SS) ld16_shared(cb + 4 * Dp + co, c4);
-                if (op.kind == OP_CS || op.kind == OP_CC || op.kind == OP_JI) ld16_shared(cb + 5 * Dp + co, c5);
-                T ra[4][VE];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int e = 0; e < VE; ++e) ra[k][e] = T(0);
-                switch (op.kind) {
-                    case OP_SS: bwd_elem<C, OP_SS>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                    case OP_CS: bwd_elem<C, OP_CS>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                    case OP_CC: bwd_elem<C, OP_CC>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                    case OP_JO: bwd_elem<C, OP_JO>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                    default: bwd_elem<C, OP_JI>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                }
-                const int nr = n_rowslots_of(op.kind, 0);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (k < nr) acc16_shared<T, VE>(s_acc + ((size_t(op.roff + k) * C::CH + q) * NT + tid) * VE, ra[k]);
-            }
-            zt = xt;   // the input of this op is the output of the previous one
-        }
-    }
-    // ---- CTA reduction in float64, fixed order
+    const int64_t n_items = C::PACKED ? ((N + C::LN - 1) / C::LN) : N;
     const int n_raw = desc.n_rowslots * Dp + desc.n_scalars + 2;
     double* out = partials + size_t(blockIdx.x) * n_raw;
-    __syncthreads();
-    if (GRAD) {
-        for (int pi = tid; pi < desc.n_rowslots * Dp; pi += NT) {
-            const int rs = pi / Dp, row = pi - rs * Dp;
-            const int vecidx = row / VE, e = row - vecidx * VE;
-            int q, gg;
-            if (C::PACKED) { q = 0; gg = 0; }
-            else { q = vecidx >> C::LG; gg = vecidx & (C::G - 1); }
-            const T* acc = s_acc + (size_t(rs) * C::CH + q) * NT * VE + e;
-            double s = 0.0;
-            for (int j = gg; j < NT; j += C::G) s += double(acc[size_t(j) * VE]);
-            out[pi] = s;
+    // The per-thread accumulators are Float32 for Float32 chains.  To keep their depth bounded however many tiles a CTA
+    // visits (the grid is capped at a few CTAs per SM), they are folded into the float64 partial sums of this CTA - in
+    // a fixed order, so the result stays bitwise reproducible - every GRAD_FLUSH_TILES tiles and cleared.
+    bool first_flush = true;
+    auto flush = [&](bool first) {
+        __syncthreads();
+        if (GRAD) {
+            for (int pi = tid; pi < desc.n_rowslots * Dp; pi += NT) {
+                const int rs = pi / Dp, row = pi - rs * Dp;
+                const int vecidx = row / VE, e = row - vecidx * VE;
+                int q, gg;
+                if (C::PACKED) { q = 0; gg = 0; }
+                else { q = vecidx >> C::LG; gg = vecidx & (C::G - 1); }
+                const T* acc = s_acc + (size_t(rs) * C::CH + q) * NT * VE + e;
+                double sacc = 0.0;
+                for (int j = gg; j < NT; j += C::G) sacc += double(acc[size_t(j) * VE]);
+                out[pi] = first ? sacc : out[pi] + sacc;
+            }
+            for (int k = tid; k < desc.n_scalars; k += NT) {
+                const T* sc = sm.sc + size_t(k) * NT;
+                double sacc = 0.0;
+                for (int j = 0; j < NT; j += C::G) sacc += double(sc[j]);
+                double* o = out + desc.n_rowslots * Dp + k;
+                *o = first ? sacc : *o + sacc;
+            }
+            __syncthreads();
+            const T zero[VE] = {};
+            for (int i = 0; i < desc.n_rowslots * C::CH; ++i) st16_shared(s_acc + (size_t(i) * NT + tid) * VE, zero);
+            for (int i = 0; i < desc.n_scalars; ++i) sm.sc[size_t(i) * NT + tid] = T(0);
+        } else if (first) {
+            for (int pi = tid; pi < desc.n_rowslots * Dp + desc.n_scalars; pi += NT) out[pi] = 0.0;
         }
-        for (int k = tid; k < desc.n_scalars; k += NT) {
-            const T* sc = s_sc + size_t(k) * NT;
-            double s = 0.0;
-            for (int j = 0; j < NT; j += C::G) s += double(sc[j]);
-            out[desc.n_rowslots * Dp + k] = s;
+        loss_y64 += double(loss_y);
+        loss_l64 += double(loss_l);
+        loss_y = T(0);
+        loss_l = T(0);
+    };
+    int visited = 0;
+    for (int64_t tile = blockIdx.x; tile < nt; tile += gridDim.x, ++visited) {
+        if (visited != 0 && (visited % GRAD_FLUSH_TILES) == 0) {
+            flush(first_flush);
+            first_flush = false;
         }
-    } else {
-        for (int pi = tid; pi < desc.n_rowslots * Dp + desc.n_scalars; pi += NT) out[pi] = 0.0;
+        Tile<C> zt;
+        T l[C::SPT][C::LN];
+        T m[C::SPT][C::LN];  // 1 for real samples, 0 for the padding of the last tile (unused on full tiles)
+        const bool full = HOTFULL && (tile + 1) * (int64_t(C::SB) * C::SPT) <= n_items;
+        // forward with the fast ladj (one log per op and lane-sample); the whole forward again with per-element
+        // logs (and masks) if a factor product left the float range; the ragged last tile is always masked
+        bool use_mask;
+        if (full) {
+            use_mask = __any_sync(0xffffffffu, grad_fwd_tile<C, GRAD, HOTFULL, false>(desc, sm, x, N, tile, zt, l, m));
+            if (use_mask) grad_fwd_tile<C, GRAD, false, true>(desc, sm, x, N, tile, zt, l, m);
+        } else if (HOTFULL) {
+            grad_fwd_tile<C, GRAD, false, true>(desc, sm, x, N, tile, zt, l, m);
+            use_mask = true;
+        } else {
+            // layouts without a mask-free path (scalar / packed accesses): fast masked forward first
+            if (__any_sync(0xffffffffu, grad_fwd_tile<C, GRAD, false, false>(desc, sm, x, N, tile, zt, l, m)))
+                grad_fwd_tile<C, GRAD, false, true>(desc, sm, x, N, tile, zt, l, m);
+            use_mask = true;
+        }
+        if (!use_mask) {
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u) {
+                T sy = T(0);
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                    for (int e = 0; e < VE; ++e) sy = P::fma_(zt.v[u][q][e], zt.v[u][q][e], sy);
+                loss_y = P::fma_(T(0.5), sy, loss_y);
+#pragma unroll
+                for (int p = 0; p < C::LN; ++p) loss_l += l[u][p];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u) {
+                T sy = T(0);
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                    for (int e = 0; e < VE; ++e) sy = P::fma_(m[u][C::slot(e)] * zt.v[u][q][e], zt.v[u][q][e], sy);
+                loss_y = P::fma_(T(0.5), sy, loss_y);
+#pragma unroll
+                for (int p = 0; p < C::LN; ++p) loss_l = P::fma_(m[u][p], l[u][p], loss_l);
+            }
+        }
+        if constexpr (!GRAD) continue;
+        if (!use_mask) grad_bwd_tile<C, HOTFULL>(desc, sm, zt, m);
+        else grad_bwd_tile<C, false>(desc, sm, zt, m);
     }
+    flush(first_flush);
     // loss partials: warp shuffle, then one double per warp through shared memory
     __shared__ double s_loss[2][NT / 32];
-    double ly = double(loss_y), ll = double(loss_l) * double(Prim<T>::LGU);
+    double ly = loss_y64, ll = loss_l64 * double(Prim<T>::LGU);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         ly += __shfl_xor_sync(0xffffffffu, ly, off);

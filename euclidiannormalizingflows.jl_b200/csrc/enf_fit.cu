@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(256) fit_update_kernel(const __grid_constant__
             const double r0 = row_sum(fd, sums, op.roff, 0, i), r1 = row_sum(fd, sums, op.roff, 1, i);
             int nf = 2;
             switch (op.kind) {
-                case OP_CS: { const double r2 = row_sum(fd, sums, op.roff, 2, i); g[0] = r1; g[1] = r2; g[2] = r0; nf = 3; break; }
-                case OP_CC: { const double r2 = row_sum(fd, sums, op.roff, 2, i); g[0] = r1; g[1] = r2; g[2] = -r0; nf = 3; break; }
+                case OP_CS: { const double r2 = row_sum(fd, sums, op.roff, 2, i); g[0] = -r1; g[1] = -r2 / p[D + i]; g[2] = r0; nf = 3; break; }
+                case OP_CC: { const double r2 = row_sum(fd, sums, op.roff, 2, i); g[0] = r1; g[1] = r2 / p[D + i]; g[2] = -r0; nf = 3; break; }
                 case OP_JO: {
                     const double r2 = row_sum(fd, sums, op.roff, 2, i), r3 = row_sum(fd, sums, op.roff, 3, i);
                     const double gm = p[i], dl = p[D + i], lm = p[3 * D + i];

@@ -49,7 +49,7 @@ cudaError_t launch_reduce(const double* partials, int n_blocks, int n_raw, doubl
 constexpr int P2P_MAX_RANKS = 16;
 constexpr int P2P_SLOT = 8192;                         // doubles per rank and parity
 constexpr size_t P2P_SEQ_OFF = 0, P2P_ERR_OFF = 8, P2P_FLAG_OFF = 256, P2P_DATA_OFF = 1024;
-constexpr long long P2P_SPIN_LIMIT = 4000000;          // ~1 s of waiting for a peer before giving up
+constexpr long long P2P_SPIN_LIMIT = 400000000;        // ~2 minutes of waiting for a peer (rank skew: first-call set-up, host jitter) before giving up
 inline size_t p2p_bytes(int nranks) { return P2P_DATA_OFF + size_t(2) * nranks * P2P_SLOT * sizeof(double); }
 struct P2PDesc {
     void* peer[P2P_MAX_RANKS];                         // peer[r]: rank r's buffer as mapped in this process

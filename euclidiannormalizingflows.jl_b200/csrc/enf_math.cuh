@@ -51,6 +51,13 @@ template <> struct Prim<float> {
     static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
     static __device__ __forceinline__ float sign_(float x) { return x < 0.f ? -1.f : 1.f; }
     static __device__ __forceinline__ float csign(float mag, float sgn) { return copysignf(mag, sgn); }
+    // v * sign(s) as a sign-bit XOR (one LOP3 on the ALU pipe instead of a compare, a select and a multiply)
+    static __device__ __forceinline__ float xsign(float v, float s) {
+        return __uint_as_float(__float_as_uint(v) ^ (__float_as_uint(s) & 0x80000000u));
+    }
+    static __device__ __forceinline__ float xnsign(float v, float s) {   // -v * sign(s)
+        return __uint_as_float(__float_as_uint(v) ^ (~__float_as_uint(s) & 0x80000000u));
+    }
     // lg(|z| + sqrt(1+z^2)) * sign(z), given s = 1 + z^2 and r = rsqrt(s)   [asinh(z) / LGU]
     static __device__ __forceinline__ float asinh_lg(float z, float s, float r) {
         return copysignf(lg(fma_(s, r, fabsf(z))), z);
@@ -84,6 +91,12 @@ template <> struct Prim<double> {
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
     static __device__ __forceinline__ double sign_(double x) { return x < 0.0 ? -1.0 : 1.0; }
     static __device__ __forceinline__ double csign(double mag, double sgn) { return copysign(mag, sgn); }
+    static __device__ __forceinline__ double xsign(double v, double s) {
+        return __longlong_as_double(__double_as_longlong(v) ^ (__double_as_longlong(s) & (long long)0x8000000000000000ull));
+    }
+    static __device__ __forceinline__ double xnsign(double v, double s) {
+        return __longlong_as_double(__double_as_longlong(v) ^ (~__double_as_longlong(s) & (long long)0x8000000000000000ull));
+    }
     static __device__ __forceinline__ double asinh_lg(double z, double s, double r) { return asinh(z); }
     static __device__ __forceinline__ void sinhcosh(double sa, double& sh, double& ch) {
         sh = sinh(sa);
@@ -437,80 +450,78 @@ struct Prim<F2> {
     static __device__ __forceinline__ F2 fma_(F2 a, F2 b, F2 c) { return F2(fma2(a.v, b.v, c.v)); }
     static __device__ __forceinline__ F2 abs_(F2 x) { return F2(fabsf(x.v.x), fabsf(x.v.y)); }
     static __device__ __forceinline__ F2 sign_(F2 x) { return F2(x.v.x < 0.f ? -1.f : 1.f, x.v.y < 0.f ? -1.f : 1.f); }
+    static __device__ __forceinline__ F2 xsign(F2 v, F2 s) { return F2(S::xsign(v.v.x, s.v.x), S::xsign(v.v.y, s.v.y)); }
+    static __device__ __forceinline__ F2 xnsign(F2 v, F2 s) { return F2(S::xnsign(v.v.x, s.v.x), S::xnsign(v.v.y, s.v.y)); }
 };
 
 // ---------------------------------------------------------------- backward
 // Every *_bwd takes the op's INPUT x, its OUTPUT y (both are at hand in the reverse sweep: y is the
 // input of the next op) and the output cotangent G; it returns the input cotangent and writes the
 // raw-sum integrands r[...] (summed over samples on the device, mapped to parameter gradients by
-// enf_abi.cu: finish).  Using y avoids recomputing the forward transcendental (log / asinh / sinh), and
-// the three reciprocals of the CenterContract sigmoids collapse into one:
-//   n1 = 1 + A w, n2 = A + w, n3 = n2 + w n1, R = 1/(n1 n2 n3):
-//   sigma_1 = 1/n1 = n2 n3 R,  sigma_2 = w/n2 = w n1 n3 R,  S = n3/(n1 n2) = n3^2 R,  1/S = (n1 n2)^2 R.
-
+// enf_abi.cu: finish).  Using y avoids recomputing the forward transcendental (log / asinh / sinh).
+//
+// CenterContract / CenterStretch share the sigmoid algebra of src/center_stretch.jl:17-22.  With w = e^{-b|u|},
+// A = e^{ba}:  n1 = 1 + A w, n2 = A + w, n3 = n2 + w n1, ONE reciprocal R = 1/(n1 n2 n3), t = n3 R = 1/(n1 n2):
+//   sigma_1 = 1/n1, sigma_2 = w/n2, S = sigma_1 + sigma_2 = n3 t, ds = sigma_2 - sigma_1 = (w n1 - n2) t,
+//   sigma_i' = sigma_i (1 - sigma_i):  sigma_1' = A w / n1^2, sigma_2' = A w / n2^2   (no 1 - sigma cancellation),
+//   E_i = b sigma_i' / S = (b A w R) n_(3-i)^2;  Ed = E1 - E2 = b S_u / S (times sign u), Es = E1 + E2 = -b S_a / S ... (1/b) of
+//   the reference's dladj/du, dladj/da; dladj/db = (|u| Ed - a Es) / b.
+// The b-gradient integrand is accumulated times b (one multiplication per row on the host instead of one per element).
 template <typename T>
-struct CcParts { T S, iS, Su, Sa, Sb, ds; };   // ds = sigma_2 - sigma_1
+struct CcParts { T S, iS, ds, nEd, Es; };   // nEd = -Ed
 
-template <typename T>
-__device__ __forceinline__ CcParts<T> cc_parts(T au, T w, T A, T a, T b, T& s1au, T& s2au) {
+template <typename T, bool INV>
+__device__ __forceinline__ CcParts<T> cc_parts(T w, T A, T b) {
     using P = Prim<T>;
-    const T n1 = P::fma_(A, w, T(1));
+    const T aw = A * w;
+    const T n1 = aw + T(1);
     const T n2 = A + w;
     const T n3 = P::fma_(w, n1, n2);
     const T p12 = n1 * n2;
     const T R = P::rcp(p12 * n3);
     const T t = n3 * R;
-    const T s1 = n2 * t;
-    const T s2 = w * n1 * t;
-    const T d1 = s1 * (T(1) - s1);
-    const T d2 = s2 * (T(1) - s2);
+    const T hb = (aw * b) * R;
+    const T q1 = n1 * n1, q2 = n2 * n2;
     CcParts<T> o;
     o.S = n3 * t;
-    o.iS = p12 * (p12 * R);
-    o.Su = b * (d1 - d2);
-    o.Sa = -b * (d1 + d2);
-    o.Sb = (au - a) * d1 - (au + a) * d2;
-    o.ds = s2 - s1;
-    s1au = s1 * (au - a);
-    s2au = s2 * (au + a);
+    o.ds = P::fma_(w, n1, -n2) * t;
+    o.nEd = hb * (q1 - q2);
+    o.Es = hb * (q1 + q2);
+    if (INV) o.iS = p12 * (p12 * R);
     return o;
 }
 
-// CenterContract.  raw: r0 -> -dc, r1 -> da, r2 -> db.
+// CenterContract.  raw: r0 -> -dc, r1 -> da, r2 -> b db.
 template <typename T>
 __device__ __forceinline__ T cc_bwd(T x, T y, T G, T nb2, T A, T ib2, T c, T a, T b, T* r) {
     using P = Prim<T>;
-    const T ib = ib2 * P::INV_LGU;
     const T u = x - c;
     const T au = P::abs_(u);
-    const T sg = P::sign_(u);
-    T s1au, s2au;
-    const CcParts<T> k = cc_parts<T>(au, P::ex2(nb2 * au), A, a, b, s1au, s2au);
-    const T ya_b = (s1au + s2au - P::abs_(y)) * ib;
-    const T Gx = G * k.S - sg * k.Su * k.iS;       // LB = -1
+    const CcParts<T> k = cc_parts<T, false>(P::ex2(nb2 * au), A, b);
+    const T sgG = P::xsign(G, u);                                   // sign(u) G
+    const T Gx = P::fma_(G, k.S, P::xsign(k.nEd, u));               // G S + LB sign(u) b S_u / S,  LB = -1
+    const T ya = P::fma_(au, k.S, a * k.ds) - P::abs_(y);           // b d|y|/db
     r[0] = Gx;
-    r[1] = sg * G * k.ds - k.Sa * k.iS;
-    r[2] = sg * G * ya_b - k.Sb * k.iS;
+    r[1] = P::fma_(sgG, k.ds, k.Es);
+    r[2] = P::fma_(sgG, ya, P::fma_(au, k.nEd, a * k.Es));
     return Gx;
 }
 
 // CenterStretch (implicit inverse of CenterContract: its output y plays the contract's input).
-// raw: r0 -> dc, r1 -> da, r2 -> db.
+// raw: r0 -> dc, r1 -> -da, r2 -> -b db.
 template <typename T>
 __device__ __forceinline__ T cs_bwd(T x, T y, T G, T nb2, T A, T ib2, T c, T a, T b, T* r) {
     using P = Prim<T>;
-    const T ib = ib2 * P::INV_LGU;
     const T u = y - c;
     const T au = P::abs_(u);
-    const T sg = P::sign_(x);
-    T s1au, s2au;
-    const CcParts<T> k = cc_parts<T>(au, P::ex2(nb2 * au), A, a, b, s1au, s2au);
-    const T Cb = (s1au + s2au - P::abs_(x)) * ib;
-    const T Gy = G + sg * k.Su * k.iS;              // G - LB*sg*Su/S
+    const CcParts<T> k = cc_parts<T, true>(P::ex2(nb2 * au), A, b);
+    const T Gy = G + P::xnsign(k.nEd, x);                           // G - LB sign(x) b S_u / S
     const T Gx = Gy * k.iS;
+    const T sgGx = P::xsign(Gx, x);
+    const T cb = P::fma_(au, k.S, a * k.ds) - P::abs_(x);
     r[0] = G;
-    r[1] = -Gx * sg * k.ds + k.Sa * k.iS;
-    r[2] = -Gx * sg * Cb + k.Sb * k.iS;
+    r[1] = P::fma_(sgGx, k.ds, k.Es);
+    r[2] = P::fma_(sgGx, cb, P::fma_(au, k.nEd, a * k.Es));
     return Gx;
 }
 

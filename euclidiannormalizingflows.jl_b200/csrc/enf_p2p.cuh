@@ -48,11 +48,15 @@ __device__ __forceinline__ void p2p_allreduce_block(const P2PDesc& d, double* __
         long long spins = 0;
         while (ld_acquire_sys(flag) < seq) {
             if (++spins > P2P_SPIN_LIMIT) {
-                *reinterpret_cast<int*>(local + P2P_ERR_OFF) = 1;
+                // a rank never arrived: raise the sticky error flag in EVERY rank's buffer, so that the ranks that do
+                // complete this exchange later fail the same way at their next p2p_check (enf_abi.cu)
+                for (int r = 0; r < R; ++r)
+                    *reinterpret_cast<volatile int*>(static_cast<unsigned char*>(d.peer[r]) + P2P_ERR_OFF) = 1;
+                __threadfence_system();
                 s_timeout = 1;
                 break;
             }
-            __nanosleep(64);
+            __nanosleep(spins < 4096 ? 32 : 256);
         }
     }
     __syncthreads();
@@ -63,9 +67,11 @@ __device__ __forceinline__ void p2p_allreduce_block(const P2PDesc& d, double* __
         sums[i] = a;
     }
     __syncthreads();
-    // a rank did not show up: poison the last value (the sample count of the batch) so that the host notices with the
-    // copy it makes anyway
-    if (s_timeout && tid == 0) sums[n - 1] = __longlong_as_double(0x7FF8000000000000LL);
+    // a rank did not show up (here, or in an earlier exchange of any rank: the error flag is sticky and raised in every
+    // rank's buffer): poison the last value (the sample count of the batch) so that the host notices with the copy it
+    // makes anyway
+    if (tid == 0 && (s_timeout || *reinterpret_cast<volatile int*>(local + P2P_ERR_OFF) != 0))
+        sums[n - 1] = __longlong_as_double(0x7FF8000000000000LL);
 }
 
 }  // namespace

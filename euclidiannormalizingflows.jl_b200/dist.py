@@ -36,6 +36,14 @@ def shard_batches(ranges: List[Tuple[int, int]], rank: int, world: int) -> List[
     return out
 
 
+def local_batch_counts(n_global: int, nbatches: int, rank: int, world: int) -> List[int]:
+    """Number of columns of every global batch (src/optimize_whitening.jl:31-32 on the GLOBAL sample count) that
+    fall to `rank`: what `optimize_whitening(..., group=True, batch_counts=...)` needs when the local sample counts
+    of the ranks differ (deriving the batches from the local count would give the ranks different numbers of steps)."""
+    from .whitening import batch_ranges
+    return [b - a for a, b in shard_batches(batch_ranges(n_global, nbatches), rank, world)]
+
+
 def allreduce_sums(sums: np.ndarray, n_local: int):
     """Host-side all-reduce of raw float64 sums plus the local sample count over
     the default torch.distributed group (gloo or nccl).  Returns (sums, N_global).

@@ -76,8 +76,8 @@ def _pack_tree(trafo, tree, D):
     for lf, st in zip(flatten(trafo), _leaves_of(trafo, tree)):
         for n in lf.fields:
             a = np.asarray(st[n], dtype=np.float64)
-            if a.ndim == 0:
-                raise TypeError("the device loop needs vector-valued parameters (expand scalar fields first)")
+            if a.ndim == 0 and D > 1:
+                raise TypeError("the device loop needs vector-valued parameters (one value per row)")
             out.append(np.asfortranarray(a.reshape(D, -1)).ravel(order="F"))
     return np.ascontiguousarray(np.concatenate(out))
 
@@ -113,21 +113,36 @@ def _rebuild(trafo, tree):
     return type(trafo)(**{n: tree[n] for n in trafo.fields})
 
 
-def _optimize_whitening_device(smpls, trafo, optimizer, nbatches, nepochs, optstate, group):
+def _optimize_whitening_device(smpls, trafo, optimizer, nbatches, nepochs, optstate, group, batch_counts=None):
     """enf_optimize_whitening: the whole loop on the device."""
     import ctypes as C
     from . import _lib as L
     from .trafos import get_chain
     ctx = smpls.ctx
+    # The C ABI trains one parameter per row and field.  A scalar-valued field of the reference structs is ONE shared
+    # parameter (its gradient is the sum over the rows): for D > 1 that is a different model, so it is rejected here
+    # instead of being expanded silently; for D = 1 the two coincide.
+    if smpls.D > 1:
+        for lf in flatten(trafo):
+            for n in lf.fields:
+                if np.ndim(getattr(lf, n)) == 0:
+                    raise TypeError(f"{type(lf).__name__}.{n} is a scalar: the device loop needs vector-valued parameters "
+                                    "(one value per row); use the host loop (device_loop=False) for shared scalar fields")
     ch = get_chain(trafo, smpls.D, smpls.dtype, ctx)
     P = ch.nparams
     state = _pack_tree(trafo, optstate, smpls.D) if optstate is not None else np.empty(P, dtype=np.float64)
-    nb = len(batch_ranges(smpls.N, nbatches))
+    if batch_counts is None:
+        batch_counts = [e - s for s, e in batch_ranges(smpls.N, nbatches)]
+    counts = np.asarray(batch_counts, dtype=np.int64)
+    if counts.sum() != smpls.N:
+        raise ValueError(f"batch_counts sum to {counts.sum()} but there are {smpls.N} local samples")
+    nb = len(counts)
     hist = np.empty(max(nb * nepochs, 1), dtype=np.float64)
     params = np.empty(P, dtype=smpls.dtype)
     n_steps = C.c_int64()
-    L.check(ctx._lib.enf_optimize_whitening(
-        ch.handle, C.c_void_p(smpls.ptr), smpls.N, int(nbatches), int(nepochs), float(optimizer.eta), float(optimizer.epsilon),
+    L.check(ctx._lib.enf_optimize_whitening_batches(
+        ch.handle, C.c_void_p(smpls.ptr), nb, counts.ctypes.data_as(C.POINTER(C.c_int64)), int(nepochs),
+        float(optimizer.eta), float(optimizer.epsilon),
         L.ENF_NEGLL_ZYGOTE_PRIMAL, 1 if group else 0, 0 if optstate is not None else 1,
         state.ctypes.data_as(C.c_void_p), params.ctypes.data_as(C.c_void_p), hist.ctypes.data_as(C.c_void_p),
         C.byref(n_steps)), ctx.handle)
@@ -138,25 +153,34 @@ def _optimize_whitening_device(smpls, trafo, optimizer, nbatches, nepochs, optst
 
 def optimize_whitening(smpls, initial_trafo, optimizer: ADAGrad, *, nbatches: int = 100, nepochs: int = 100,
                        optstate=None, negll_history=None, group: bool = False, ctx: Optional[Context] = None,
-                       device_loop: bool = False):
+                       device_loop: bool = False, batch_counts=None):
     """Returns {'result', 'optimizer_state', 'negll_history'} like the
     reference's NamedTuple.  `smpls`: D x N samples (B200Matrix, or a host array
     that is uploaded once).  group=True: `smpls` holds this rank's column block
     of every global batch (see dist.shard_batches); all ranks apply the
-    identical update from all-reduced sums.  device_loop=True: the whole loop runs on the device
-    (enf_optimize_whitening: four kernel launches per step, no host round trip)."""
+    identical update from all-reduced sums.  batch_counts: number of local columns of every batch (default: the
+    batches of src/optimize_whitening.jl:31-32 on the LOCAL sample count; with group=True pass
+    dist.local_batch_counts(N_global, nbatches, rank, world) whenever the ranks hold different numbers of samples --
+    every rank must take the same number of steps).  device_loop=True: the whole loop runs on the device
+    (enf_optimize_whitening_batches: two kernel launches per step, no host round trip)."""
     if not isinstance(smpls, B200Matrix):
         X = np.asarray(smpls)
         dt = result_dtype(initial_trafo, X.dtype if X.dtype.kind == "f" else np.float64)
         smpls = B200Matrix.from_host(np.asarray(X, dtype=dt), ctx or default_context())
     if device_loop:
         result, state, hist = _optimize_whitening_device(smpls, copy.deepcopy(initial_trafo), optimizer, nbatches, nepochs,
-                                                         optstate, group)
+                                                         optstate, group, batch_counts)
         return {"result": result, "optimizer_state": state, "negll_history": list(negll_history or []) + hist}
     trafo = copy.deepcopy(initial_trafo)
     state = copy.deepcopy(optstate) if optstate is not None else setup(optimizer, trafo)
     hist: List[float] = []
-    ranges = batch_ranges(smpls.N, nbatches)
+    if batch_counts is None:
+        ranges = batch_ranges(smpls.N, nbatches)
+    else:
+        ends = np.cumsum(np.asarray(batch_counts, dtype=np.int64))
+        if len(ends) == 0 or ends[-1] != smpls.N:
+            raise ValueError("batch_counts must sum to the number of local samples")
+        ranges = [(int(e - c), int(e)) for c, e in zip(batch_counts, ends)]
     for _ in range(nepochs):
         for (s, e) in ranges:
             negll, d_trafo = mvnormal_negll_trafograd(trafo, smpls.cols(s, e), group=group)

@@ -137,8 +137,8 @@ int enf_negll_grad(enf_chain* chain, const void* x_dev, int64_t N, int flags,
 
 /* Two-phase form used for sharded batches: phase 1 leaves this rank's
  * un-normalised partial sums (float64, `n` of them) in a device buffer owned by
- * the chain; the caller all-reduces them (enf_group_allreduce_sums or any other
- * transport); phase 2 maps the summed vector to (negll, grads) for the GLOBAL
+ * the chain; the caller all-reduces them (any transport; enf_negll_grad_group
+ * does all three steps with the library's own exchange); phase 2 maps the summed vector to (negll, grads) for the GLOBAL
  * batch size. */
 int enf_negll_grad_partial(enf_chain* chain, const void* x_dev, int64_t N_local,
                            double** sums_dev, int64_t* n);
@@ -180,6 +180,16 @@ int enf_negll_grad_group(enf_chain* chain, const void* x_dev, int64_t N_local, i
 int enf_optimize_whitening(enf_chain* chain, const void* x_dev, int64_t N, int64_t nbatches, int64_t nepochs,
                            double eta, double epsilon, int flags, int use_group, int fresh_state,
                            double* state_inout, void* params_out, double* history_out, int64_t* n_steps_out);
+
+/* The same loop over explicitly given batches: batch b is the next local_counts[b] consecutive columns of x.  This is the
+ * form for sharded data (use_group != 0): x holds this rank's columns of every global batch in batch order and
+ * local_counts[b] how many of them belong to global batch b (zero is allowed: the rank then only takes part in the
+ * exchange of that step).  Every rank must pass the same n_batches; the library compares it over the group before
+ * anything is launched and fails on every rank (ENF_ERR_INVALID) if they differ.  enf_optimize_whitening(N, nbatches)
+ * is this call with the counts of src/optimize_whitening.jl:31-32 derived from the LOCAL N. */
+int enf_optimize_whitening_batches(enf_chain* chain, const void* x_dev, int64_t n_batches, const int64_t* local_counts,
+                                   int64_t nepochs, double eta, double epsilon, int flags, int use_group, int fresh_state,
+                                   double* state_inout, void* params_out, double* history_out, int64_t* n_steps_out);
 
 /* ---- timing on the context stream ---------------------------------------------
  * The library launches on its own stream, which events of other libraries do

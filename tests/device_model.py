@@ -97,64 +97,63 @@ def hh_fwd(x, V):
 
 # ---------------------------------------------------------------- backward
 # each returns (Gx, raw) ; finish_*() maps raw sums -> parameter gradients
-def _cc_parts(au, w, A, a, b):
-    """sigma_1 = 1/n1, sigma_2 = w/n2, S = sigma_1 + sigma_2 and 1/S from ONE reciprocal."""
-    n1 = 1 + A * w
+def _cc_parts(w, A, b):
+    """sigma_1 = 1/n1, sigma_2 = w/n2 from ONE reciprocal R = 1/(n1 n2 n3):  S = sigma_1 + sigma_2, 1/S,
+    ds = sigma_2 - sigma_1, and E_i = b sigma_i (1 - sigma_i) / S = (b A w R) n_(3-i)^2 (no 1 - sigma cancellation):
+    nEd = -(E1 - E2), Es = E1 + E2."""
+    aw = A * w
+    n1 = aw + 1
     n2 = A + w
     n3 = n2 + w * n1
     p12 = n1 * n2
     R = 1 / (p12 * n3)
     t = n3 * R
-    s1 = n2 * t
-    s2 = w * n1 * t
-    d1 = s1 * (1 - s1)
-    d2 = s2 * (1 - s2)
-    S = n3 * t
-    iS = p12 * (p12 * R)
-    Su = b * (d1 - d2)                       # * sgn
-    Sa = -b * (d1 + d2)
-    Sb = (au - a) * d1 - (au + a) * d2
-    return S, iS, Su, Sa, Sb, s2 - s1, s1 * (au - a) + s2 * (au + a)
+    hb = (aw * b) * R
+    q1, q2 = n1 * n1, n2 * n2
+    return n3 * t, p12 * (p12 * R), (w * n1 - n2) * t, hb * (q1 - q2), hb * (q1 + q2)
 
 
 def cc_bwd(x, y, G, a, b, c):
-    """x: the op's input, y: its output (|y| replaces the recomputed forward value)."""
+    """x: the op's input, y: its output (|y| replaces the recomputed forward value).  The b integrand is
+    accumulated times b (cc_finish divides)."""
     a, b, c = a[:, None], b[:, None], c[:, None]
     A = np.exp(b * a)
     u = x - c
     au = np.abs(u)
-    sg = np.where(u < 0, -1.0, 1.0)
-    S, iS, Su, Sa, Sb, ds, ssum = _cc_parts(au, np.exp2(-b * LOG2E * au), A, a, b)
-    ya_b = (ssum - np.abs(y)) / b
-    Gx = G * S + LB * sg * Su * iS
-    ra = sg * G * ds + LB * Sa * iS
-    rb = sg * G * ya_b + LB * Sb * iS
+    sg = np.where(np.signbit(u), -1.0, 1.0).astype(u.dtype)
+    S, iS, ds, nEd, Es = _cc_parts(np.exp2(-b * LOG2E * au), A, b)
+    sgG = sg * G
+    Gx = G * S + sg * nEd                      # LB = -1
+    ya = au * S + a * ds - np.abs(y)
+    ra = sgG * ds + Es
+    rb = sgG * ya + (au * nEd + a * Es)
     return Gx, (Gx.sum(1), ra.sum(1), rb.sum(1))
 
 
 def cc_finish(raw, N, a, b, c):
     R1, R2, R3 = raw
-    return {"a": R2, "b": R3, "c": -R1}
+    return {"a": R2, "b": R3 / b, "c": -R1}
 
 
 def cs_bwd(x, y, G, a, b, c):
-    """Implicit differentiation of the inverse of CenterContract at u = y - c."""
+    """Implicit differentiation of the inverse of CenterContract at u = y - c.  Raw sums: dc, -da, -b db."""
     a, b, c = a[:, None], b[:, None], c[:, None]
     A = np.exp(b * a)
     au = np.abs(y - c)
-    sg = np.where(x < 0, -1.0, 1.0)
-    S, iS, Su, Sa, Sb, ds, ssum = _cc_parts(au, np.exp2(-b * LOG2E * au), A, a, b)
-    Cb = (ssum - np.abs(x)) / b
-    Gy = G - LB * sg * Su * iS               # total cotangent on y
+    sg = np.where(np.signbit(x), -1.0, 1.0).astype(x.dtype)
+    S, iS, ds, nEd, Es = _cc_parts(np.exp2(-b * LOG2E * au), A, b)
+    Gy = G - sg * nEd                          # total cotangent on y
     Gx = Gy * iS
-    ra = -Gx * sg * ds - LB * Sa * iS
-    rb = -Gx * sg * Cb - LB * Sb * iS
+    sgGx = sg * Gx
+    cb = au * S + a * ds - np.abs(x)
+    ra = sgGx * ds + Es
+    rb = sgGx * cb + (au * nEd + a * Es)
     return Gx, (G.sum(1), ra.sum(1), rb.sum(1))
 
 
 def cs_finish(raw, N, a, b, c):
     R1, R2, R3 = raw
-    return {"a": R2, "b": R3, "c": R1}
+    return {"a": -R2, "b": -R3 / b, "c": R1}
 
 
 def jo_bwd(x, y, G, gamma, delta, xi, lam):

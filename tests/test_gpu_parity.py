@@ -259,10 +259,13 @@ def test_against_committed_golden_fixtures(ctx, dtype, name):
         vz, g = E.mvnormal_negll_trafograd(fe, Xd)
         assert abs(vz - float(z["negll_zygote_primal"])) <= 1e-12 * (abs(vz) + 1)
         keys = sorted(k for k in z.files if k.startswith("grad_"))
+        g_rms = float(np.sqrt(np.mean(np.concatenate([z[k].ravel() for k in keys]) ** 2)))
         for k, (_, a) in zip(keys, flat_grads(g, fe)):
-            # floor: the gradient of an OUTERMOST Householder stack is mathematically zero (|Hy| = |y|), the fixture
-            # holds rounding noise there; everything else is measured at the stated tolerance
-            assert_close(a, z[k].reshape(a.shape), dtype, f"golden {k} {name}", floor=1e-3)
+            # the gradient of an OUTERMOST Householder stack is mathematically zero (|Hy| = |y|): the fixture holds
+            # rounding noise there, which is measured against the size of the whole gradient; every other leaf is
+            # measured against itself at the stated tolerance
+            leaf_rms = float(np.sqrt(np.mean(z[k] ** 2)))
+            assert_close(a, z[k].reshape(a.shape), dtype, f"golden {k} {name}", floor=g_rms if leaf_rms < 1e-10 * g_rms else 0.0)
         X2, L2 = E.with_logabsdet_jacobian(E.inverse(fe), Y)
         assert_close(X2.to_host(), z["X"], dtype, "golden roundtrip", factor=3000)
 
@@ -563,7 +566,7 @@ def test_fill_normal_matches_numpy_philox_twin(ctx, dtype):
     D, N, seed = 16, 40_000, 42
     ref = _fill_normal_twin(D, N, 0, seed)
     got = E.B200Matrix.randn(D, N, dtype, seed=seed, col0=0, ctx=ctx).to_host()
-    tol = 2e-6 if dtype == np.float32 else 1e-13      # float32: logf/cospif of the rounded uniforms
+    tol = 3e-5 if dtype == np.float32 else 1e-13      # float32: float32 logf / cospif of the uniforms rounded to float32 (u1 near 1: -2 log u1 is conditioned like 1/(1 - u1))
     assert np.max(np.abs(got - ref) / (np.abs(ref) + 1)) < tol
     # sharding: columns [col0, col0 + n) generated on their own are the same bits as inside the whole matrix
     for col0, n in ((1, 100), (12_345, 5000), (39_999, 1)):
