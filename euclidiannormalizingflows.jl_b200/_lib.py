@@ -57,6 +57,7 @@ SYMBOLS = [
     ("enf_group_init", _i, [_vp, _i, _i, _vp]),
     ("enf_group_destroy", _i, [_vp]),
     ("enf_negll_grad_group", _i, [_vp, _vp, _i64, _i, C.POINTER(C.c_double), _vp]),
+    ("enf_group_allreduce_sums", _i, [_vp, _i64]),
     ("enf_optimize_whitening", _i, [_vp, _vp, _i64, _i64, _i64, C.c_double, C.c_double, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_i64)]),
     ("enf_optimize_whitening_batches", _i, [_vp, _vp, _i64, C.POINTER(_i64), _i64, C.c_double, C.c_double, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_i64)]),
     ("enf_event_record", _i, [_vp, _i]),

@@ -1213,6 +1213,18 @@ extern "C" int enf_group_destroy(enf_ctx* ctx) {
     return ENF_OK;
 }
 
+// all-reduce (sum over the group) of the raw sums enf_negll_grad_partial left on the device, plus the local sample
+// count: the exchange step of a sharded gradient step on its own (asynchronous on the context stream)
+extern "C" int enf_group_allreduce_sums(enf_chain* ch, int64_t N_local) {
+    if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
+    enf_ctx* ctx = ch->ctx;
+    if (!ctx->comm) return fail(ctx, ENF_ERR_INVALID, "enf_group_init has not been called on this context");
+    CU(ctx, cudaSetDevice(ctx->device));
+    ch->h_sums[ch->n_raw] = double(N_local);
+    CU(ctx, cudaMemcpyAsync(ch->d_sums + ch->n_raw, ch->h_sums + ch->n_raw, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return group_allreduce(ctx, ch->d_sums, size_t(ch->n_raw + 1));
+}
+
 extern "C" int enf_negll_grad_group(enf_chain* ch, const void* x, int64_t N_local, int flags, double* negll,
                                     void* grads_host) {
     if (!ch) return fail(nullptr, ENF_ERR_INVALID, "chain is NULL");
@@ -1220,10 +1232,7 @@ extern "C" int enf_negll_grad_group(enf_chain* ch, const void* x, int64_t N_loca
     if (!ctx->comm) return fail(ctx, ENF_ERR_INVALID, "enf_group_init has not been called on this context");
     int rc = enf_negll_grad_partial(ch, x, N_local, nullptr, nullptr);
     if (rc != ENF_OK) return rc;
-    // append N_local so one all-reduce also yields the global batch size
-    ch->h_sums[ch->n_raw] = double(N_local);
-    CU(ctx, cudaMemcpyAsync(ch->d_sums + ch->n_raw, ch->h_sums + ch->n_raw, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    rc = group_allreduce(ctx, ch->d_sums, size_t(ch->n_raw + 1));
+    rc = enf_group_allreduce_sums(ch, N_local);      // N_local is appended so one all-reduce also yields the global batch size
     if (rc != ENF_OK) return rc;
     if (ch->moments && !host_chain_rule()) {                 // N_global = S^[D][D]
         rc = moments_finish_device(ch, flags, negll, grads_host);        // synchronises the stream

@@ -161,6 +161,9 @@ int enf_group_destroy(enf_ctx* ctx);
  * N_global = sum of N_local over ranks (all-reduced together with the sums). */
 int enf_negll_grad_group(enf_chain* chain, const void* x_dev, int64_t N_local, int flags,
                          double* negll_host, void* grads_host);
+/* The exchange step on its own: sums the raw sums that enf_negll_grad_partial left on the device (and N_local, appended
+ * as one more value) over the group, in place, asynchronously on the context stream. */
+int enf_group_allreduce_sums(enf_chain* chain, int64_t N_local);
 
 /* ---- optimize_whitening on the device -----------------------------
  * The whole loop of src/optimize_whitening.jl:36-43 -- for epoch, for batch: (negll, grad) ->

@@ -69,6 +69,27 @@ WORKER = textwrap.dedent("""
     hf, hf_ref = np.array(rf["negll_history"]), np.array(rf_ref["negll_history"])
     assert hf.shape == hf_ref.shape and np.max(np.abs(hf[:6] - hf_ref[:6]) / (np.abs(hf_ref[:6]) + 1)) < 1e-5, (hf, hf_ref)
     assert np.max(np.abs(hf - hf_ref) / (np.abs(hf_ref) + 1)) < 2e-3, (hf, hf_ref)
+    # ranks with DIFFERENT local sample counts: batches must come from the global partition (dist.local_batch_counts), a
+    # rank may hold no column of a batch; deriving the batches from the local count is refused on every rank
+    from enf_b200.dist import local_batch_counts
+    Ng = 1001
+    Xu = np.random.default_rng(11).standard_normal((D, Ng)) * 1.1
+    cnt = local_batch_counts(Ng, 4, rank, world)
+    assert len(cnt) == 5 and sum(local_batch_counts(Ng, 4, r, world)[4] for r in range(world)) == 1
+    mine = shard_batches(E.batch_ranges(Ng, 4), rank, world)
+    Xul = np.concatenate([Xu[:, a:b] for a, b in mine], axis=1)
+    Xud = E.B200Matrix.from_host(Xul, ctx)
+    ru_ref = O.optimize_whitening(Xu, fo, O.ADAGrad(), nbatches=4, nepochs=2)
+    for dev in (True, False):
+        ru = E.optimize_whitening(Xud, fe, E.ADAGrad(), nepochs=2, group=True, device_loop=dev, batch_counts=cnt)
+        hu, hu_ref = np.array(ru["negll_history"]), np.array(ru_ref["negll_history"])
+        assert hu.shape == hu_ref.shape == (10,) and np.max(np.abs(hu - hu_ref) / (np.abs(hu_ref) + 1)) < 1e-9, (dev, hu, hu_ref)
+    Xmis = E.B200Matrix.from_host(Xu[:, :502] if rank == 0 else Xu[:, :498], ctx)      # 4 local batches of 167/... vs 3 of 166
+    try:
+        E.optimize_whitening(Xmis, fe, E.ADAGrad(), nbatches=3, nepochs=1, group=True, device_loop=True)
+        raise SystemExit("mismatching batch counts were not detected")
+    except E.EnfError as exc:
+        assert "disagree" in str(exc), exc
     dist.barrier(); dist.destroy_process_group()
     print("rank", rank, "ok")
 """) % (ROOT, ROOT)

@@ -581,3 +581,59 @@ def test_fill_normal_matches_numpy_philox_twin(ctx, dtype):
     assert np.abs(other - got).mean() > 0.5
     big = E.B200Matrix.randn(4, 1_000_000, dtype, seed=7, ctx=ctx).to_host().astype(np.float64)
     assert abs(big.mean()) < 4e-3 and abs(big.std() - 1) < 4e-3 and abs((big ** 3).mean()) < 2e-2 and abs((big ** 4).mean() - 3) < 5e-2
+
+
+# ---- round 2: parameter domain, explicit batches, shared scalar fields
+def test_parameter_domain_is_validated(ctx):
+    """b <= 0 (CenterStretch/CenterContract are the b > 0 branch, src/center_stretch.jl:6-7), delta = 0, lambda = 0,
+    a = 0, a zero Householder vector and non-finite values are rejected with an error code at chain creation and at
+    set_params (the chain keeps its previous parameters), never evaluated."""
+    import enf_b200 as E
+    one = np.ones(4)
+    X = E.B200Matrix.from_host(np.ones((4, 8)), ctx)
+    bad = [E.CenterStretch(one, -one, 0 * one), E.CenterContract(one, 0 * one, 0 * one), E.JohnsonTrafo(one, 0 * one, one, one),
+           E.JohnsonTrafoInv(one, one, one, 0 * one), E.ScaleShiftTrafo(np.array([1.0, 0.0, 1.0, 1.0]), one),
+           E.HouseholderTrafo(np.zeros((4, 2))), E.ScaleShiftTrafo(np.array([1.0, np.nan, 1.0, 1.0]), one)]
+    for f in bad:
+        with pytest.raises(E.EnfError):
+            E.with_logabsdet_jacobian(f, X)
+    good = E.CenterContract(one, 2 * one, 0 * one)
+    y0 = E.with_logabsdet_jacobian(good, X)[0].to_host()
+    with pytest.raises(E.EnfError):
+        E.with_logabsdet_jacobian(E.CenterContract(one, -2 * one, 0 * one), X)     # same chain structure: set_params path
+    np.testing.assert_array_equal(E.with_logabsdet_jacobian(good, X)[0].to_host(), y0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_device_loop_with_explicit_batches_and_scalar_fields(ctx, dtype):
+    """enf_optimize_whitening_batches: an arbitrary contiguous partition gives the same history as the host loop over the
+    same partition; scalar-valued fields (one shared parameter in the reference) are accepted at D = 1 and rejected at
+    D > 1 instead of being trained as D independent parameters."""
+    import enf_b200 as E
+    rng = np.random.default_rng(5)
+    D, N = 3, 2000
+    X = (rng.standard_normal((D, N)) * 1.3 + 0.2).astype(dtype)
+    one = np.ones(D, dtype=dtype)
+    f0 = E.compose(E.ScaleShiftTrafo(one.copy(), 0 * one), E.JohnsonTrafo(0 * one, 5 * one, 0 * one, 5 * one))
+    counts = [700, 1, 299, 1000]
+    Xd = E.B200Matrix.from_host(X, ctx)
+    r_dev = E.optimize_whitening(Xd, f0, E.ADAGrad(), nepochs=2, device_loop=True, batch_counts=counts)
+    r_host = E.optimize_whitening(Xd, f0, E.ADAGrad(), nepochs=2, batch_counts=counts)
+    hd, hh = np.array(r_dev["negll_history"]), np.array(r_host["negll_history"])
+    assert hd.shape == hh.shape == (8,)
+    assert np.max(np.abs(hd - hh) / (np.abs(hh) + 1)) < (2e-4 if dtype == np.float32 else 1e-9)
+    with pytest.raises(ValueError):
+        E.optimize_whitening(Xd, f0, E.ADAGrad(), nepochs=1, device_loop=True, batch_counts=[5, 5])
+    # shared scalar fields
+    fs = E.compose(E.ScaleShiftTrafo(one.copy(), 0 * one), E.JohnsonTrafo(dtype(0), dtype(5), dtype(0), dtype(5)))
+    with pytest.raises(TypeError):
+        E.optimize_whitening(Xd, fs, E.ADAGrad(), nbatches=4, nepochs=1, device_loop=True)
+    r_s = E.optimize_whitening(Xd, fs, E.ADAGrad(), nbatches=4, nepochs=1)          # host loop: gradient summed over rows
+    assert np.ndim(E.flatten(r_s["result"])[0].gamma) == 0
+    X1 = E.B200Matrix.from_host(X[:1], ctx)
+    f1 = E.compose(E.ScaleShiftTrafo(one[:1].copy(), 0 * one[:1]), E.JohnsonTrafo(dtype(0), dtype(5), dtype(0), dtype(5)))
+    r1d = E.optimize_whitening(X1, f1, E.ADAGrad(), nbatches=4, nepochs=2, device_loop=True)
+    r1h = E.optimize_whitening(X1, f1, E.ADAGrad(), nbatches=4, nepochs=2)
+    h1d, h1h = np.array(r1d["negll_history"]), np.array(r1h["negll_history"])
+    assert np.max(np.abs(h1d - h1h) / (np.abs(h1h) + 1)) < (2e-4 if dtype == np.float32 else 1e-9)
+    assert np.ndim(E.flatten(r1d["result"])[0].gamma) == 0
