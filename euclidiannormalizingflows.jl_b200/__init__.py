@@ -10,10 +10,12 @@ from .trafos import (CenterContract, CenterStretch, ComposedFunction, Householde
                      mvnormal_negll_trafo, mvnormal_negll_trafograd, pack_params, result_dtype, unpack_grads,
                      with_logabsdet_jacobian)
 from .whitening import ADAGrad, batch_ranges, optimize_whitening, setup, update
+from .johnsonsu import JohnsonSU
+from .variational import GaussMixture, nELBO, nELBO_trafograd, optimise_ELBO
 from . import dist
 
 __all__ = [
-    "ADAGrad", "B200Matrix", "CenterContract", "CenterStretch", "ComposedFunction", "Context", "EnfError",
+    "ADAGrad", "B200Matrix", "GaussMixture", "JohnsonSU", "nELBO", "nELBO_trafograd", "optimise_ELBO", "CenterContract", "CenterStretch", "ComposedFunction", "Context", "EnfError",
     "HouseholderTrafo", "JohnsonTrafo", "JohnsonTrafoInv", "LIB_PATH", "ScaleShiftTrafo", "Trafo",
     "batch_ranges", "compose", "default_context", "dist", "flatten", "get_chain", "inverse", "lib",
     "mvnormal_negll_trafo", "mvnormal_negll_trafograd", "optimize_whitening", "pack_params", "result_dtype",

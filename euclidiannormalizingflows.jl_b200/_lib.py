@@ -28,6 +28,14 @@ class enf_op(C.Structure):
     _fields_ = [("kind", C.c_int32), ("K", C.c_int32), ("params", C.c_void_p)]
 
 
+class enf_target(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("K", C.c_int32), ("weights", C.POINTER(C.c_double)), ("means", C.POINTER(C.c_double)),
+                ("sigmas", C.POINTER(C.c_double))]
+
+
+ENF_TARGET_GAUSS_MIXTURE = 1
+(ENF_JSU_PDF, ENF_JSU_LOGPDF, ENF_JSU_CDF, ENF_JSU_LOGCDF, ENF_JSU_CCDF, ENF_JSU_LOGCCDF, ENF_JSU_QUANTILE) = range(7)
+
 SYMBOLS = [
     ("enf_init", _i, [_i, _pvp]),
     ("enf_destroy", _i, [_vp]),
@@ -53,6 +61,8 @@ SYMBOLS = [
     ("enf_negll_grad", _i, [_vp, _vp, _i64, _i, C.POINTER(C.c_double), _vp]),
     ("enf_negll_grad_partial", _i, [_vp, _vp, _i64, _pvp, C.POINTER(_i64)]),
     ("enf_negll_grad_finish", _i, [_vp, _vp, _i64, _i, C.POINTER(C.c_double), _vp]),
+    ("enf_elbo_grad", _i, [_vp, C.POINTER(enf_target), _vp, _i64, _i, C.POINTER(C.c_double), _vp]),
+    ("enf_johnsonsu", _i, [_vp, _i, _i, C.POINTER(C.c_double), _vp, _i64, _vp]),
     ("enf_group_unique_id", _i, [_vp]),
     ("enf_group_init", _i, [_vp, _i, _i, _vp]),
     ("enf_group_destroy", _i, [_vp]),

@@ -439,7 +439,9 @@ void finish_moments(const enf_chain* ch, const double* sums, int64_t N, int flag
 }
 
 // raw device sums -> (negll, grads).  Transcribes tests/device_model.py *_finish.
-void finish(const enf_chain* ch, const double* sums, int64_t N, int flags, double* negll, std::vector<double>* grads) {
+// elbo: the objective is the negative ELBO of examples/nf_variational_1d.jl:29-41 (sum_y then holds sum -log p(z)):
+// nELBO = -[(sum log p(z) + sum ladj) / N - (log 2 pi + 1)/2 * D]
+void finish(const enf_chain* ch, const double* sums, int64_t N, int flags, double* negll, std::vector<double>* grads, bool elbo = false) {
     if (ch->moments) return finish_moments(ch, sums, N, flags, negll, grads);
     const int D = ch->D, Dp = ch->desc.Dp;
     const bool packed = ch->plan.packed;
@@ -448,7 +450,7 @@ void finish(const enf_chain* ch, const double* sums, int64_t N, int flags, doubl
     const int n_raw = ch->n_raw;
     const double sum_y = sums[n_raw - 2], sum_l = sums[n_raw - 1];
     const double lconst = ch->ladj_const_other + ((flags & ENF_NEGLL_ZYGOTE_PRIMAL) ? 0.0 : ch->ladj_const_ss);
-    if (negll) *negll = (sum_y + 0.5 * LOG2PI * Nd * D - (sum_l + Nd * lconst)) / Nd;
+    if (negll) *negll = (sum_y + 0.5 * (LOG2PI + (elbo ? 1.0 : 0.0)) * Nd * D - (sum_l + Nd * lconst)) / Nd;
     if (!grads) return;
     grads->assign(ch->n_params, 0.0);
     std::vector<double> R(size_t(4) * D);
@@ -526,7 +528,7 @@ void export_grads(const enf_chain* ch, const std::vector<double>& g, void* out) 
     }
 }
 
-int run_partial(enf_chain* ch, const void* x, int64_t N, bool grad) {
+int run_partial(enf_chain* ch, const void* x, int64_t N, bool grad, const ChainDesc* desc_override = nullptr) {
     enf_ctx* ctx = ch->ctx;
     if (N < 0) return fail(ctx, ENF_ERR_INVALID, "N must be >= 0");
     if (ch->moments) {
@@ -537,7 +539,8 @@ int run_partial(enf_chain* ch, const void* x, int64_t N, bool grad) {
         return ENF_OK;
     }
     KernelSet ks;
-    const int mode = pick_mode(ch, x, nullptr);
+    // a target density (ELBO objective) is compiled into the scalar-access layouts only
+    const int mode = desc_override ? (ch->plan.packed ? MODE_PACKU : MODE_SCALAR) : pick_mode(ch, x, nullptr);
     if (!select_kernels(ch->dtype, ch->plan, mode, ks))
         return fail(ctx, ENF_ERR_INVALID, "no kernel variant for dtype=%d D=%d", ch->dtype, ch->D);
     const size_t smem = grad_smem_bytes(ch->dtype, ch->desc, ks, grad);
@@ -546,8 +549,8 @@ int run_partial(enf_chain* ch, const void* x, int64_t N, bool grad) {
                     "chain needs %zu bytes of shared memory per CTA for the fused %s kernel (limit 232448)", smem,
                     grad ? "gradient" : "loss");
     int blocks = 0;
-    CU(ctx, launch_grad(ch->dtype, ks, ch->desc, ch->d_consts, x, N, grad, ch->d_partials, ch->max_blocks, &blocks,
-                        ctx->sm_count, ctx->stream));
+    CU(ctx, launch_grad(ch->dtype, ks, desc_override ? *desc_override : ch->desc, ch->d_consts, x, N, grad, ch->d_partials,
+                        ch->max_blocks, &blocks, ctx->sm_count, ctx->stream));
     CU(ctx, launch_reduce(ch->d_partials, blocks, ch->n_raw, ch->d_sums, false, ctx->stream));
     ctx->launches += 2;
     return ENF_OK;
@@ -1077,6 +1080,55 @@ extern "C" int enf_negll_grad(enf_chain* ch, const void* x, int64_t N, int flags
     CU(ctx, cudaMemcpyAsync(ch->h_sums, ch->d_sums, size_t(ch->n_raw) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return enf_negll_grad_finish(ch, ch->h_sums, N, flags, negll, grads_host);
+}
+
+// ------------------------------------------------------------------ ELBO objective, JohnsonSU operations
+// nELBO(trafo, xi) and its parameter gradient (examples/nf_variational_1d.jl:29-47) for xi of shape D x N (samples are
+// columns, as everywhere in this library; the example passes a (2 batchsize) x 1 matrix and swaps the roles of rows and
+// columns, :32-34 -- the shim transposes).  The target log-density is applied element-wise like the example's my_ll.(z).
+extern "C" int enf_elbo_grad(enf_chain* ch, const enf_target* target, const void* xi_dev, int64_t N, int flags, double* nelbo,
+                             void* grads_host) {
+    if (!ch || !target || !nelbo) return fail(ch ? ch->ctx : nullptr, ENF_ERR_INVALID, "NULL argument");
+    enf_ctx* ctx = ch->ctx;
+    if (N < 1 || !xi_dev) return fail(ctx, ENF_ERR_INVALID, "N must be >= 1 and xi_dev non-NULL");
+    if (target->kind != ENF_TARGET_GAUSS_MIXTURE) return fail(ctx, ENF_ERR_INVALID, "unknown target kind %d", target->kind);
+    if (target->K < 1 || target->K > MAX_TARGET_K || !target->weights || !target->means || !target->sigmas)
+        return fail(ctx, ENF_ERR_INVALID, "Gaussian-mixture target needs 1..%d components", MAX_TARGET_K);
+    if (ch->moments) return fail(ctx, ENF_ERR_INVALID, "the ELBO objective is not available for second-moment (Householder/ScaleShift-only, D=%d) chains", ch->D);
+    CU(ctx, cudaSetDevice(ctx->device));
+    ChainDesc d = ch->desc;
+    d.target_kind = 1;
+    d.target_K = target->K;
+    for (int k = 0; k < target->K; ++k) {
+        const double w = target->weights[k], sg = target->sigmas[k];
+        if (!(w > 0.0) || !(sg > 0.0) || !std::isfinite(target->means[k]))
+            return fail(ctx, ENF_ERR_INVALID, "mixture component %d: weight and sigma must be positive, the mean finite", k);
+        d.tlw[k] = std::log(w / sg) - 0.5 * LOG2PI;
+        d.tmu[k] = target->means[k];
+        d.tis[k] = 1.0 / sg;
+    }
+    int rc = run_partial(ch, xi_dev, N, grads_host != nullptr, &d);
+    if (rc != ENF_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(ch->h_sums, ch->d_sums, size_t(ch->n_raw) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<double> g;
+    finish(ch, ch->h_sums, N, flags, nelbo, grads_host ? &g : nullptr, true);
+    if (grads_host) export_grads(ch, g, grads_host);
+    return ENF_OK;
+}
+
+// Element-wise JohnsonSU operations (src/johnson_trafo.jl:109-129): out[i] = op(JohnsonSU(gamma, delta, xi, lambda), x[i]).
+extern "C" int enf_johnsonsu(enf_ctx* ctx, int dtype, int op, const double* params4, const void* x_dev, int64_t N, void* out_dev) {
+    if (!ctx || !params4) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    if (dtype != ENF_F32 && dtype != ENF_F64) return fail(ctx, ENF_ERR_INVALID, "bad dtype %d", dtype);
+    if (op < ENF_JSU_PDF || op > ENF_JSU_QUANTILE) return fail(ctx, ENF_ERR_INVALID, "bad JohnsonSU operation %d", op);
+    if (N < 0 || (N > 0 && (!x_dev || !out_dev))) return fail(ctx, ENF_ERR_INVALID, "bad N / NULL device pointer");
+    if (params4[1] == 0.0 || params4[3] == 0.0 || !std::isfinite(params4[0] + params4[1] + params4[2] + params4[3]))
+        return fail(ctx, ENF_ERR_INVALID, "JohnsonSU needs finite parameters with delta != 0 and lambda != 0");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, launch_johnsonsu(dtype, op, x_dev, out_dev, N, params4, ctx->sm_count, ctx->stream));
+    if (N > 0) ctx->launches += 1;
+    return ENF_OK;
 }
 
 // ------------------------------------------------------------------ NCCL group

@@ -24,6 +24,7 @@
 namespace enf {
 
 constexpr int MAX_OPS = 24;
+constexpr int MAX_TARGET_K = 8;
 #ifndef ENF_NT
 #define ENF_NT 256
 #endif
@@ -49,6 +50,13 @@ struct ChainDesc {
     int n_save;      // saved-input tiles the gradient kernel needs
     int n_rowslots;  // raw-sum slots holding one value per row
     int n_scalars;   // raw-sum slots holding one value per chain
+    // Objective of the loss / gradient kernels.  0: the whitening loss of src/optimize_whitening.jl:7-15 (target =
+    // standard normal).  1: the negative ELBO of examples/nf_variational_1d.jl:29-41 with an element-wise Gaussian-mixture
+    // target log-density (the example's my_ll, :25-27): component k has log weight tlw[k] = log(w_k / (sigma_k sqrt(2 pi))),
+    // mean tmu[k], inverse width tis[k].
+    int target_kind;
+    int target_K;
+    double tlw[MAX_TARGET_K], tmu[MAX_TARGET_K], tis[MAX_TARGET_K];
     DevOp ops[MAX_OPS];
 };
 
@@ -835,6 +843,30 @@ __device__ __forceinline__ void bwd_elem(const Tile<C>& xt, const Tile<C>& yt, T
         }
 }
 
+// -log p(z) and its derivative for the Gaussian-mixture target of the ELBO objective (log-sum-exp over the components).
+// Deliberately out of line: the whitening loss never calls it, and it must not cost the hot path any registers.
+template <typename T> struct ValGrad { T val, grad; };
+template <typename T>
+__device__ __noinline__ ValGrad<T> target_eval(const ChainDesc& d, T z) {
+    T e[MAX_TARGET_K];
+    T mx = T(-1e30);
+    for (int k = 0; k < d.target_K; ++k) {
+        const T t = (z - T(d.tmu[k])) * T(d.tis[k]);
+        e[k] = T(d.tlw[k]) - T(0.5) * t * t;
+        mx = e[k] > mx ? e[k] : mx;
+    }
+    T s = T(0), gsum = T(0);
+    for (int k = 0; k < d.target_K; ++k) {
+        const T p = sizeof(T) == 4 ? T(expf(float(e[k] - mx))) : T(exp(double(e[k] - mx)));
+        s += p;
+        gsum += p * (z - T(d.tmu[k])) * T(d.tis[k]) * T(d.tis[k]);
+    }
+    ValGrad<T> r;
+    r.val = -(mx + (sizeof(T) == 4 ? T(logf(float(s))) : T(log(double(s)))));
+    r.grad = gsum / s;
+    return r;
+}
+
 // ------------------------------------------------------------------ loss / gradient kernel
 // F3 of SURVEY §2.3: mvnormal_negll_trafo and the reverse pass of
 // mvnormal_negll_trafograd (src/optimize_whitening.jl:7-22) in one pass over x.
@@ -909,10 +941,11 @@ __device__ __forceinline__ bool grad_fwd_tile(const ChainDesc& desc, const GradS
     return bad;
 }
 
-// Reverse pass of one tile: gt = N dL/d(activation), seeded with y (src/optimize_whitening.jl:12); zt holds the
-// chain's output on entry and is walked back to the input.
+// Reverse pass of one tile: gt = N dL/d(activation), seeded by the caller (y for the whitening loss,
+// src/optimize_whitening.jl:12; -dlog p/dz for the ELBO objective); zt holds the chain's output on entry and is walked
+// back to the input.
 template <class C, bool FULL>
-__device__ __forceinline__ void grad_bwd_tile(const ChainDesc& desc, const GradSmem<typename C::T>& sm, Tile<C>& zt,
+__device__ __forceinline__ void grad_bwd_tile(const ChainDesc& desc, const GradSmem<typename C::T>& sm, Tile<C>& zt, Tile<C>& gt,
                                               const typename C::T (&m)[C::SPT][C::LN]) {
     using T = typename C::T;
     using P = Prim<T>;
@@ -921,13 +954,6 @@ __device__ __forceinline__ void grad_bwd_tile(const ChainDesc& desc, const GradS
     constexpr int Dp = C::DP;
     const int tid = threadIdx.x;
     const int g = tid & (C::G - 1);
-    Tile<C> gt;
-#pragma unroll
-    for (int u = 0; u < C::SPT; ++u)
-#pragma unroll
-        for (int q = 0; q < C::CH; ++q)
-#pragma unroll
-            for (int e = 0; e < VE; ++e) gt.v[u][q][e] = zt.v[u][q][e];
     for (int o = desc.n_ops - 1; o >= 0; --o) {
         const DevOp op = desc.ops[o];
         const uint32_t cb = sm.c32 + uint32_t(op.coff) * uint32_t(sizeof(T));   // this op's constants
@@ -1191,14 +1217,39 @@ __global__ void __launch_bounds__(NT, ENF_GRAD_MIN_CTAS) chain_grad_kernel(const
                 grad_fwd_tile<C, GRAD, false, true>(desc, sm, x, N, tile, zt, l, m);
             use_mask = true;
         }
-        if (!use_mask) {
+        Tile<C> gt;
+        // The ELBO objective is compiled into the scalar-access layouts only (enf_elbo_grad always dispatches to them): its
+        // batches are a few hundred draws, and the hot vectorised instantiations must not pay registers for it.
+        constexpr bool HAS_TARGET = (C::MODE == MODE_SCALAR || C::MODE == MODE_PACKU);
+        if (HAS_TARGET && desc.target_kind != 0) {
+            // loss term -log p(z) per element, cotangent seed -dlog p/dz (cold path, out of line)
+            const int g_ = tid & (C::G - 1);
+#pragma unroll
+            for (int u = 0; u < C::SPT; ++u) {
+#pragma unroll
+                for (int q = 0; q < C::CH; ++q)
+#pragma unroll
+                    for (int e = 0; e < VE; ++e) {
+                        const bool row_ok = C::PACKED ? true : ((q * C::G + g_) * VE + e < desc.D);
+                        const T w = use_mask ? m[u][C::slot(e)] : T(1);
+                        const ValGrad<T> r = target_eval<T>(desc, zt.v[u][q][e]);
+                        loss_y = P::fma_(row_ok ? w : T(0), r.val, loss_y);
+                        gt.v[u][q][e] = row_ok ? r.grad : T(0);
+                    }
+#pragma unroll
+                for (int p = 0; p < C::LN; ++p) loss_l = use_mask ? P::fma_(m[u][p], l[u][p], loss_l) : loss_l + l[u][p];
+            }
+        } else if (!use_mask) {
 #pragma unroll
             for (int u = 0; u < C::SPT; ++u) {
                 T sy = T(0);
 #pragma unroll
                 for (int q = 0; q < C::CH; ++q)
 #pragma unroll
-                    for (int e = 0; e < VE; ++e) sy = P::fma_(zt.v[u][q][e], zt.v[u][q][e], sy);
+                    for (int e = 0; e < VE; ++e) {
+                        sy = P::fma_(zt.v[u][q][e], zt.v[u][q][e], sy);
+                        gt.v[u][q][e] = zt.v[u][q][e];
+                    }
                 loss_y = P::fma_(T(0.5), sy, loss_y);
 #pragma unroll
                 for (int p = 0; p < C::LN; ++p) loss_l += l[u][p];
@@ -1210,15 +1261,18 @@ __global__ void __launch_bounds__(NT, ENF_GRAD_MIN_CTAS) chain_grad_kernel(const
 #pragma unroll
                 for (int q = 0; q < C::CH; ++q)
 #pragma unroll
-                    for (int e = 0; e < VE; ++e) sy = P::fma_(m[u][C::slot(e)] * zt.v[u][q][e], zt.v[u][q][e], sy);
+                    for (int e = 0; e < VE; ++e) {
+                        sy = P::fma_(m[u][C::slot(e)] * zt.v[u][q][e], zt.v[u][q][e], sy);
+                        gt.v[u][q][e] = zt.v[u][q][e];
+                    }
                 loss_y = P::fma_(T(0.5), sy, loss_y);
 #pragma unroll
                 for (int p = 0; p < C::LN; ++p) loss_l = P::fma_(m[u][p], l[u][p], loss_l);
             }
         }
         if constexpr (!GRAD) continue;
-        if (!use_mask) grad_bwd_tile<C, HOTFULL>(desc, sm, zt, m);
-        else grad_bwd_tile<C, false>(desc, sm, zt, m);
+        if (!use_mask) grad_bwd_tile<C, HOTFULL>(desc, sm, zt, gt, m);
+        else grad_bwd_tile<C, false>(desc, sm, zt, gt, m);
     }
     flush(first_flush);
     // loss partials: warp shuffle, then one double per warp through shared memory

@@ -93,6 +93,11 @@ cudaError_t launch_fit_update(int dtype, const FitDesc& fd, double* sums, const 
                               double* lconst, double* params, double* state, double eta, double eps, int flags,
                               double* history, long long* step_ctr, void* consts, cudaStream_t st, const P2PDesc* p2p = nullptr);
 
+// JohnsonSU distribution operations (enf_johnsonsu.cu); `op` values are the ABI's enf_johnsonsu_op
+enum : int { JSU_PDF = 0, JSU_LOGPDF = 1, JSU_CDF = 2, JSU_LOGCDF = 3, JSU_CCDF = 4, JSU_LOGCCDF = 5, JSU_QUANTILE = 6 };
+cudaError_t launch_johnsonsu(int dtype, int op, const void* x, void* out, int64_t N, const double* params4, int sm_count,
+                             cudaStream_t st);
+
 // synthetic data (enf_fill.cu)
 cudaError_t launch_fill_normal(int dtype, void* x, int D, int64_t N, int64_t col0, uint64_t seed, cudaStream_t st);
 

@@ -115,6 +115,35 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 ld2(const float* p) { return make_float2(p[0], p[1]); }
 
+// 2^t for t <= 0 on the FMA pipe (packed pairs), for the kernels whose special-function (XU) pipe is the limiter:
+// Cody-Waite split t = n + f with the round-to-nearest "magic number" trick (n lands in the low mantissa bits of
+// r = t + 1.5 * 2^23), a degree-6 minimax polynomial for 2^f on [-1/2, 1/2] (relative error 1e-7 in Float32 Horner form,
+// as good as ex2.approx) and the exponent added with integer arithmetic.  t is clamped at -126 (the result then is 2^-126,
+// the flush-to-zero boundary of the MUFU version).  MEASURED (profiles/README.md, round 2): CenterStretch alone 0.88 ->
+// 0.93 of the HBM peak, but the C3 chain 0.70 -> 0.64: the extra 6.5 issue slots per element cost more than the freed XU
+// cycles give back (the chain kernel is issue-limited as much as XU-limited).  Off by default.
+#ifndef ENF_EX2_POLY
+#define ENF_EX2_POLY 0
+#endif
+__device__ __forceinline__ float2 ex2_neg_poly2(float2 t) {
+    const float2 magic = make_float2(12582912.f, 12582912.f);
+    t.x = fmaxf(t.x, -126.f);
+    t.y = fmaxf(t.y, -126.f);
+    const float2 r = add2(t, magic);
+    const float2 nf = add2(r, make_float2(-12582912.f, -12582912.f));
+    const float2 f = fma2(nf, make_float2(-1.f, -1.f), t);
+    float2 p = make_float2(0.00015345810970757157f, 0.00015345810970757157f);
+    p = fma2(p, f, make_float2(0.0013399930903688073f, 0.0013399930903688073f));
+    p = fma2(p, f, make_float2(0.009618489071726799f, 0.009618489071726799f));
+    p = fma2(p, f, make_float2(0.05550328642129898f, 0.05550328642129898f));
+    p = fma2(p, f, make_float2(0.24022646248340607f, 0.24022646248340607f));
+    p = fma2(p, f, make_float2(0.6931471824645996f, 0.6931471824645996f));
+    p = fma2(p, f, make_float2(1.f, 1.f));
+    p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
+    p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
+    return p;
+}
+
 // lg(prod_i p[i]).  Fast form (SAFE = false): ONE log of the product; if the product
 // left the safe range (over/underflow), `bad` is raised and the caller recomputes the
 // whole tile with SAFE = true (sum of per-element logs).  No branch on the fast path:
@@ -193,7 +222,11 @@ __device__ __forceinline__ void cs_fwd_v(T* v, const T* nb2, const T* Ah, const 
             const float2 x = make_float2(v[e], v[e + 1]);
             const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
             const float2 t = mul2(ld2(nb2 + e), ax);
+#if ENF_EX2_POLY
+            const float2 w = ex2_neg_poly2(t);
+#else
             const float2 w = make_float2(P::ex2(t.x), P::ex2(t.y));
+#endif
             const float2 ah = ld2(Ah + e);
             const float2 m = fma2(make_float2(-ah.x, -ah.y), w, ah);
             const float2 q = fma2(m, m, w);

@@ -145,6 +145,41 @@ int enf_negll_grad_partial(enf_chain* chain, const void* x_dev, int64_t N_local,
 int enf_negll_grad_finish(enf_chain* chain, const double* sums_host, int64_t N_global, int flags,
                           double* negll_host, void* grads_host);
 
+/* ---- the callers next to the path ---------------------------------------------
+ * Target log-density of the variational objective, applied element-wise like `my_ll.(z)` of
+ * examples/nf_variational_1d.jl:25-27 (no callbacks cross the ABI: a fixed set of densities).
+ * ENF_TARGET_GAUSS_MIXTURE: p(z) = sum_k weights[k] N(z | means[k], sigmas[k]), 1 <= K <= 8. */
+typedef enum { ENF_TARGET_GAUSS_MIXTURE = 1 } enf_target_kind;
+typedef struct {
+    int32_t kind;            /* enf_target_kind */
+    int32_t K;               /* number of mixture components */
+    const double* weights;   /* host pointers, K values each */
+    const double* means;
+    const double* sigmas;
+} enf_target;
+
+/* nELBO(trafo, xi) and nELBO_trafograd(trafo, xi): examples/nf_variational_1d.jl:29-47,
+ *   nELBO = -[(sum_ij log p(z_ij) + sum_j ladj_j) / N - (log 2 pi + 1)/2 * D],  (z, ladj) = with_logabsdet_jacobian(trafo, xi)
+ * for a D x N matrix xi of standard-normal draws (samples are columns; the example builds a (2 batchsize) x 1 matrix
+ * with the roles of rows and columns swapped, :32-34).  One fused kernel: forward + ladj + target log-density + reverse
+ * pass.  grads_host: packed like the params, chain dtype; NULL: value only.  flags as for enf_negll_grad.  Blocking. */
+int enf_elbo_grad(enf_chain* chain, const enf_target* target, const void* xi_dev, int64_t N, int flags,
+                  double* nelbo_host, void* grads_host);
+
+/* Batched operations of the JohnsonSU distribution object (src/johnson_trafo.jl:1-26,109-129), element-wise over N
+ * values: out[i] = op(JohnsonSU(gamma, delta, xi, lambda), x[i]); params4 = {gamma, delta, xi, lambda}.  For
+ * ENF_JSU_QUANTILE x holds probabilities.  Asynchronous on the context stream; out may alias x. */
+typedef enum {
+    ENF_JSU_PDF = 0,      /* Distributions.pdf      src/johnson_trafo.jl:120 */
+    ENF_JSU_LOGPDF = 1,   /* Distributions.logpdf   :123 */
+    ENF_JSU_CDF = 2,      /* Distributions.cdf      :121 */
+    ENF_JSU_LOGCDF = 3,   /* Distributions.logcdf   :124 */
+    ENF_JSU_CCDF = 4,     /* Distributions.ccdf     :125 */
+    ENF_JSU_LOGCCDF = 5,  /* Distributions.logccdf  :126 */
+    ENF_JSU_QUANTILE = 6  /* Statistics.quantile    :129 */
+} enf_johnsonsu_op;
+int enf_johnsonsu(enf_ctx* ctx, int dtype, int op, const double* params4, const void* x_dev, int64_t N, void* out_dev);
+
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink ------------------------
  * The only collective on the path is the all-reduce of the loss and the
  * parameter-gradient sums.  libnccl.so.2 is dlopen'ed on first use.

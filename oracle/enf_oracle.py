@@ -540,3 +540,118 @@ def optimize_whitening(X, initial_trafo, optimizer: ADAGrad, *, nbatches=100, ne
             hist.append(float(negll))
     return {"result": trafo, "optimizer_state": state,
             "negll_history": list(negll_history or []) + hist}
+
+
+# --------------------------------------------------------------------------
+# JohnsonSU distribution object and the variational (ELBO) objective
+# --------------------------------------------------------------------------
+@dataclass
+class JohnsonSU:
+    """src/johnson_trafo.jl:1-26,109-129 (`JohnsonSU <: Distribution{Univariate,Continuous}`), scalar parameters.
+    Distributions.jl / StatsFuns.jl (un-vendored; PARITY UNPINNED) supply the standard-normal pdf / cdf / logcdf /
+    quantile: restated with scipy.special.ndtr / log_ndtr / ndtri."""
+    gamma: float = 10.0
+    delta: float = 3.5
+    xi: float = 10.0
+    lam: float = 1.0           # Julia field name: lambda
+
+    def params(self):          # StatsBase.params, :18
+        return (self.gamma, self.delta, self.xi, self.lam)
+
+    def mean(self):            # :24
+        return self.xi - self.lam * math.exp(self.delta ** -2 / 2) * math.sinh(self.gamma / self.delta)
+
+    def median(self):          # :25
+        return self.xi + self.lam * math.sinh(-self.gamma / self.delta)
+
+    def var(self):             # :26
+        return (self.lam ** 2) / 2 * (math.exp(self.delta ** -2) - 1) * (math.exp(self.delta ** -2) * math.cosh(2 * self.gamma / self.delta) + 1)
+
+    def _z(self, x):
+        return johnsontrafo(x, self.gamma, self.delta, self.xi, self.lam)
+
+    def pdf(self, x):          # :120
+        z = self._z(x)
+        return deriv_johnsontrafo(x, self.gamma, self.delta, self.xi, self.lam) * np.exp(-0.5 * z * z) / math.sqrt(2 * math.pi)
+
+    def logpdf(self, x):       # :123 (log of the product; evaluated as the sum of logs where the product underflows)
+        z = self._z(x)
+        return np.log(np.abs(deriv_johnsontrafo(x, self.gamma, self.delta, self.xi, self.lam))) - 0.5 * z * z - 0.5 * LOG2PI
+
+    def cdf(self, x):          # :121
+        from scipy.special import ndtr
+        return ndtr(self._z(x))
+
+    def logcdf(self, x):       # :124
+        from scipy.special import log_ndtr
+        return log_ndtr(self._z(x))
+
+    def ccdf(self, x):         # :125
+        return 1 - self.cdf(x)
+
+    def logccdf(self, x):      # :126
+        return np.log(1 - self.cdf(x))
+
+    def quantile(self, p):     # :129
+        from scipy.special import ndtri
+        return johnsontrafo_inv(ndtri(np.asarray(p, dtype=np.float64)), self.gamma, self.delta, self.xi, self.lam)
+
+    def rand(self, rng, n):
+        """Distributions' default sampler for a continuous univariate distribution without its own `rand`:
+        quantile(d, rand()) (inverse-cdf sampling)."""
+        return self.quantile(rng.uniform(size=n))
+
+
+@dataclass
+class GaussMixture:
+    """Element-wise target log-density of examples/nf_variational_1d.jl:25-27:
+    my_ll(x) = log(0.3 N(x-2) + 0.5 N(x-5) + 0.2 N(x+1)), generalised to K components with widths."""
+    weights: Any = (0.3, 0.5, 0.2)
+    means: Any = (2.0, 5.0, -1.0)
+    sigmas: Any = (1.0, 1.0, 1.0)
+
+    def logpdf(self, x):
+        xp = _ns(x)
+        acc = None
+        for w, mu, sg in zip(self.weights, self.means, self.sigmas):
+            t = (x - mu) / sg
+            term = (w / sg) * xp.exp(-(t * t + LOG2PI) / 2)       # w * std_normal_pdf, :23
+            acc = term if acc is None else acc + term
+        return xp.log(acc)
+
+
+def nELBO(trafo, xi, target=None):
+    """examples/nf_variational_1d.jl:29-41, literal: `xi` is what the example passes, a (N_samps x xi_dim) matrix
+    (there: (2 batchsize) x 1) that with_logabsdet_jacobian treats like any D x N matrix -- its ROWS are the draws,
+    the length-1 parameter vectors broadcast along them, and `ladj` is summed over them."""
+    target = target or GaussMixture()
+    z, ladj = with_logabsdet_jacobian(trafo, xi)
+    xi_dim = xi.shape[1]
+    n_samps = xi.shape[0]
+    elbo = (target.logpdf(z).sum() + ladj.sum()) / n_samps - 0.5 * (LOG2PI + 1) * xi_dim
+    return -elbo
+
+
+def nELBO_trafograd(trafo, xi, target=None):
+    """examples/nf_variational_1d.jl:43-47 (torch float64 autograd in the role of Zygote)."""
+    import torch
+    ft = _to_torch_params(trafo)
+    val = nELBO(ft, torch.tensor(np.asarray(xi, dtype=np.float64), dtype=torch.float64), target)
+    val.backward()
+    return float(val.detach()), _grads_of(ft)
+
+
+def optimise_ELBO(initial_trafo, optimizer: ADAGrad, batches, *, target=None, optstate=None, nelbo_history=None):
+    """examples/nf_variational_1d.jl:49-69 with the standard-normal draws of every epoch passed in (`batches`: list of
+    length-batchsize vectors; the example draws them from the unseeded global RNG): antithetic pairs `vcat(xi, -xi)`."""
+    import copy
+    trafo = copy.deepcopy(initial_trafo)
+    state = copy.deepcopy(optstate) if optstate is not None else optim_setup(optimizer, trafo)
+    hist = []
+    for b in batches:
+        b = np.asarray(b, dtype=np.float64).reshape(-1, 1)
+        xi = np.vstack([b, -b])                                    # antithetic sampling, :62
+        nelbo, d_trafo = nELBO_trafograd(trafo, xi, target)
+        state, trafo = optim_update(optimizer, state, trafo, d_trafo)
+        hist.append(nelbo)
+    return {"result": trafo, "optimizer_state": state, "nelbo_history": list(nelbo_history or []) + hist}
