@@ -76,17 +76,145 @@ template <> struct Prim<float> {
     }
 };
 
-// Float64: correctly rounded-ish libm, natural logs.
+// Float64: hand-written branch-free exp / log / rsqrt / sqrt / reciprocal (natural logs) for the value ranges the chain
+// kernels produce -- positive normal arguments for log / sqrt / rsqrt / rcp (Jacobian-factor products are range-checked
+// by the callers), |x| < 700 for exp -- instead of libm's general-purpose versions: asinh(double) alone is 384 SASS
+// instructions, log 104, exp2 / sqrt / division 80 each (special cases, denormals, correctly rounded results), and every
+// chain-kernel instantiation inlines them several times.  Accuracy ~2e-16 relative (the Float64 parity budget is 1e-12).
+//   rsqrt / rcp : MUFU.RSQ64H / MUFU.RCP64H seed (rsqrt.approx.ftz.f64, rcp.approx.ftz.f64: ~20 bits) + two Newton steps
+//   exp2(t), t <= 0 : t = n + f (magic-number rounding), degree-12 Taylor polynomial of 2^f on [-1/2, 1/2], exponent
+//                     added with integer arithmetic; t is clamped at -1020
+//   exp(x)      : Cody-Waite x = n ln2 + f with a two-part ln2, degree-13 polynomial of e^f
+//   log(x)      : x = 2^e m, m in [sqrt(1/2), sqrt(2)); s = (m-1)/(m+1); log m = 2 atanh(s) as a degree-10 polynomial in s^2
+#ifndef ENF_F64_LIBM
+#define ENF_F64_LIBM 0   // 1: libm everywhere (cross-check of the hand-written versions)
+#endif
+__device__ __forceinline__ double d_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double d_rsqrt(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = fma(fma(-hx * r, r, 0.5), r, r);
+    r = fma(fma(-hx * r, r, 0.5), r, r);
+    return r;
+}
+__device__ __forceinline__ double d_sqrt(double x) {
+    const double r = d_rsqrt(x);
+    const double s = x * r;
+    return fma(fma(-s, s, x), 0.5 * r, s);      // one more Newton step on the square root itself
+}
+__device__ __forceinline__ double d_poly_exp(double f, const double c1) {
+    // 1 + c1 f + (c1 f)^2/2! + ... written in g = c1 f (|g| <= 0.35): degree 13
+    const double g = c1 * f;
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, g, 2.0876756987868099e-09);        // 1/12!
+    p = fma(p, g, 2.5052108385441720e-08);        // 1/11!
+    p = fma(p, g, 2.7557319223985893e-07);        // 1/10!
+    p = fma(p, g, 2.7557319223985888e-06);        // 1/9!
+    p = fma(p, g, 2.4801587301587302e-05);        // 1/8!
+    p = fma(p, g, 1.9841269841269841e-04);        // 1/7!
+    p = fma(p, g, 1.3888888888888889e-03);        // 1/6!
+    p = fma(p, g, 8.3333333333333332e-03);        // 1/5!
+    p = fma(p, g, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, g, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, g, 0.5);
+    p = fma(p, g, 1.0);
+    return fma(p, g, 1.0);
+}
+__device__ __forceinline__ double d_scale2(double p, double r_magic) {
+    // p * 2^n with n in the low mantissa bits of r_magic = n + 1.5 * 2^52
+    const int n = __double2loint(r_magic);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+__device__ __forceinline__ double d_exp2_neg(double t) {             // 2^t, t <= 0
+    t = fmax(t, -1020.0);
+    const double r = t + 6755399441055744.0;
+    const double f = t - (r - 6755399441055744.0);
+    return d_scale2(d_poly_exp(f, 0.69314718055994530942), r);
+}
+__device__ __forceinline__ double d_exp(double x) {                  // e^x, |x| < 700
+    const double r = fma(x, 1.4426950408889634074, 6755399441055744.0);
+    const double n = r - 6755399441055744.0;
+    double f = fma(n, -6.93147180369123816490e-01, x);               // ln2 hi (32 bits), lo: exact products for |n| < 2^20
+    f = fma(n, -1.90821492927058770002e-10, f);
+    return d_scale2(d_poly_exp(f, 1.0), r);
+}
+__device__ __forceinline__ double d_log(double x) {                  // natural log, x positive and normal
+    int hi = __double2hiint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;                             // m in [1, 2)
+    double m = __hiloint2double(hi, __double2loint(x));
+    const bool big = m > 1.4142135623730951;
+    m = big ? 0.5 * m : m;
+    e = big ? e + 1 : e;
+    const double f = m - 1.0;
+    const double s = f * d_rcp(2.0 + f);
+    const double z = s * s;
+    double p = 9.5238095238095233e-02;          // 2/21
+    p = fma(p, z, 1.0526315789473684e-01);      // 2/19
+    p = fma(p, z, 1.1764705882352941e-01);      // 2/17
+    p = fma(p, z, 1.3333333333333333e-01);      // 2/15
+    p = fma(p, z, 1.5384615384615385e-01);      // 2/13
+    p = fma(p, z, 1.8181818181818182e-01);      // 2/11
+    p = fma(p, z, 2.2222222222222221e-01);      // 2/9
+    p = fma(p, z, 2.8571428571428570e-01);      // 2/7
+    p = fma(p, z, 4.0000000000000002e-01);      // 2/5
+    p = fma(p, z, 6.6666666666666663e-01);      // 2/3
+    const double de = double(e);
+    // log m = 2 s + s z p ;  log x = e ln2_hi + (e ln2_lo + log m)
+    const double lm = fma(s * z, p, 2.0 * s);
+    return fma(de, 6.93147180369123816490e-01, fma(de, 1.90821492927058770002e-10, lm));
+}
+
 template <> struct Prim<double> {
     static constexpr double LGU = 1.0;
     static constexpr double INV_LGU = 1.0;
     static constexpr double LG_OF_2 = 0.69314718055994530942;
     static constexpr double LG_SAFE = 600.0;
+#if ENF_F64_LIBM
     static __device__ __forceinline__ double ex2(double x) { return exp2(x); }
     static __device__ __forceinline__ double lg(double x) { return log(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double rsq(double x) { return 1.0 / sqrt(x); }
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double asinh_lg(double z, double s, double r) { return asinh(z); }
+    static __device__ __forceinline__ void sinhcosh(double sa, double& sh, double& ch) {
+        sh = sinh(sa);
+        ch = cosh(sa);
+    }
+#else
+    static __device__ __forceinline__ double ex2(double x) { return d_exp2_neg(x); }     // every call site has x <= 0
+    static __device__ __forceinline__ double lg(double x) { return d_log(x); }
+    static __device__ __forceinline__ double rcp(double x) { return d_rcp(x); }
+    static __device__ __forceinline__ double rsq(double x) { return d_rsqrt(x); }
+    static __device__ __forceinline__ double sqrt_(double x) { return d_sqrt(x); }
+    // asinh z = sign(z) log(|z| + sqrt(1 + z^2)), given s = 1 + z^2 and r = rsqrt(s)
+    static __device__ __forceinline__ double asinh_lg(double z, double s, double r) {
+        return copysign(d_log(fma(s, r, fabs(z))), z);
+    }
+    static __device__ __forceinline__ void sinhcosh(double sa, double& sh, double& ch) {
+        const double e = d_exp(fabs(sa));
+        const double ei = d_rcp(e);
+        ch = 0.5 * (e + ei);
+        // (e - 1/e)/2 cancels for small arguments: odd Taylor polynomial below |sa| = 0.3 (next term 0.3^16/17! < 2e-23)
+        const double s2 = sa * sa;
+        double p = 7.6471637318198164e-13;          // 1/15!
+        p = fma(p, s2, 1.6059043836821613e-10);     // 1/13!
+        p = fma(p, s2, 2.5052108385441720e-08);     // 1/11!
+        p = fma(p, s2, 2.7557319223985888e-06);     // 1/9!
+        p = fma(p, s2, 1.9841269841269841e-04);     // 1/7!
+        p = fma(p, s2, 8.3333333333333332e-03);     // 1/5!
+        p = fma(p, s2, 1.6666666666666666e-01);     // 1/3!
+        const double small = fma(sa * s2, p, sa);
+        sh = fabs(sa) < 0.3 ? small : copysign(0.5 * (e - ei), sa);
+    }
+#endif
     static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
     static __device__ __forceinline__ double sign_(double x) { return x < 0.0 ? -1.0 : 1.0; }
@@ -96,11 +224,6 @@ template <> struct Prim<double> {
     }
     static __device__ __forceinline__ double xnsign(double v, double s) {
         return __longlong_as_double(__double_as_longlong(v) ^ (~__double_as_longlong(s) & (long long)0x8000000000000000ull));
-    }
-    static __device__ __forceinline__ double asinh_lg(double z, double s, double r) { return asinh(z); }
-    static __device__ __forceinline__ void sinhcosh(double sa, double& sh, double& ch) {
-        sh = sinh(sa);
-        ch = cosh(sa);
     }
 };
 
