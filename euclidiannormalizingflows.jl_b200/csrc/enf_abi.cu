@@ -29,6 +29,10 @@ void affine_fold(int D, int n_ops, const int* kinds, const int* Ks, const double
                  std::vector<float>& wl, std::vector<float>& bias);
 }
 
+namespace enf {
+void wy_fold(int D, int n_ops, const int* kinds, const int* Ks, const double* const* params, std::vector<float>& out);
+}
+
 using namespace enf;
 
 // ------------------------------------------------------------------ errors
@@ -161,6 +165,8 @@ struct enf_chain {
     double* h_sums = nullptr;  // pinned, n_raw + 1
     // Householder/ScaleShift-only chains at large D: folded affine map for the tensor-core kernel (enf_affine.cu)
     bool affine = false;
+    bool wy = false;            // ... of which those with few enough reflections run in compact-WY form (enf_wy.cu)
+    float* d_wy = nullptr;      // Wt hi | Wt lo | U hi | U lo | alpha | c
     float* d_affine = nullptr;  // Wh | Wl | bias
     // ... and their loss/gradient from the batch's second moments (enf_moments.cu): the raw sums are
     // [[S, m], [m^T, N]] ((D+1)^2 doubles) instead of per-op sums
@@ -308,6 +314,12 @@ int ensure_affine(enf_chain* ch) {
             kinds.push_back(op.kind);
             Ks.push_back(op.K);
             pp.push_back(ch->params.data() + op.poff);
+        }
+        if (ch->wy) {
+            std::vector<float> buf;
+            wy_fold(D, int(kinds.size()), kinds.data(), Ks.data(), pp.data(), buf);
+            CU(ctx, cudaMemcpyAsync(ch->d_wy, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
         }
         std::vector<float> wh, wl, bias;
         affine_fold(D, int(kinds.size()), kinds.data(), Ks.data(), pp.data(), wh, wl, bias);
@@ -843,6 +855,7 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
     d.n_save = save;
     ch->n_raw = d.n_rowslots * d.Dp + d.n_scalars + 2;
     ch->affine = affine_supported(dtype, D, d);
+    ch->wy = ch->affine && wy_rank(dtype, D, d) > 0;
     ch->moments = ch->affine && moments_supported(dtype, D) && getenv("ENF_NO_MOMENTS") == nullptr;
     if (ch->moments) ch->n_raw = (D + 1) * (D + 1);
     if (fwd_smem_bytes(dtype, d) > 200 * 1024) {
@@ -882,6 +895,10 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
         enf_chain_destroy(ch);
         return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
     }
+    if (ch->wy && (e = cudaMalloc(reinterpret_cast<void**>(&ch->d_wy), wy_buffer_floats(D) * sizeof(float))) != cudaSuccess) {
+        enf_chain_destroy(ch);
+        return fail(ctx, ENF_ERR_CUDA, "chain allocation failed: %s", cudaGetErrorString(e));
+    }
     int rc = validate_params(ch);
     if (rc == ENF_OK) rc = derive_constants(ch);
     if (rc != ENF_OK) { enf_chain_destroy(ch); return rc; }
@@ -918,6 +935,7 @@ extern "C" int enf_chain_destroy(enf_chain* ch) {
     if (ch->d_sums) cudaFree(ch->d_sums);
     if (ch->h_sums) cudaFreeHost(ch->h_sums);
     if (ch->d_affine) cudaFree(ch->d_affine);
+    if (ch->d_wy) cudaFree(ch->d_wy);
     if (ch->d_params64) cudaFree(ch->d_params64);
     if (ch->d_mom_out) cudaFree(ch->d_mom_out);
     if (ch->d_mom_part) cudaFree(ch->d_mom_part);
@@ -956,7 +974,11 @@ static int forward_impl(enf_chain* ch, const void* x, int64_t N, void* y, void* 
         // Householder / ScaleShift stack at large D: one tcgen05 GEMM per tile (enf_affine.cu)
         int rca = ensure_affine(ch);
         if (rca != ENF_OK) return rca;
-        CU(ctx, launch_affine(ch->D, ch->d_affine, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));
+        static const bool no_wy = getenv("ENF_NO_WY") != nullptr;      // cross-check: dense fold instead of compact WY
+        if (ch->wy && !no_wy)
+            CU(ctx, launch_wy(ch->D, ch->d_wy, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));
+        else
+            CU(ctx, launch_affine(ch->D, ch->d_affine, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));
         ctx->launches += 1;
         return ENF_OK;
     }

@@ -58,6 +58,11 @@ struct P2PDesc {
 cudaError_t launch_p2p_allreduce(const P2PDesc& d, double* sums, int n, cudaStream_t st);
 
 bool affine_supported(int dtype, int D, const ChainDesc& d);
+// compact-WY form on the tensor cores (enf_wy.cu): y = alpha . x - U (W^T x) + c, two chained tcgen05 GEMMs per tile
+int wy_rank(int dtype, int D, const ChainDesc& d);      // number of reflections if the WY kernel applies, else 0
+size_t wy_buffer_floats(int D);
+cudaError_t launch_wy(int D, const float* d_wy, const void* x, void* y, void* ladj, int64_t N, double ladj_const,
+                      int sm_count, cudaStream_t st);
 // second moments [[S, m], [m^T, N]] of a D x N batch on tensor cores (enf_moments.cu); d_part: scratch of
 // moments_partial_bytes() bytes, d_sums: (D+1)^2 + 1 doubles
 bool moments_supported(int dtype, int D);
