@@ -30,7 +30,7 @@ void affine_fold(int D, int n_ops, const int* kinds, const int* Ks, const double
 }
 
 namespace enf {
-void wy_fold(int D, int n_ops, const int* kinds, const int* Ks, const double* const* params, std::vector<float>& out);
+bool wy_fold(int D, int n_ops, const int* kinds, const int* Ks, const double* const* params, std::vector<float>& out);
 }
 
 using namespace enf;
@@ -166,6 +166,7 @@ struct enf_chain {
     // Householder/ScaleShift-only chains at large D: folded affine map for the tensor-core kernel (enf_affine.cu)
     bool affine = false;
     bool wy = false;            // ... of which those with few enough reflections run in compact-WY form (enf_wy.cu)
+    bool wy_valid = false;      // ... unless the current parameters have a zero scale
     float* d_wy = nullptr;      // Wt hi | Wt lo | U hi | U lo | alpha | c
     float* d_affine = nullptr;  // Wh | Wl | bias
     // ... and their loss/gradient from the batch's second moments (enf_moments.cu): the raw sums are
@@ -317,7 +318,7 @@ int ensure_affine(enf_chain* ch) {
         }
         if (ch->wy) {
             std::vector<float> buf;
-            wy_fold(D, int(kinds.size()), kinds.data(), Ks.data(), pp.data(), buf);
+            ch->wy_valid = wy_fold(D, int(kinds.size()), kinds.data(), Ks.data(), pp.data(), buf);
             CU(ctx, cudaMemcpyAsync(ch->d_wy, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
             CU(ctx, cudaStreamSynchronize(ctx->stream));
         }
@@ -975,7 +976,7 @@ static int forward_impl(enf_chain* ch, const void* x, int64_t N, void* y, void* 
         int rca = ensure_affine(ch);
         if (rca != ENF_OK) return rca;
         static const bool no_wy = getenv("ENF_NO_WY") != nullptr;      // cross-check: dense fold instead of compact WY
-        if (ch->wy && !no_wy)
+        if (ch->wy && ch->wy_valid && !no_wy)
             CU(ctx, launch_wy(ch->D, ch->d_wy, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));
         else
             CU(ctx, launch_affine(ch->D, ch->d_affine, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));

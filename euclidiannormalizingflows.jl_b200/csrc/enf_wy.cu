@@ -3,30 +3,35 @@
 //
 // A chain of HouseholderTrafo and ScaleShiftTrafo ops is "diagonal + low rank":  with the pre-scaled vectors
 // v' = v sqrt(2 / v.v) every reflection (src/householder_trafo.jl:4-11) is I - v' v'^T, and the whole chain folds into
-//        y = alpha . x  -  U (W^T x)  +  c ,        U, W : D x Kt  (Kt = number of reflections),
-// on the host in float64 (wy_fold: one column of U and W per reflection, ScaleShift scales alpha, U and c).  Per sample
-// that is 4 D Kt flops instead of the 2 D^2 of the dense fold y = W x + c (enf_affine.cu): at D = 256, Kt = 64 half
-// the tensor work, and the dense kernel is tensor-bound.  Chains with Kt > 64 (or Kt > D/2) keep the dense kernel.
+//        y = alpha . (x + U' (W^T x)) + c ,        U', W : D x Kt  (Kt = number of reflections),
+// on the host in float64 (wy_fold: one column of U' and W per reflection; U' = -U / alpha row-wise).  Per sample that is
+// 4 D Kt flops instead of the 2 D^2 of the dense fold y = W x + c (enf_affine.cu): at D = 256, Kt = 64 half the tensor
+// work, and the dense kernel is tensor-bound.  Chains with Kt > 64 (or Kt > D/2, or a zero scale) keep the dense kernel.
 //
-// Per 128-sample tile, TWO chained GEMMs on the 5th-generation tensor cores (kind::tf32, 3xTF32 for Float32 accuracy):
-//   GEMM1   T[128 x 64]  = X[128 x D] . W[D x 64]       A = sample tile from shared memory (the column-major D x N sample
-//                                                        matrix IS the K-major operand), B = W^T chunks, D = TMEM
-//   hand-off T -> (Thi, Tlo): four warps read the accumulator (tcgen05.ld), split it into tf32 high / low parts and write
-//                             them back to TENSOR MEMORY (tcgen05.st) -- GEMM2 takes its A operand from TMEM, so the
-//                             128 x 64 intermediate never touches shared memory
-//   GEMM2   V[128 x D]   = T[128 x 64] . U^T[64 x D]    A = Thi / Tlo in TMEM, B = U (resident in shared memory), D = TMEM
-//   epilogue y = alpha . x - V + c: TMEM hands a lane one sample, global memory wants a lane to own columns: -V is
-//            transposed through a 4 KB shared-memory box per warp, the sample tile is re-read from L2 (it was streamed
-//            through the ring and is gone from shared memory) with coalesced loads, y is stored with coalesced stores.
-// GEMM1 and GEMM2 are issued by two different warps, so that neither waits behind the other's barriers; T is double
-// buffered, so GEMM1 runs up to two tiles ahead of GEMM2 and the hand-off / epilogue overlap tensor work.
+// Per 128-sample tile the sample tile LIVES IN TENSOR MEMORY: the accumulator V (128 lanes x D columns) is initialised
+// with x itself, serves as the A operand of the first GEMM, receives the low-rank update from the second GEMM, and is
+// drained once as y.  Nothing is read twice from HBM or L2, and only the remainder xl = x - tf32(x) of the 3xTF32 split
+// ever sits in shared memory as an operand.
+//   split    four warps (one TMEM lane quarter each, thread = sample row) read a 32-column chunk of x from the TMA ring,
+//            store it to V with tcgen05.st, and overwrite it IN PLACE with xl = tf32(x - trunc_tf32(x)) (the tensor core
+//            reads the upper 19 bits of a 32-bit container, so V itself is the truncated high part)
+//   GEMM1    T[128 x 64] = X W:  (main | correction) += V[:, k..k+8] (A from TMEM) . [Wh | Wl]  (one N = 128 MMA),
+//                                 correction += xl (A from smem) . Wh
+//   hand-off T -> (Thi, Tlo): eight warps read the accumulator pair, split the sum into tf32 high / low parts and write
+//            them back to tensor memory in place; GEMM2 takes its A operand from there
+//   GEMM2    V += Thi . U'h + Tlo . U'h + Thi . U'l   (A from TMEM, B = 16 KB pieces of U' streamed through four buffers),
+//            first for the columns [0, D/2), then for [D/2, D): the epilogue drains the first half while the second runs
+//   epilogue y = alpha . V + c: TMEM hands a lane one sample, global memory wants a lane to own columns: V is transposed
+//            through a 4 KB shared-memory box per warp and stored with coalesced 16-byte stores.  A drained 32-column
+//            chunk of V is handed back to the splitters at once, so the next tile's x flows in behind the epilogue.
+// GEMM1 and GEMM2 are issued by two different warps; T is double buffered (GEMM1 of the next tile starts while the second
+// half of GEMM2 still reads T).
 //
-// Shared memory at D = 256: 3-stage ring of 32-column chunks (x, xl, Wh, Wl: 48 KB per stage, 96 KB of TMA loads in
-// flight) + two 32 KB buffers through which the four pieces of U (hi / lo x two k-halves) stream per tile + 4 staging
-// boxes = 224 KB (a resident U would leave room for only 72 KB of ring: measured, the ring then starves).  TMEM: two T buffers of (main | correction) accumulators (2 x 128 columns; the hand-off
-// rewrites a buffer in place as Thi | Tlo) | V (D columns) = 512.
-// Warp roles (352 threads): warp 0 TMA producer (x, W), warp 1 TMEM owner + MMA issuer, warps 2-5 xh/xl split of every
-// chunk, warps 6-9 hand-off + epilogue (one TMEM lane quarter each), warp 10 TMA producer of the U pieces.
+// Shared memory: 4-stage ring of 32-column chunks (x -> xl 16 KB | Wh 8 KB | Wl 8 KB) = 128 KB, four 16 KB buffers for
+// the pieces of U', eight 4 KB staging boxes = 224 KB.  TMEM: two T buffers of (main | correction) = 2 x 128 columns,
+// then V (D columns).
+// Warp roles (512 threads): warp 0 TMA producer (x, W), warp 1 TMEM owner + GEMM1 issuer, warps 2-5 splitters, warps 6-13
+// hand-off + epilogue (two per TMEM lane quarter), warp 14 TMA producer of the U' pieces, warp 15 GEMM2 issuer.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -45,25 +50,24 @@ namespace {
 constexpr int WY_TILE_M = 128;
 constexpr int WY_KC = 32;            // columns per ring chunk: one 128-byte swizzle atom per row
 constexpr int WY_KT = 64;            // reflections (padded with zero columns)
-constexpr int WY_STAGES = 3;
-constexpr int WY_SPLITTERS = 128;
-constexpr int WY_THREADS = 64 + WY_SPLITTERS + 128 + 64;   // + warp 10: producer of the U pieces, warp 11: GEMM2 issuer
-constexpr int WY_EPI_WARPS = 4;
+constexpr int WY_STAGES = 4;
+constexpr int WY_UBUFS = 4;
+constexpr int WY_SPLIT_WARPS = 4;
+constexpr int WY_EPI_WARPS = 8;
+constexpr int WY_THREADS = 32 * (2 + WY_SPLIT_WARPS + WY_EPI_WARPS + 2);
 
 template <int ND>
 struct WySmem {
-    static constexpr int X_BYTES = WY_TILE_M * WY_KC * 4;          // 16 KB
-    static constexpr int W_BYTES = WY_KT * WY_KC * 4;              // 8 KB
-    static constexpr int STAGE_BYTES = 2 * X_BYTES + 2 * W_BYTES;  // xh | xl | Wh | Wl = 48 KB
-    static constexpr int U_CHUNK_BYTES = ND * 32 * 4;              // one piece of U: [ND rows x 32 k], 128B swizzle (32 KB at ND = 256)
-    static constexpr int U_BYTES = 2 * U_CHUNK_BYTES;              // two piece buffers; the four pieces (Ul k0, Ul k1, Uh k0, Uh k1) of a
-    static constexpr int RING_OFF = U_BYTES;                       // tile stream through them
+    static constexpr int HALF = ND / 2;                             // output columns per GEMM2 pass
+    static constexpr int X_BYTES = WY_TILE_M * WY_KC * 4;           // 16 KB
+    static constexpr int W_BYTES = WY_KT * WY_KC * 4;               // 8 KB
+    static constexpr int STAGE_BYTES = X_BYTES + 2 * W_BYTES;       // x -> xl | Wh | Wl = 32 KB
+    static constexpr int U_PIECE_BYTES = HALF * 32 * 4;             // one piece of U': [HALF rows x 32 k], 128B swizzle
+    static constexpr int RING_OFF = WY_UBUFS * U_PIECE_BYTES;
     static constexpr int OUT_BYTES = 32 * 32 * 4;
     static constexpr int OUT_OFF = RING_OFF + WY_STAGES * STAGE_BYTES;
     static constexpr int BAR_OFF = OUT_OFF + WY_EPI_WARPS * OUT_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
-    // tensor memory: two T buffers of (main | correction) accumulators, 64 columns each, then V.  The hand-off rewrites a
-    // buffer in place as (Thi | Tlo).
+    static constexpr int TOTAL = BAR_OFF + 512 + 1024;
     static constexpr uint32_t T_COL = 0, T_BUF_COLS = 128, TC_OFF = 64, V_COL = 256;
     static constexpr uint32_t TMEM_COLS = 512;
 };
@@ -93,23 +97,24 @@ __global__ void __launch_bounds__(WY_THREADS, 1)
 wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
                const __grid_constant__ CUtensorMap map_wl, const __grid_constant__ CUtensorMap map_uh,
                const __grid_constant__ CUtensorMap map_ul,
-               const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ alpha,
+               float* __restrict__ y, const float* __restrict__ alpha,
                const float* __restrict__ cvec, float* __restrict__ ladj, float ladj_const, int64_t N) {
     using S = WySmem<ND>;
-    constexpr int NKC = ND / WY_KC;                    // ring chunks per tile
+    constexpr int NKC = ND / WY_KC;                    // ring chunks per tile = 32-column chunks of V
+    constexpr int HALF = S::HALF;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // TMA landed                     (1 + tx)
-    uint64_t* split = full + WY_STAGES;                                // xh / xl written                (4 warps)
+    uint64_t* split = full + WY_STAGES;                                // x in V, xl written             (4 warps)
     uint64_t* empty = split + WY_STAGES;                               // MMAs of the stage retired      (tcgen05.commit)
-    uint64_t* u_full = empty + WY_STAGES;                              // [2] a piece of U landed        (1 + tx)
-    uint64_t* u_empty = u_full + 2;                                    // [2] its MMAs retired           (tcgen05.commit)
-    uint64_t* t_full = u_empty + 2;                                    // [2] GEMM1 of a tile retired    (tcgen05.commit)
-    uint64_t* t_split = t_full + 2;                                    // [2] Thi / Tlo written          (4 warps)
+    uint64_t* u_full = empty + WY_STAGES;                              // a piece of U' landed           (1 + tx)
+    uint64_t* u_empty = u_full + WY_UBUFS;                             // its MMAs retired               (tcgen05.commit)
+    uint64_t* t_full = u_empty + WY_UBUFS;                             // [2] GEMM1 of a tile retired    (tcgen05.commit)
+    uint64_t* t_split = t_full + 2;                                    // [2] Thi / Tlo written          (8 warps)
     uint64_t* t_free = t_split + 2;                                    // [2] GEMM2 has read Thi / Tlo   (tcgen05.commit)
-    uint64_t* v_full = t_free + 2;                                     // GEMM2 of a tile retired        (tcgen05.commit)
-    uint64_t* v_empty = v_full + 1;                                    // epilogue has drained V         (4 warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + 1);
+    uint64_t* v_full = t_free + 2;                                     // [2] a column half of V is final (tcgen05.commit)
+    uint64_t* v_free = v_full + 2;                                     // [NKC] a chunk of V is drained  (4 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_free + NKC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (N + WY_TILE_M - 1) / WY_TILE_M;
@@ -118,18 +123,20 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < WY_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&split[s], WY_SPLITTERS / 32);
+            mbar_init(&split[s], WY_SPLIT_WARPS);
             mbar_init(&empty[s], 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < WY_UBUFS; ++b) {
             mbar_init(&u_full[b], 1);
             mbar_init(&u_empty[b], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
             mbar_init(&t_full[b], 1);
             mbar_init(&t_split[b], WY_EPI_WARPS);
             mbar_init(&t_free[b], 1);
+            mbar_init(&v_full[b], 1);
         }
-        mbar_init(v_full, 1);
-        mbar_init(v_empty, WY_EPI_WARPS);
+        for (int c = 0; c < NKC; ++c) mbar_init(&v_free[c], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -138,6 +145,7 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tV = tmem_base + S::V_COL;
 
     if (warp == 0) {
         // ===== TMA producer: x and W chunks =====
@@ -150,15 +158,16 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     if (it >= uint32_t(WY_STAGES)) mbar_wait(&empty[s], ((it / WY_STAGES) - 1) & 1);
                     unsigned char* st = smem + S::RING_OFF + size_t(s) * S::STAGE_BYTES;
                     mbar_expect_tx(&full[s], S::X_BYTES + 2 * S::W_BYTES);
-                    tma_load_2d(st, &map_x, kc * WY_KC, int(tile * WY_TILE_M), &full[s]);              // x chunk  [128 x 32]
-                    tma_load_2d(st + 2 * S::X_BYTES, &map_wh, kc * WY_KC, 0, &full[s]);                // Wh chunk [64 x 32]
-                    tma_load_2d(st + 2 * S::X_BYTES + S::W_BYTES, &map_wl, kc * WY_KC, 0, &full[s]);   // Wl chunk
+                    tma_load_2d_hint(st, &map_x, kc * WY_KC, int(tile * WY_TILE_M), &full[s], L2_EVICT_FIRST);   // x chunk [128 x 32]
+                    tma_load_2d_hint(st + S::X_BYTES, &map_wh, kc * WY_KC, 0, &full[s], L2_EVICT_LAST);          // Wh chunk [64 x 32]
+                    tma_load_2d_hint(st + S::X_BYTES + S::W_BYTES, &map_wl, kc * WY_KC, 0, &full[s], L2_EVICT_LAST);
                 }
             }
         }
     } else if (warp == 1) {
         // ===== GEMM1 issuer: T(i) = X(i) W into a (main | correction) accumulator pair =====
-        constexpr uint32_t idesc1 = make_idesc_tf32(WY_TILE_M, WY_KT);
+        constexpr uint32_t idesc_n128 = make_idesc_tf32(WY_TILE_M, 2 * WY_KT);
+        constexpr uint32_t idesc_n64 = make_idesc_tf32(WY_TILE_M, WY_KT);
         uint32_t it = 0;
         for (int i = 0; i < my_tiles; ++i) {
             const uint32_t buf = uint32_t(i) & 1u;
@@ -173,18 +182,16 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     unsigned char* st = smem + S::RING_OFF + size_t(s) * S::STAGE_BYTES;
-                    const uint64_t dxh = make_desc_kmajor<WY_KC>(st), dxl = make_desc_kmajor<WY_KC>(st + S::X_BYTES);
-                    const uint64_t dwh = make_desc_kmajor<WY_KC>(st + 2 * S::X_BYTES);
-                    const uint64_t dwl = make_desc_kmajor<WY_KC>(st + 2 * S::X_BYTES + S::W_BYTES);
+                    const uint64_t dxl = make_desc_kmajor<WY_KC>(st);
+                    const uint64_t dw = make_desc_kmajor<WY_KC>(st + S::X_BYTES);      // rows 0-63 Wh, rows 64-127 Wl
 #pragma unroll
                     for (int j = 0; j < WY_KC / 8; ++j) {          // UMMA K = 8 tf32 = 32 bytes inside the swizzle atom
                         const uint64_t adv = uint64_t((j * 32) >> 4);
-                        // The tensor core truncates when it adds into the f32 accumulator, one ulp of the ACCUMULATOR per MMA
-                        // whatever the size of the addend.  The two correction products (2^-11 of the main one) get an
-                        // accumulator of their own: the main one then sees 32 instead of 96 truncating additions per tile.
-                        umma_tf32(tM, dxh + adv, dwh + adv, idesc1, (kc | j) != 0);
-                        umma_tf32(tC, dxl + adv, dwh + adv, idesc1, (kc | j) != 0);
-                        umma_tf32(tC, dxh + adv, dwl + adv, idesc1, 1);
+                        // (main | correction) (+)= trunc(x) . [Wh | Wl]: A = the chunk's columns of V.  The tensor core truncates
+                        // when it adds into the f32 accumulator, one ulp of the ACCUMULATOR per MMA whatever the size of the
+                        // addend: the 2^-11-small correction products have an accumulator of their own.
+                        umma_tf32_ts(tM, tV + uint32_t(kc * WY_KC + j * 8), dw + adv, idesc_n128, (kc | j) != 0);
+                        umma_tf32(tC, dxl + adv, dw + adv, idesc_n64, 1);              // correction += xl . Wh
                     }
                     umma_commit(&empty[s]);
                     if (kc == NKC - 1) umma_commit(&t_full[buf]);
@@ -192,170 +199,162 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 __syncwarp();
             }
         }
-    } else if (warp == 11) {
-        // ===== GEMM2 issuer: V(j) = T(j) U^T, A = Thi | Tlo in tensor memory, B = the streamed pieces of U =====
-        constexpr uint32_t idesc2 = make_idesc_tf32(WY_TILE_M, ND);
+    } else if (warp == 15) {
+        // ===== GEMM2 issuer: V(j) += T(j) U'^T, A = Thi | Tlo in tensor memory, B = the streamed pieces of U' =====
+        constexpr uint32_t idesc2 = make_idesc_tf32(WY_TILE_M, HALF);
+        uint32_t q = 0;
         for (int j = 0; j < my_tiles; ++j) {
             const uint32_t buf = uint32_t(j) & 1u;
             mbar_wait(&t_split[buf], uint32_t(j >> 1) & 1u);                           // Thi / Tlo of tile j are in TMEM
-            if (j >= 1) mbar_wait(v_empty, uint32_t(j - 1) & 1u);                      // epilogue of tile j-1 has drained V
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tV = tmem_base + S::V_COL;
             const uint32_t tHI = tmem_base + S::T_COL + buf * S::T_BUF_COLS, tLO = tHI + S::TC_OFF;
-            // pieces in the order Ul k0, Ul k1 (corrections Thi . Ul first: while the accumulator is still 2^-11 small their
-            // truncation errors are too), then Uh k0, Uh k1 (correction Tlo . Uh, then the main product Thi . Uh)
 #pragma unroll 1
-            for (int pc = 0; pc < 4; ++pc) {
-                const int q = 4 * j + pc, b = q & 1;
-                mbar_wait(&u_full[b], uint32_t(q >> 1) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint64_t du = make_desc_kmajor<32>(smem + b * S::U_CHUNK_BYTES);
-                    const uint32_t k0 = uint32_t(pc & 1) * 32u;                        // first T column of this piece
+            for (int h = 0; h < 2; ++h) {
+                // pieces of a half: U'l k0, U'l k1 (correction Thi . U'l), U'h k0, U'h k1 (Tlo . U'h and the main product)
+#pragma unroll 1
+                for (int pc = 0; pc < 4; ++pc, ++q) {
+                    const uint32_t b = q % WY_UBUFS;
+                    mbar_wait(&u_full[b], (q / WY_UBUFS) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (lane == 0) {
+                        const uint64_t du = make_desc_kmajor<32>(smem + b * S::U_PIECE_BYTES);
+                        const uint32_t k0 = uint32_t(pc & 1) * 32u;                    // first T column of this piece
+                        const uint32_t tD = tV + uint32_t(h * HALF);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t adv = uint64_t((kk * 32) >> 4);
-                        if (pc < 2) {
-                            umma_tf32_ts(tV, tHI + k0 + uint32_t(kk * 8), du + adv, idesc2, (pc | kk) != 0);
-                        } else {
-                            umma_tf32_ts(tV, tLO + k0 + uint32_t(kk * 8), du + adv, idesc2, 1);
-                            umma_tf32_ts(tV, tHI + k0 + uint32_t(kk * 8), du + adv, idesc2, 1);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t adv = uint64_t((kk * 32) >> 4);
+                            if (pc >= 2) umma_tf32_ts(tD, tLO + k0 + uint32_t(kk * 8), du + adv, idesc2, 1);
+                            umma_tf32_ts(tD, tHI + k0 + uint32_t(kk * 8), du + adv, idesc2, 1);
+                        }
+                        umma_commit(&u_empty[b]);
+                        if (pc == 3) {
+                            umma_commit(&v_full[h]);
+                            if (h == 1) umma_commit(&t_free[buf]);
                         }
                     }
-                    umma_commit(&u_empty[b]);
-                    if (pc == 3) {
-                        umma_commit(v_full);
-                        umma_commit(&t_free[buf]);
-                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
-    } else if (warp == 10) {
-        // ===== producer of the U pieces: per tile Ul k0, Ul k1, Uh k0, Uh k1 through two buffers =====
+    } else if (warp == 14) {
+        // ===== producer of the U' pieces: per tile and column half U'l k0, U'l k1, U'h k0, U'h k1 =====
         if (lane == 0) {
-            for (int q = 0; q < 4 * my_tiles; ++q) {
-                const int b = q & 1, pc = q & 3;
-                if (q >= 2) mbar_wait(&u_empty[b], uint32_t((q >> 1) - 1) & 1u);
-                mbar_expect_tx(&u_full[b], S::U_CHUNK_BYTES);
-                tma_load_2d(smem + b * S::U_CHUNK_BYTES, pc < 2 ? &map_ul : &map_uh, (pc & 1) * 32, 0, &u_full[b]);
+            for (uint32_t q = 0; q < uint32_t(8 * my_tiles); ++q) {
+                const uint32_t b = q % WY_UBUFS, pc = q & 3u, h = (q >> 2) & 1u;
+                if (q >= uint32_t(WY_UBUFS)) mbar_wait(&u_empty[b], ((q / WY_UBUFS) - 1) & 1u);
+                mbar_expect_tx(&u_full[b], S::U_PIECE_BYTES);
+                tma_load_2d_hint(smem + b * S::U_PIECE_BYTES, pc < 2 ? &map_ul : &map_uh, int(pc & 1u) * 32, int(h) * HALF, &u_full[b],
+                                 L2_EVICT_LAST);
             }
         }
-    } else if (warp < 2 + WY_SPLITTERS / 32) {
-        // ===== splitters: x -> xh (round-to-nearest tf32, in place) and xl = x - xh (second buffer) =====
-        const int wt = threadIdx.x - 64;
+    } else if (warp < 2 + WY_SPLIT_WARPS) {
+        // ===== splitters (thread = sample row of this warp's TMEM lane quarter): x -> V, xl = tf32(x - trunc(x)) in place =====
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_off = uint32_t(quarter * 32) << 16;
         uint32_t it = 0;
         for (int i = 0; i < my_tiles; ++i) {
             for (int kc = 0; kc < NKC; ++kc, ++it) {
                 const int s = it % WY_STAGES;
                 mbar_wait(&full[s], (it / WY_STAGES) & 1);
-                float4* xs = reinterpret_cast<float4*>(smem + S::RING_OFF + size_t(s) * S::STAGE_BYTES);
-                float4* xl = reinterpret_cast<float4*>(smem + S::RING_OFF + size_t(s) * S::STAGE_BYTES + S::X_BYTES);
+                if (i >= 1) mbar_wait(&v_free[kc], uint32_t(i - 1) & 1u);      // the epilogue of tile i-1 has drained these columns
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // 16-byte chunk q of row r sits at chunk q ^ (r & 7) of the row (TMA 128-byte swizzle): conflict-free LDS.128
+                uint4* xs = reinterpret_cast<uint4*>(smem + S::RING_OFF + size_t(s) * S::STAGE_BYTES) + row * 8;
+                uint32_t xv[32];
 #pragma unroll
-                for (int q = 0; q < S::X_BYTES / 16 / WY_SPLITTERS; ++q) {
-                    const float4 v = xs[wt + q * WY_SPLITTERS];
-                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                    xs[wt + q * WY_SPLITTERS] = h;
-                    xl[wt + q * WY_SPLITTERS] = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 v = xs[q ^ (row & 7)];
+                    xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
                 }
+                tmem_st32(tV + uint32_t(kc * WY_KC) + lane_off, xv);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint4 o;
+                    o.x = __float_as_uint(tf32_hi(__uint_as_float(xv[4 * q]) - __uint_as_float(xv[4 * q] & 0xFFFFE000u)));
+                    o.y = __float_as_uint(tf32_hi(__uint_as_float(xv[4 * q + 1]) - __uint_as_float(xv[4 * q + 1] & 0xFFFFE000u)));
+                    o.z = __float_as_uint(tf32_hi(__uint_as_float(xv[4 * q + 2]) - __uint_as_float(xv[4 * q + 2] & 0xFFFFE000u)));
+                    o.w = __float_as_uint(tf32_hi(__uint_as_float(xv[4 * q + 3]) - __uint_as_float(xv[4 * q + 3] & 0xFFFFE000u)));
+                    xs[q ^ (row & 7)] = o;
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&split[s]);
             }
         }
     } else {
-        // ===== warps 6-9: hand-off (T -> Thi | Tlo, in place in tensor memory) and epilogue (y = alpha x + c - V), whichever
-        // is ready first: the hand-off of tile j+1 must not wait behind the epilogue of tile j, nor the other way round =====
+        // ===== warps 6-13: per tile the hand-off (T -> Thi | Tlo, in place in tensor memory), then the epilogue (y = alpha V + c).
+        // Two warps share a TMEM lane quarter: member p takes the T columns [32 p, 32 p + 32) and the V chunks c = p (mod 2) =====
         const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
-        const int ew = warp - 2 - WY_SPLITTERS / 32;
+        const int ew = warp - 2 - WY_SPLIT_WARPS;
+        const int p = ew >> 2;
         float4* box = reinterpret_cast<float4*>(smem + S::OUT_OFF + size_t(ew) * S::OUT_BYTES);
         const uint32_t lane_off = uint32_t(quarter * 32) << 16;
         const int rq = lane >> 3, cq = lane & 7;                       // epilogue phase 2: rows rq + 4 i, 16-byte chunk cq
-        int jh = 0, je = 0;                                            // next tile to hand off / to drain
-        while (je < my_tiles) {
-            int what = 0;                                              // 1: hand-off, 2: epilogue
-            if (lane == 0) {
-                for (;;) {
-                    if (jh < my_tiles && jh <= je + 1 && mbar_try_wait(&t_full[jh & 1], uint32_t(jh >> 1) & 1u)) { what = 1; break; }
-                    if (je < jh && mbar_try_wait(v_full, uint32_t(je) & 1u)) { what = 2; break; }
-                }
-            }
-            what = __shfl_sync(0xffffffffu, what, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (what == 1) {
-                // ---- hand-off: this warp's 32 rows of T(jh): main + correction, split into tf32 high / low parts
-                const uint32_t buf = uint32_t(jh) & 1u;
-#pragma unroll 1
-                for (int h = 0; h < WY_KT / 32; ++h) {
-                    const uint32_t tM = tmem_base + S::T_COL + buf * S::T_BUF_COLS + uint32_t(h * 32) + lane_off, tC = tM + S::TC_OFF;
-                    float v[32], w[32];
-                    tmem_ld32(tM, v);
-                    tmem_ld32(tC, w);
-                    uint32_t hi[32], lo[32];
+        for (int j = 0; j < my_tiles; ++j) {
+            {
+                // ---- hand-off: this warp's 32 rows x 32 columns of T(j): main + correction, split into tf32 high / low parts
+                const uint32_t buf = uint32_t(j) & 1u;
+                mbar_wait(&t_full[buf], uint32_t(j >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tM = tmem_base + S::T_COL + buf * S::T_BUF_COLS + uint32_t(p * 32) + lane_off, tC = tM + S::TC_OFF;
+                float v[32], w[32];
+                tmem_ld32(tM, v);
+                tmem_ld32(tC, w);
+                uint32_t hi[32], lo[32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float t = v[e] + w[e];
-                        const float hh = tf32_hi(t);
-                        hi[e] = __float_as_uint(hh);
-                        lo[e] = __float_as_uint(tf32_hi(t - hh));
-                    }
-                    tmem_st32(tM, hi);                                 // in place: (main | correction) -> (Thi | Tlo)
-                    tmem_st32(tC, lo);
+                for (int e = 0; e < 32; ++e) {
+                    const float t = v[e] + w[e];
+                    const float hh = tf32_hi(t);
+                    hi[e] = __float_as_uint(hh);
+                    lo[e] = __float_as_uint(tf32_hi(t - hh));
                 }
+                tmem_st32(tM, hi);                                     // in place: (main | correction) -> (Thi | Tlo)
+                tmem_st32(tC, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&t_split[buf]);
-                ++jh;
-                continue;
             }
-            // ---- epilogue of tile je.  TMEM hands a lane one SAMPLE (32 columns of it); global memory wants a lane to own
-            // COLUMNS.  A 4 KB shared-memory box does the transpose: -V goes in by rows, then every lane adds alpha . x + c to
-            // the 16-byte chunks of ITS column group (8 lanes cover one 128-byte row segment: coalesced re-read of the tile
-            // from L2 and coalesced stores of y, 4 rows per instruction).
-            const int64_t tile = int64_t(blockIdx.x) + int64_t(je) * gridDim.x;
+            // ---- epilogue of tile j.  TMEM hands a lane one SAMPLE (32 columns of it); global memory wants a lane to own
+            // COLUMNS.  A 4 KB shared-memory box does the transpose: V goes in by rows, then every lane scales the 16-byte
+            // chunks of ITS column group (8 lanes cover one 128-byte row segment: coalesced stores of y, 4 rows per instruction).
+            const int64_t tile = int64_t(blockIdx.x) + int64_t(j) * gridDim.x;
             const int64_t row0 = tile * WY_TILE_M + quarter * 32;      // this warp's 32 samples
-            const float* xbase = x + (row0 + rq) * int64_t(ND) + cq * 4;
             float* ybase = y + (row0 + rq) * int64_t(ND) + cq * 4;
-            auto load_x = [&](int c, float4 (&xr)[8]) {
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(&v_full[h], uint32_t(j) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    xr[i] = (row0 + rq + 4 * i < N) ? __ldcg(reinterpret_cast<const float4*>(xbase + int64_t(4 * i) * ND + c * 32))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-            };
-            constexpr int PF = 3;                                      // boxes of x in flight (L2 latency >> time per box)
-            float4 xr[PF][8];
+                for (int cc = 0; cc < NKC / 4; ++cc) {
+                    const int c = h * (NKC / 2) + 2 * cc + p;
+                    float v[32];
+                    tmem_ld32(tV + uint32_t(c * 32) + lane_off, v);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&v_free[c]);            // the splitters may refill these columns
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(alpha + c * 32 + cq * 4));
+                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvec + c * 32 + cq * 4));
+                    // phase 1 (lane = sample row): V into the box, 16-byte chunk q of row r at chunk (q ^ (r & 7)): conflict-free both ways
 #pragma unroll
-            for (int c = 0; c < PF; ++c) load_x(c, xr[c]);
+                    for (int q = 0; q < 8; ++q)
+                        box[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    __syncwarp();
+                    // phase 2 (lane = column group)
 #pragma unroll
-            for (int c = 0; c < ND / 32; ++c) {
-                float v[32];
-                tmem_ld32(tmem_base + S::V_COL + uint32_t(c * 32) + lane_off, v);
-                const float4 a4 = __ldg(reinterpret_cast<const float4*>(alpha + c * 32 + cq * 4));
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvec + c * 32 + cq * 4));
-                // phase 1 (lane = sample row): -V into the box, 16-byte chunk q of row r at chunk (q ^ (r & 7)): conflict-free both ways
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    box[lane * 8 + (q ^ (lane & 7))] = make_float4(-v[4 * q], -v[4 * q + 1], -v[4 * q + 2], -v[4 * q + 3]);
-                __syncwarp();
-                // phase 2 (lane = column group)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = rq + 4 * i;
-                    const float4 b = box[r * 8 + (cq ^ (r & 7))];
-                    const float4 xv = xr[c % PF][i];
-                    const float4 o = make_float4(fmaf(a4.x, xv.x, c4.x) + b.x, fmaf(a4.y, xv.y, c4.y) + b.y,
-                                                 fmaf(a4.z, xv.z, c4.z) + b.z, fmaf(a4.w, xv.w, c4.w) + b.w);
-                    if (row0 + r < N) __stcs(reinterpret_cast<float4*>(ybase + int64_t(4 * i) * ND + c * 32), o);
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = rq + 4 * i;
+                        const float4 b = box[r * 8 + (cq ^ (r & 7))];
+                        const float4 o = make_float4(fmaf(a4.x, b.x, c4.x), fmaf(a4.y, b.y, c4.y), fmaf(a4.z, b.z, c4.z), fmaf(a4.w, b.w, c4.w));
+                        if (row0 + r < N) __stcs(reinterpret_cast<float4*>(ybase + int64_t(4 * i) * ND + c * 32), o);
+                    }
+                    __syncwarp();
                 }
-                if (c + PF < ND / 32) load_x(c + PF, xr[c % PF]);
-                __syncwarp();
             }
-            if (ladj != nullptr && row0 + lane < N) __stcs(ladj + row0 + lane, ladj_const);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(v_empty);
-            ++je;
+            if (p == 0 && ladj != nullptr && row0 + lane < N) __stcs(ladj + row0 + lane, ladj_const);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -391,9 +390,11 @@ int wy_rank(int dtype, int D, const ChainDesc& d) {
 
 size_t wy_buffer_floats(int D) { return size_t(4) * WY_KT * D + 2 * size_t(D); }
 
-// Fold the chain into y = alpha . x - U (W^T x) + c in float64 (one column of U, W per reflection) and lay the operands
-// out for the kernel: Wt hi | Wt lo ([64][D]) | U hi | U lo ([D][64]) | alpha [D] | c [D].
-void wy_fold(int D, int n_ops, const int* kinds, const int* Ks, const double* const* params, std::vector<float>& out) {
+// Fold the chain into y = alpha . x - U (W^T x) + c = alpha . (x + U' (W^T x)) + c in float64 (one column of U, W per
+// reflection; U' = -U / alpha row by row) and lay the operands out for the kernel:
+// Wt hi | Wt lo ([64][D]) | U' hi | U' lo ([D][64]) | alpha [D] | c [D].  False if a scale is zero (or so small that U' is
+// not finite in Float32): the caller then uses the dense fold.
+bool wy_fold(int D, int n_ops, const int* kinds, const int* Ks, const double* const* params, std::vector<float>& out) {
     std::vector<double> alpha(D, 1.0), c(D, 0.0), U, W;     // U, W: column-major D x kt
     int kt = 0;
     std::vector<double> vp(D), t;
@@ -438,19 +439,24 @@ void wy_fold(int D, int n_ops, const int* kinds, const int* Ks, const double* co
     float* ul = uh + size_t(D) * WY_KT;
     float* al = ul + size_t(D) * WY_KT;
     float* cc = al + D;
+    bool ok = true;
     for (int k = 0; k < kt && k < WY_KT; ++k)
         for (int i = 0; i < D; ++i) {
             split_tf32(W[size_t(k) * D + i], wth[size_t(k) * D + i], wtl[size_t(k) * D + i]);
-            split_tf32(U[size_t(k) * D + i], uh[size_t(i) * WY_KT + k], ul[size_t(i) * WY_KT + k]);
+            const double up = -U[size_t(k) * D + i] / alpha[i];
+            if (!(std::fabs(up) < 1e30)) ok = false;
+            split_tf32(ok ? up : 0.0, uh[size_t(i) * WY_KT + k], ul[size_t(i) * WY_KT + k]);
         }
     for (int i = 0; i < D; ++i) {
         al[i] = float(alpha[i]);
         cc[i] = float(c[i]);
     }
+    return ok;
 }
 
 cudaError_t launch_wy(int D, const float* d_wy, const void* x, void* y, void* ladj, int64_t N, double ladj_const,
                       int sm_count, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return cudaErrorInvalidValue;
     if (N <= 0) return cudaSuccess;
     const float* wth = d_wy;
     const float* wtl = wth + size_t(WY_KT) * D;
@@ -462,14 +468,13 @@ cudaError_t launch_wy(int D, const float* d_wy, const void* x, void* y, void* la
     if (!make_map(&mx, x, uint64_t(N), uint64_t(D), WY_TILE_M, WY_KC) ||
         !make_map(&mwh, wth, uint64_t(WY_KT), uint64_t(D), WY_KT, WY_KC) ||
         !make_map(&mwl, wtl, uint64_t(WY_KT), uint64_t(D), WY_KT, WY_KC) ||
-        !make_map(&muh, uh, uint64_t(D), uint64_t(WY_KT), uint32_t(D), 32) ||
-        !make_map(&mul, ul, uint64_t(D), uint64_t(WY_KT), uint32_t(D), 32))
+        !make_map(&muh, uh, uint64_t(D), uint64_t(WY_KT), uint32_t(D / 2), 32) ||
+        !make_map(&mul, ul, uint64_t(D), uint64_t(WY_KT), uint32_t(D / 2), 32))
         return cudaErrorInvalidValue;
     const int64_t tiles = (N + WY_TILE_M - 1) / WY_TILE_M;
     const unsigned grid = unsigned(tiles < sm_count ? tiles : sm_count);
     const float lc = float(ladj_const);
     float* lf = static_cast<float*>(ladj);
-    const float* xf = static_cast<const float*>(x);
     float* yf = static_cast<float*>(y);
     cudaError_t e = cudaSuccess;
 #define ENF_WY_LAUNCH(ND)                                                                                              \
@@ -483,7 +488,7 @@ cudaError_t launch_wy(int D, const float* d_wy, const void* x, void* y, void* la
             if (e != cudaSuccess) return e;                                                                            \
             set[dev & 63] = true;                                                                                      \
         }                                                                                                              \
-        wy_gemm_kernel<ND><<<grid, WY_THREADS, smem, st>>>(mx, mwh, mwl, muh, mul, xf, yf, al, cc, lf, lc, N);         \
+        wy_gemm_kernel<ND><<<grid, WY_THREADS, smem, st>>>(mx, mwh, mwl, muh, mul, yf, al, cc, lf, lc, N);             \
     }
     if (D == 256) ENF_WY_LAUNCH(256)
     else if (D == 128) ENF_WY_LAUNCH(128)
