@@ -486,13 +486,25 @@ def main():
                 E.with_logabsdet_jacobian(f4, X4, out=(Y4, L4))
             ctx.record(5)
             c4_ms = max_over_ranks(ctx.elapsed_ms(4, 5) / 3)
-            flops = 3 * 2 * 256 * 256                      # issued TF32 flops per sample (3xTF32, dense folded map)
+            # issued TF32 flops per sample, compact WY (enf_wy.cu): T = x W  3 x 2.256.64, V += T U'  3 x 2.64.256
+            flops = 3 * 2 * 256 * 64 * 2
+            os.environ["ENF_NO_WY"] = "1"                  # the dense fold y = W x + c (enf_affine.cu) on the same chain, for comparison
+            E.with_logabsdet_jacobian(f4, X4, out=(Y4, L4))
+            ctx.record(6)
+            for _ in range(3):
+                E.with_logabsdet_jacobian(f4, X4, out=(Y4, L4))
+            ctx.record(7)
+            dense_ms = max_over_ranks(ctx.elapsed_ms(6, 7) / 3)
+            del os.environ["ENF_NO_WY"]
             extras["c4_d256_k64_tensor"] = {"samples_per_s": n4 * world / (c4_ms * 1e-3), "ms_per_pass": c4_ms, "samples_per_gpu": n4,
                                             "hbm_frac": (2 * 256 + 1) * 4 * n4 / (c4_ms * 1e-3) / 1e9 / hbm_peak,
                                             "tf32_tflops_issued": flops * n4 / (c4_ms * 1e-3) / 1e12,
                                             "tensor_frac": flops * n4 / (c4_ms * 1e-3) / 1e12 / tensor_peak_tf32()[0],
                                             "tensor_peak": {"tflops": tensor_peak_tf32()[0], "source": tensor_peak_tf32()[1]},
-                                            "path": "tcgen05.mma kind::tf32, 3xTF32 split, y = W x + c folded on the host"}
+                                            "path": "compact WY, two chained tcgen05.mma kind::tf32 GEMMs per 128-sample tile (3xTF32), "
+                                                    "y = alpha.(x + U'(W^T x)) + c with the tile held in tensor memory",
+                                            "dense_fold_ms_per_pass": dense_ms,
+                                            "dense_fold_hbm_frac": (2 * 256 + 1) * 4 * n4 / (dense_ms * 1e-3) / 1e9 / hbm_peak}
 
             # C4 gradient: loss + dV, da, db of the same chain from tensor-core second moments
             # (enf_moments.cu: S = X X^T with the samples as the contraction dimension) + cluster chain-rule kernel

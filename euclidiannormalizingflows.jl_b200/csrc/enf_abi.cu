@@ -954,10 +954,11 @@ extern "C" int enf_chain_describe(const enf_chain* ch, char* buf, size_t buflen)
     select_kernels(ch->dtype, ch->plan, mode, ks);
     snprintf(buf, buflen,
              "dtype=%s D=%d Dp=%d layout=%s lanes_per_sample=%d vectors_per_lane=%d ops=%d consts=%d "
-             "fwd_smem=%zu grad_smem=%zu n_raw=%d",
+             "fwd_smem=%zu grad_smem=%zu n_raw=%d forward=%s",
              ch->dtype == ENF_F32 ? "f32" : "f64", ch->D, ch->desc.Dp, ch->plan.packed ? "packed" : "lane-group",
              1 << ch->plan.LG, ch->plan.CH, ch->desc.n_ops, ch->desc.n_consts, fwd_smem_bytes(ch->dtype, ch->desc),
-             grad_smem_bytes(ch->dtype, ch->desc, ks, true), ch->n_raw);
+             grad_smem_bytes(ch->dtype, ch->desc, ks, true), ch->n_raw,
+             !ch->affine ? "simt" : (ch->wy && getenv("ENF_NO_WY") == nullptr) ? "tcgen05-compact-wy" : "tcgen05-dense-fold");
     return ENF_OK;
 }
 
@@ -975,7 +976,7 @@ static int forward_impl(enf_chain* ch, const void* x, int64_t N, void* y, void* 
         // Householder / ScaleShift stack at large D: one tcgen05 GEMM per tile (enf_affine.cu)
         int rca = ensure_affine(ch);
         if (rca != ENF_OK) return rca;
-        static const bool no_wy = getenv("ENF_NO_WY") != nullptr;      // cross-check: dense fold instead of compact WY
+        const bool no_wy = getenv("ENF_NO_WY") != nullptr;             // cross-check: dense fold instead of compact WY
         if (ch->wy && ch->wy_valid && !no_wy)
             CU(ctx, launch_wy(ch->D, ch->d_wy, x, y, want_ladj ? ladj : nullptr, N, lc, ctx->sm_count, st));
         else

@@ -36,6 +36,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -61,14 +62,17 @@ struct WySmem {
     static constexpr int HALF = ND / 2;                             // output columns per GEMM2 pass
     static constexpr int X_BYTES = WY_TILE_M * WY_KC * 4;           // 16 KB
     static constexpr int W_BYTES = WY_KT * WY_KC * 4;               // 8 KB
-    static constexpr int STAGE_BYTES = X_BYTES + 2 * W_BYTES;       // x -> xl | Wh | Wl = 32 KB
     static constexpr int U_PIECE_BYTES = HALF * 32 * 4;             // one piece of U': [HALF rows x 32 k], 128B swizzle
-    static constexpr int RING_OFF = WY_UBUFS * U_PIECE_BYTES;
+    static constexpr int XRING_OFF = WY_UBUFS * U_PIECE_BYTES;      // x chunks: a slot is free again once the splitters have read it
+    static constexpr int WRING_OFF = XRING_OFF + WY_STAGES * X_BYTES;   // Wh | Wl chunks: free once GEMM1 of the chunk has retired
     static constexpr int OUT_BYTES = 32 * 32 * 4;
-    static constexpr int OUT_OFF = RING_OFF + WY_STAGES * STAGE_BYTES;
-    static constexpr int BAR_OFF = OUT_OFF + WY_EPI_WARPS * OUT_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 512 + 1024;
-    static constexpr uint32_t T_COL = 0, T_BUF_COLS = 128, TC_OFF = 64, V_COL = 256;
+    static constexpr int OUT_OFF = WRING_OFF + WY_STAGES * 2 * W_BYTES;
+    static constexpr int AC_OFF = OUT_OFF + WY_EPI_WARPS * OUT_BYTES;   // alpha | c (2 ND floats)
+    static constexpr int BAR_OFF = AC_OFF + 2 * ND * 4;
+    static constexpr int TOTAL = BAR_OFF + 512;                     // the dynamic window starts 1024-byte aligned (checked)
+    // tensor memory: T (main | correction accumulators, rewritten in place as Thi | Tlo by the hand-off), a window of
+    // WY_STAGES 32-column chunks of xl (the A operand of the correction product), V
+    static constexpr uint32_t T_COL = 0, TC_OFF = 64, XL_COL = 128, V_COL = 256;
     static constexpr uint32_t TMEM_COLS = 512;
 };
 
@@ -92,27 +96,36 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
+#ifdef ENF_WY_TRACE   // tuning aid (tools/build_variant.sh): clock64() of the hand-shakes of CTA 0 for tiles 100-103
+__device__ long long wy_trace_buf[7 * 4 * 16];
+#define WY_T(role, j, ev)                                                                \
+    if (blockIdx.x == 0 && lane == 0 && (j) >= 100 && (j) < 104) wy_trace_buf[((role) * 4 + ((j) - 100)) * 16 + (ev)] = clock64();
+#else
+#define WY_T(role, j, ev)
+#endif
+
 template <int ND>
 __global__ void __launch_bounds__(WY_THREADS, 1)
 wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wh,
                const __grid_constant__ CUtensorMap map_wl, const __grid_constant__ CUtensorMap map_uh,
-               const __grid_constant__ CUtensorMap map_ul,
-               float* __restrict__ y, const float* __restrict__ alpha,
+               const __grid_constant__ CUtensorMap map_ul, const __grid_constant__ CUtensorMap map_y,
+               const float* __restrict__ alpha,
                const float* __restrict__ cvec, float* __restrict__ ladj, float ladj_const, int64_t N) {
     using S = WySmem<ND>;
     constexpr int NKC = ND / WY_KC;                    // ring chunks per tile = 32-column chunks of V
     constexpr int HALF = S::HALF;
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // TMA landed                     (1 + tx)
-    uint64_t* split = full + WY_STAGES;                                // x in V, xl written             (4 warps)
-    uint64_t* empty = split + WY_STAGES;                               // MMAs of the stage retired      (tcgen05.commit)
+    extern __shared__ __align__(1024) unsigned char smem[];       // no static shared memory in this kernel: offset 0 of the window
+    if (smem_u32(smem) & 1023u) __trap();
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF); // x chunk landed                 (1 + tx)
+    uint64_t* w_full = x_full + WY_STAGES;                             // Wh | Wl chunk landed           (1 + tx)
+    uint64_t* split = w_full + WY_STAGES;                              // x in V, xl in the TMEM window  (4 warps)
+    uint64_t* empty = split + WY_STAGES;                               // MMAs of the chunk retired      (tcgen05.commit)
     uint64_t* u_full = empty + WY_STAGES;                              // a piece of U' landed           (1 + tx)
     uint64_t* u_empty = u_full + WY_UBUFS;                             // its MMAs retired               (tcgen05.commit)
-    uint64_t* t_full = u_empty + WY_UBUFS;                             // [2] GEMM1 of a tile retired    (tcgen05.commit)
-    uint64_t* t_split = t_full + 2;                                    // [2] Thi / Tlo written          (8 warps)
-    uint64_t* t_free = t_split + 2;                                    // [2] GEMM2 has read Thi / Tlo   (tcgen05.commit)
-    uint64_t* v_full = t_free + 2;                                     // [2] a column half of V is final (tcgen05.commit)
+    uint64_t* t_full = u_empty + WY_UBUFS;                             // GEMM1 of a tile retired        (tcgen05.commit)
+    uint64_t* t_split = t_full + 1;                                    // Thi / Tlo written              (8 warps)
+    uint64_t* t_free = t_split + 1;                                    // GEMM2 has read Thi / Tlo       (tcgen05.commit)
+    uint64_t* v_full = t_free + 1;                                     // [2] a column half of V is final (tcgen05.commit)
     uint64_t* v_free = v_full + 2;                                     // [NKC] a chunk of V is drained  (4 warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_free + NKC);
 
@@ -122,7 +135,8 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < WY_STAGES; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&x_full[s], 1);
+            mbar_init(&w_full[s], 1);
             mbar_init(&split[s], WY_SPLIT_WARPS);
             mbar_init(&empty[s], 1);
         }
@@ -130,17 +144,21 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             mbar_init(&u_full[b], 1);
             mbar_init(&u_empty[b], 1);
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&t_full[b], 1);
-            mbar_init(&t_split[b], WY_EPI_WARPS);
-            mbar_init(&t_free[b], 1);
-            mbar_init(&v_full[b], 1);
-        }
+        mbar_init(t_full, 1);
+        mbar_init(t_split, WY_EPI_WARPS);
+        mbar_init(t_free, 1);
+        mbar_init(&v_full[0], 1);
+        mbar_init(&v_full[1], 1);
         for (int c = 0; c < NKC; ++c) mbar_init(&v_free[c], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
+    float* s_ac = reinterpret_cast<float*>(smem + S::AC_OFF);
+    for (int i = threadIdx.x; i < ND; i += WY_THREADS) {
+        s_ac[i] = alpha[i];
+        s_ac[ND + i] = cvec[i];
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -148,78 +166,74 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t tV = tmem_base + S::V_COL;
 
     if (warp == 0) {
-        // ===== TMA producer: x and W chunks =====
+        // ===== TMA producer of the x chunks: runs up to WY_STAGES chunks ahead of the splitters =====
         if (lane == 0) {
             uint32_t it = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int64_t tile = int64_t(blockIdx.x) + int64_t(i) * gridDim.x;
                 for (int kc = 0; kc < NKC; ++kc, ++it) {
                     const int s = it % WY_STAGES;
-                    if (it >= uint32_t(WY_STAGES)) mbar_wait(&empty[s], ((it / WY_STAGES) - 1) & 1);
-                    unsigned char* st = smem + S::RING_OFF + size_t(s) * S::STAGE_BYTES;
-                    mbar_expect_tx(&full[s], S::X_BYTES + 2 * S::W_BYTES);
-                    tma_load_2d_hint(st, &map_x, kc * WY_KC, int(tile * WY_TILE_M), &full[s], L2_EVICT_FIRST);   // x chunk [128 x 32]
-                    tma_load_2d_hint(st + S::X_BYTES, &map_wh, kc * WY_KC, 0, &full[s], L2_EVICT_LAST);          // Wh chunk [64 x 32]
-                    tma_load_2d_hint(st + S::X_BYTES + S::W_BYTES, &map_wl, kc * WY_KC, 0, &full[s], L2_EVICT_LAST);
+                    if (it >= uint32_t(WY_STAGES)) mbar_wait(&split[s], ((it / WY_STAGES) - 1) & 1);
+                    WY_T(4, i, kc)
+                    mbar_expect_tx(&x_full[s], S::X_BYTES);
+                    tma_load_2d_hint(smem + S::XRING_OFF + s * S::X_BYTES, &map_x, kc * WY_KC, int(tile * WY_TILE_M), &x_full[s], L2_EVICT_FIRST);
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== GEMM1 issuer: T(i) = X(i) W into a (main | correction) accumulator pair =====
+        // ===== GEMM1 issuer: T(i) = X(i) W into the (main | correction) accumulator pair.  ONE thread runs the whole loop: the
+        // tensor core's instruction queue is shallow (tools/mma_rate.cu: every cycle the issuing thread spends on barriers,
+        // re-convergence or commits between two MMAs is a cycle the tensor pipe idles), so the loop carries nothing warp-wide =====
         constexpr uint32_t idesc_n128 = make_idesc_tf32(WY_TILE_M, 2 * WY_KT);
         constexpr uint32_t idesc_n64 = make_idesc_tf32(WY_TILE_M, WY_KT);
-        uint32_t it = 0;
-        for (int i = 0; i < my_tiles; ++i) {
-            const uint32_t buf = uint32_t(i) & 1u;
-            if (i >= 2) mbar_wait(&t_free[buf], uint32_t((i >> 1) - 1) & 1u);          // GEMM2 of tile i-2 has read this buffer
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tM = tmem_base + S::T_COL + buf * S::T_BUF_COLS, tC = tM + S::TC_OFF;
-            for (int kc = 0; kc < NKC; ++kc, ++it) {
-                const int s = it % WY_STAGES;
-                const uint32_t ph = (it / WY_STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                mbar_wait(&split[s], ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    unsigned char* st = smem + S::RING_OFF + size_t(s) * S::STAGE_BYTES;
-                    const uint64_t dxl = make_desc_kmajor<WY_KC>(st);
-                    const uint64_t dw = make_desc_kmajor<WY_KC>(st + S::X_BYTES);      // rows 0-63 Wh, rows 64-127 Wl
+        const uint32_t tM = tmem_base + S::T_COL, tC = tM + S::TC_OFF;
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                if (i >= 1) mbar_wait(t_free, uint32_t(i - 1) & 1u);                   // GEMM2 of tile i-1 has read Thi | Tlo
+                for (int kc = 0; kc < NKC; ++kc, ++it) {
+                    const int s = it % WY_STAGES;
+                    mbar_wait(&w_full[s], (it / WY_STAGES) & 1);
+                    mbar_wait(&split[s], (it / WY_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    WY_T(0, i, kc)
+                    const uint64_t dw = make_desc_kmajor<WY_KC>(smem + S::WRING_OFF + s * 2 * S::W_BYTES);   // rows 0-63 Wh, 64-127 Wl
+                    const uint32_t tX = tV + uint32_t(kc * WY_KC), tXL = tmem_base + S::XL_COL + uint32_t(s * WY_KC);
 #pragma unroll
                     for (int j = 0; j < WY_KC / 8; ++j) {          // UMMA K = 8 tf32 = 32 bytes inside the swizzle atom
                         const uint64_t adv = uint64_t((j * 32) >> 4);
                         // (main | correction) (+)= trunc(x) . [Wh | Wl]: A = the chunk's columns of V.  The tensor core truncates
                         // when it adds into the f32 accumulator, one ulp of the ACCUMULATOR per MMA whatever the size of the
                         // addend: the 2^-11-small correction products have an accumulator of their own.
-                        umma_tf32_ts(tM, tV + uint32_t(kc * WY_KC + j * 8), dw + adv, idesc_n128, (kc | j) != 0);
-                        umma_tf32(tC, dxl + adv, dw + adv, idesc_n64, 1);              // correction += xl . Wh
+                        umma_tf32_ts(tM, tX + uint32_t(j * 8), dw + adv, idesc_n128, (kc | j) != 0);
+                        umma_tf32_ts(tC, tXL + uint32_t(j * 8), dw + adv, idesc_n64, 1);       // correction += xl . Wh
                     }
                     umma_commit(&empty[s]);
-                    if (kc == NKC - 1) umma_commit(&t_full[buf]);
+                    if (kc == NKC - 1) umma_commit(t_full);
                 }
-                __syncwarp();
             }
         }
     } else if (warp == 15) {
-        // ===== GEMM2 issuer: V(j) += T(j) U'^T, A = Thi | Tlo in tensor memory, B = the streamed pieces of U' =====
+        // ===== GEMM2 issuer (one thread, see GEMM1): V(j) += T(j) U'^T, A = Thi | Tlo in tensor memory, B = the pieces of U' =====
         constexpr uint32_t idesc2 = make_idesc_tf32(WY_TILE_M, HALF);
-        uint32_t q = 0;
-        for (int j = 0; j < my_tiles; ++j) {
-            const uint32_t buf = uint32_t(j) & 1u;
-            mbar_wait(&t_split[buf], uint32_t(j >> 1) & 1u);                           // Thi / Tlo of tile j are in TMEM
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tHI = tmem_base + S::T_COL + buf * S::T_BUF_COLS, tLO = tHI + S::TC_OFF;
+        const uint32_t tHI = tmem_base + S::T_COL, tLO = tHI + S::TC_OFF;
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (int j = 0; j < my_tiles; ++j) {
+                mbar_wait(t_split, uint32_t(j) & 1u);                                  // Thi / Tlo of tile j are in TMEM
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                WY_T(3, j, 0)
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                // pieces of a half: U'l k0, U'l k1 (correction Thi . U'l), U'h k0, U'h k1 (Tlo . U'h and the main product)
-#pragma unroll 1
-                for (int pc = 0; pc < 4; ++pc, ++q) {
-                    const uint32_t b = q % WY_UBUFS;
-                    mbar_wait(&u_full[b], (q / WY_UBUFS) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (lane == 0) {
+                for (int h = 0; h < 2; ++h) {
+                    // pieces of a half: U'l k0, U'l k1 (correction Thi . U'l), U'h k0, U'h k1 (Tlo . U'h and the main product)
+                    const uint32_t tD = tV + uint32_t(h * HALF);
+#pragma unroll
+                    for (int pc = 0; pc < 4; ++pc, ++q) {
+                        const uint32_t b = q % WY_UBUFS;
+                        mbar_wait(&u_full[b], (q / WY_UBUFS) & 1u);
+                        WY_T(3, j, 1 + 4 * h + pc)
                         const uint64_t du = make_desc_kmajor<32>(smem + b * S::U_PIECE_BYTES);
                         const uint32_t k0 = uint32_t(pc & 1) * 32u;                    // first T column of this piece
-                        const uint32_t tD = tV + uint32_t(h * HALF);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             const uint64_t adv = uint64_t((kk * 32) >> 4);
@@ -227,24 +241,40 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             umma_tf32_ts(tD, tHI + k0 + uint32_t(kk * 8), du + adv, idesc2, 1);
                         }
                         umma_commit(&u_empty[b]);
-                        if (pc == 3) {
-                            umma_commit(&v_full[h]);
-                            if (h == 1) umma_commit(&t_free[buf]);
-                        }
                     }
-                    __syncwarp();
+                    umma_commit(&v_full[h]);
                 }
+                umma_commit(t_free);
             }
         }
     } else if (warp == 14) {
-        // ===== producer of the U' pieces: per tile and column half U'l k0, U'l k1, U'h k0, U'h k1 =====
+        // ===== TMA producer of the W chunks and of the U' pieces (both come from L2): one thread polls both queues, neither
+        // may wait behind the other.  Per tile and column half the pieces are U'l k0, U'l k1, U'h k0, U'h k1 =====
         if (lane == 0) {
-            for (uint32_t q = 0; q < uint32_t(8 * my_tiles); ++q) {
-                const uint32_t b = q % WY_UBUFS, pc = q & 3u, h = (q >> 2) & 1u;
-                if (q >= uint32_t(WY_UBUFS)) mbar_wait(&u_empty[b], ((q / WY_UBUFS) - 1) & 1u);
-                mbar_expect_tx(&u_full[b], S::U_PIECE_BYTES);
-                tma_load_2d_hint(smem + b * S::U_PIECE_BYTES, pc < 2 ? &map_ul : &map_uh, int(pc & 1u) * 32, int(h) * HALF, &u_full[b],
-                                 L2_EVICT_LAST);
+            const uint32_t n_w = uint32_t(my_tiles) * NKC, n_u = uint32_t(my_tiles) * 8u;
+            uint32_t wq = 0, uq = 0;
+            while (wq < n_w || uq < n_u) {
+                if (wq < n_w) {
+                    const uint32_t s = wq % WY_STAGES;
+                    if (wq < uint32_t(WY_STAGES) || mbar_test(&empty[s], ((wq / WY_STAGES) - 1) & 1u)) {
+                        const int kc = int(wq % NKC);
+                        unsigned char* dst = smem + S::WRING_OFF + s * 2 * S::W_BYTES;
+                        mbar_expect_tx(&w_full[s], 2 * S::W_BYTES);
+                        tma_load_2d_hint(dst, &map_wh, kc * WY_KC, 0, &w_full[s], L2_EVICT_LAST);              // Wh chunk [64 x 32]
+                        tma_load_2d_hint(dst + S::W_BYTES, &map_wl, kc * WY_KC, 0, &w_full[s], L2_EVICT_LAST);
+                        ++wq;
+                    }
+                }
+                if (uq < n_u) {
+                    const uint32_t b = uq % WY_UBUFS, pc = uq & 3u, h = (uq >> 2) & 1u;
+                    if (uq < uint32_t(WY_UBUFS) || mbar_test(&u_empty[b], ((uq / WY_UBUFS) - 1) & 1u)) {
+                        WY_T(5, int(uq >> 3), int(uq & 7u))
+                        mbar_expect_tx(&u_full[b], S::U_PIECE_BYTES);
+                        tma_load_2d_hint(smem + b * S::U_PIECE_BYTES, pc < 2 ? &map_ul : &map_uh, int(pc & 1u) * 32, int(h) * HALF, &u_full[b],
+                                         L2_EVICT_LAST);
+                        ++uq;
+                    }
+                }
             }
         }
     } else if (warp < 2 + WY_SPLIT_WARPS) {
@@ -256,11 +286,13 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int i = 0; i < my_tiles; ++i) {
             for (int kc = 0; kc < NKC; ++kc, ++it) {
                 const int s = it % WY_STAGES;
-                mbar_wait(&full[s], (it / WY_STAGES) & 1);
+                mbar_wait(&x_full[s], (it / WY_STAGES) & 1);
+                if (warp == 2) { WY_T(1, i, kc) }
+                if (it >= uint32_t(WY_STAGES)) mbar_wait(&empty[s], ((it / WY_STAGES) - 1) & 1);   // the xl window slot is free
                 if (i >= 1) mbar_wait(&v_free[kc], uint32_t(i - 1) & 1u);      // the epilogue of tile i-1 has drained these columns
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // 16-byte chunk q of row r sits at chunk q ^ (r & 7) of the row (TMA 128-byte swizzle): conflict-free LDS.128
-                uint4* xs = reinterpret_cast<uint4*>(smem + S::RING_OFF + size_t(s) * S::STAGE_BYTES) + row * 8;
+                const uint4* xs = reinterpret_cast<const uint4*>(smem + S::XRING_OFF + s * S::X_BYTES) + row * 8;
                 uint32_t xv[32];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -269,19 +301,14 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 }
                 tmem_st32(tV + uint32_t(kc * WY_KC) + lane_off, xv);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    uint4 o;
-                    o.x = __float_as_uint(tf32_hi(__uint_as_float(xv[4 * q]) - __uint_as_float(xv[4 * q] & 0xFFFFE000u)));
-                    o.y = __float_as_uint(tf32_hi(__uint_as_float(xv[4 * q + 1]) - __uint_as_float(xv[4 * q + 1] & 0xFFFFE000u)));
-                    o.z = __float_as_uint(tf32_hi(__uint_as_float(xv[4 * q + 2]) - __uint_as_float(xv[4 * q + 2] & 0xFFFFE000u)));
-                    o.w = __float_as_uint(tf32_hi(__uint_as_float(xv[4 * q + 3]) - __uint_as_float(xv[4 * q + 3] & 0xFFFFE000u)));
-                    xs[q ^ (row & 7)] = o;
-                }
+                for (int e = 0; e < 32; ++e)
+                    xv[e] = __float_as_uint(tf32_hi(__uint_as_float(xv[e]) - __uint_as_float(xv[e] & 0xFFFFE000u)));
+                tmem_st32(tmem_base + S::XL_COL + uint32_t(s * WY_KC) + lane_off, xv);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&split[s]);
+                if (warp == 2) { WY_T(1, i, 8 + kc) }
             }
         }
     } else {
@@ -292,14 +319,13 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int p = ew >> 2;
         float4* box = reinterpret_cast<float4*>(smem + S::OUT_OFF + size_t(ew) * S::OUT_BYTES);
         const uint32_t lane_off = uint32_t(quarter * 32) << 16;
-        const int rq = lane >> 3, cq = lane & 7;                       // epilogue phase 2: rows rq + 4 i, 16-byte chunk cq
         for (int j = 0; j < my_tiles; ++j) {
             {
                 // ---- hand-off: this warp's 32 rows x 32 columns of T(j): main + correction, split into tf32 high / low parts
-                const uint32_t buf = uint32_t(j) & 1u;
-                mbar_wait(&t_full[buf], uint32_t(j >> 1) & 1u);
+                mbar_wait(t_full, uint32_t(j) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t tM = tmem_base + S::T_COL + buf * S::T_BUF_COLS + uint32_t(p * 32) + lane_off, tC = tM + S::TC_OFF;
+                if (warp == 6) { WY_T(2, j, 0) }
+                const uint32_t tM = tmem_base + S::T_COL + uint32_t(p * 32) + lane_off, tC = tM + S::TC_OFF;
                 float v[32], w[32];
                 tmem_ld32(tM, v);
                 tmem_ld32(tC, w);
@@ -316,46 +342,54 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&t_split[buf]);
+                if (lane == 0) mbar_arrive(t_split);
+                if (warp == 6) { WY_T(2, j, 1) }
             }
-            // ---- epilogue of tile j.  TMEM hands a lane one SAMPLE (32 columns of it); global memory wants a lane to own
-            // COLUMNS.  A 4 KB shared-memory box does the transpose: V goes in by rows, then every lane scales the 16-byte
-            // chunks of ITS column group (8 lanes cover one 128-byte row segment: coalesced stores of y, 4 rows per instruction).
+            // ---- epilogue of tile j.  TMEM hands a lane one SAMPLE (32 columns of it): y = alpha V + c goes row by row into a
+            // 4 KB staging box in the tensor map's 128-byte swizzle (conflict-free STS.128), and one bulk tensor store per box
+            // writes full 128-byte row segments (rows beyond N are clipped by the tensor map).
             const int64_t tile = int64_t(blockIdx.x) + int64_t(j) * gridDim.x;
             const int64_t row0 = tile * WY_TILE_M + quarter * 32;      // this warp's 32 samples
-            float* ybase = y + (row0 + rq) * int64_t(ND) + cq * 4;
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 mbar_wait(&v_full[h], uint32_t(j) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
+                if (warp == 6) { WY_T(2, j, 2 + 4 * h) }
+#pragma unroll 1
                 for (int cc = 0; cc < NKC / 4; ++cc) {
                     const int c = h * (NKC / 2) + 2 * cc + p;
                     float v[32];
                     tmem_ld32(tV + uint32_t(c * 32) + lane_off, v);
+                    if (warp == 6) { WY_T(2, j, 3 + 4 * h + cc) }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&v_free[c]);            // the splitters may refill these columns
-                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(alpha + c * 32 + cq * 4));
-                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvec + c * 32 + cq * 4));
-                    // phase 1 (lane = sample row): V into the box, 16-byte chunk q of row r at chunk (q ^ (r & 7)): conflict-free both ways
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        box[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    __syncwarp();
-                    // phase 2 (lane = column group)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = rq + 4 * i;
-                        const float4 b = box[r * 8 + (cq ^ (r & 7))];
-                        const float4 o = make_float4(fmaf(a4.x, b.x, c4.x), fmaf(a4.y, b.y, c4.y), fmaf(a4.z, b.z, c4.z), fmaf(a4.w, b.w, c4.w));
-                        if (row0 + r < N) __stcs(reinterpret_cast<float4*>(ybase + int64_t(4 * i) * ND + c * 32), o);
+                    if (warp == 6 && cc == 0) { WY_T(6, j, h * 8 + 0) }
+                    if (lane == 0) {
+                        mbar_arrive(&v_free[c]);                       // the splitters may refill these columns
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the box
                     }
                     __syncwarp();
+                    if (warp == 6 && cc == 0) { WY_T(6, j, h * 8 + 1) }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(s_ac + c * 32 + q * 4);          // broadcast LDS.128
+                        const float4 c4 = *reinterpret_cast<const float4*>(s_ac + ND + c * 32 + q * 4);
+                        box[lane * 8 + (q ^ (lane & 7))] = make_float4(fmaf(a4.x, v[4 * q], c4.x), fmaf(a4.y, v[4 * q + 1], c4.y),
+                                                                       fmaf(a4.z, v[4 * q + 2], c4.z), fmaf(a4.w, v[4 * q + 3], c4.w));
+                    }
+                    if (warp == 6 && cc == 0) { WY_T(6, j, h * 8 + 2) }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (warp == 6 && cc == 0) { WY_T(6, j, h * 8 + 3) }
+                    if (lane == 0) {
+                        tma_store_2d(&map_y, box, c * 32, int(row0));
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (warp == 6 && cc == 0) { WY_T(6, j, h * 8 + 4) }
                 }
             }
             if (p == 0 && ladj != nullptr && row0 + lane < N) __stcs(ladj + row0 + lane, ladj_const);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -378,7 +412,10 @@ void split_tf32(double v, float& h, float& l) {
 
 // total number of reflections of a Householder/ScaleShift-only chain if the compact-WY kernel applies, else 0
 int wy_rank(int dtype, int D, const ChainDesc& d) {
-    if (dtype != 0 || !(D == 128 || D == 256)) return 0;
+    // D = 128 is instantiated and correct, but measured level with the dense fold there (0.72 vs 0.75 of HBM peak: a 64 KB
+    // tile does not amortise the per-tile hand-shakes); D = 256: 0.73 vs 0.50
+    static const bool wy128 = getenv("ENF_WY_D128") != nullptr;
+    if (dtype != 0 || !(D == 256 || (D == 128 && wy128))) return 0;
     int n_refl = 0;
     for (int o = 0; o < d.n_ops; ++o) {
         if (d.ops[o].kind != OP_HH && d.ops[o].kind != OP_SS) return 0;
@@ -464,8 +501,8 @@ cudaError_t launch_wy(int D, const float* d_wy, const void* x, void* y, void* la
     const float* ul = uh + size_t(D) * WY_KT;
     const float* al = ul + size_t(D) * WY_KT;
     const float* cc = al + D;
-    CUtensorMap mx, mwh, mwl, muh, mul;
-    if (!make_map(&mx, x, uint64_t(N), uint64_t(D), WY_TILE_M, WY_KC) ||
+    CUtensorMap mx, mwh, mwl, muh, mul, my;
+    if (!make_map(&mx, x, uint64_t(N), uint64_t(D), WY_TILE_M, WY_KC) || !make_map(&my, y, uint64_t(N), uint64_t(D), 32, 32) ||
         !make_map(&mwh, wth, uint64_t(WY_KT), uint64_t(D), WY_KT, WY_KC) ||
         !make_map(&mwl, wtl, uint64_t(WY_KT), uint64_t(D), WY_KT, WY_KC) ||
         !make_map(&muh, uh, uint64_t(D), uint64_t(WY_KT), uint32_t(D / 2), 32) ||
@@ -475,7 +512,6 @@ cudaError_t launch_wy(int D, const float* d_wy, const void* x, void* y, void* la
     const unsigned grid = unsigned(tiles < sm_count ? tiles : sm_count);
     const float lc = float(ladj_const);
     float* lf = static_cast<float*>(ladj);
-    float* yf = static_cast<float*>(y);
     cudaError_t e = cudaSuccess;
 #define ENF_WY_LAUNCH(ND)                                                                                              \
     {                                                                                                                  \
@@ -488,12 +524,28 @@ cudaError_t launch_wy(int D, const float* d_wy, const void* x, void* y, void* la
             if (e != cudaSuccess) return e;                                                                            \
             set[dev & 63] = true;                                                                                      \
         }                                                                                                              \
-        wy_gemm_kernel<ND><<<grid, WY_THREADS, smem, st>>>(mx, mwh, mwl, muh, mul, yf, al, cc, lf, lc, N);             \
+        wy_gemm_kernel<ND><<<grid, WY_THREADS, smem, st>>>(mx, mwh, mwl, muh, mul, my, al, cc, lf, lc, N);             \
     }
     if (D == 256) ENF_WY_LAUNCH(256)
     else if (D == 128) ENF_WY_LAUNCH(128)
     else return cudaErrorInvalidValue;
 #undef ENF_WY_LAUNCH
+#ifdef ENF_WY_TRACE
+    {
+        static long long h[7 * 4 * 16];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, wy_trace_buf, sizeof(h));
+        long long t0 = 0;
+        for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+        const char* names[7] = {"gemm1 issue  ", "split (w2)   ", "epilogue (w6)", "gemm2 issue  ", "x producer   ", "u producer   ", "epi detail   "};
+        for (int j = 0; j < 4; ++j)
+            for (int r = 0; r < 7; ++r) {
+                fprintf(stderr, "tile %d %s", 100 + j, names[r]);
+                for (int e = 0; e < 16; ++e) fprintf(stderr, " %6lld", h[(r * 4 + j) * 16 + e] ? h[(r * 4 + j) * 16 + e] - t0 : -1);
+                fprintf(stderr, "\n");
+            }
+    }
+#endif
     return cudaGetLastError();
 }
 

@@ -8,6 +8,8 @@ the float32-rounded inputs and parameters (the reference's own Float32 path
 rounds differently from any other implementation in the last bits; the float64
 values are what both approximate).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -276,14 +278,20 @@ def test_against_committed_golden_fixtures(ctx, dtype, name):
     (["ss", "hh32"], 128, 5000),
     (["hh8"], 64, 127),
     (["hh16", "ss", "hh16"], 128, 2049),
+    (["ss", "hh9", "ss"], 256, 100001),   # compact WY with zero-padded reflections, ScaleShift on both sides, ragged last tile
+    (["hh33", "hh31"], 256, 40000),       # two stacks = 64 reflections, no ScaleShift
 ])
 def test_affine_chains_on_tensor_cores(ctx, spec, D, N):
-    """Householder/ScaleShift-only chains at D = 64/128/256 run as one tcgen05 (3xTF32) GEMM per tile
-    (enf_affine.cu): Float32 tolerance, forward and inverse, and agreement with the SIMT kernel, which
-    unaligned column views still use."""
+    """Householder/ScaleShift-only chains at D = 64/128/256 run on the tensor cores: at D = 256 with up to 64
+    reflections in compact-WY form as two chained tcgen05 (3xTF32) GEMMs per tile (enf_wy.cu), otherwise as one GEMM
+    with the dense folded map (enf_affine.cu).  Float32 tolerance, forward and inverse, and agreement with the SIMT
+    kernel, which unaligned column views still use."""
     import enf_b200 as E
     dtype = np.float32
     fo, fe = both(spec, D, 31, dtype)
+    n_refl = sum(int(c[2:]) for c in spec if c.startswith("hh"))
+    path = E.get_chain(fe, D, dtype, ctx).describe().split("forward=")[1]
+    assert path == ("tcgen05-compact-wy" if D == 256 and 8 <= n_refl <= 64 else "tcgen05-dense-fold"), path
     X = _data(D, N + 1, 32, dtype, spread=1.0)
     Xd = E.B200Matrix.from_host(X, ctx)
     y_ref, l_ref = O.with_logabsdet_jacobian(fo, X.astype(np.float64))
@@ -294,6 +302,38 @@ def test_affine_chains_on_tensor_cores(ctx, spec, D, N):
     X2, L2 = E.with_logabsdet_jacobian(E.inverse(fe), Y)
     assert_close(X2.to_host(), X, dtype, "affine roundtrip", factor=4)
     assert_close(Y.cols(0, 7).to_host(), y_ref[:, :7], dtype, "view")
+
+
+def test_compact_wy_matches_dense_fold_and_handles_tiny_scale(ctx):
+    """The two tensor-core formulations of the C4 chain agree (ENF_NO_WY=1 selects the dense fold), and a ScaleShift
+    with a scale so small that U' = -U / alpha of y = alpha.(x + U'(W^T x)) + c is not finite in Float32 falls back to
+    the dense fold instead of producing Inf / NaN."""
+    import enf_b200 as E
+    D, N = 256, 5000
+    fo, fe = both(["hh64", "ss"], D, 33, np.float32)
+    X = _data(D, N, 34, np.float32, spread=1.0)
+    Xd = E.B200Matrix.from_host(X, ctx)
+    Y, L = E.with_logabsdet_jacobian(fe, Xd)
+    os.environ["ENF_NO_WY"] = "1"
+    try:
+        Yd, Ld = E.with_logabsdet_jacobian(fe, Xd)
+    finally:
+        del os.environ["ENF_NO_WY"]
+    y_ref, l_ref = O.with_logabsdet_jacobian(fo, X.astype(np.float64))
+    assert_close(Y.to_host(), y_ref, np.float32, "wy y")
+    assert_close(Yd.to_host(), y_ref, np.float32, "dense y")
+    assert np.array_equal(L.to_host(), Ld.to_host())
+    rng = np.random.default_rng(5)
+    V = rng.standard_normal((D, 16)).astype(np.float32)
+    a = rng.uniform(0.5, 1.5, D).astype(np.float32)
+    a[7] = 1e-36
+    b = rng.standard_normal(D).astype(np.float32)
+    fz_e = E.compose(E.ScaleShiftTrafo(a, b), E.HouseholderTrafo(V))
+    fz_o = O.compose(O.ScaleShiftTrafo(a.astype(np.float64), b.astype(np.float64)), O.HouseholderTrafo(V.astype(np.float64)))
+    assert E.get_chain(fz_e, D, np.float32, ctx).describe().endswith("forward=tcgen05-compact-wy")    # by shape; the fold decides
+    yz = fz_e(Xd).to_host()
+    assert np.isfinite(yz).all()
+    assert_close(yz, O.with_logabsdet_jacobian(fz_o, X.astype(np.float64))[0], np.float32, "tiny scale y")
 
 
 @pytest.mark.parametrize("code", ["ji", "cs", "cc", "jo"])
