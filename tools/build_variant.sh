@@ -10,7 +10,7 @@ mkdir -p $OBJ $ROOT/build/variants
 cp $ROOT/build/obj/*.o $OBJ/
 for tu in "$@"; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function \
-     -I$ROOT/include -I$CSRC --expt-relaxed-constexpr $EXTRA -c $CSRC/$tu.cu -o $OBJ/$tu.o &
+     -I$ROOT/include -I$CSRC --expt-relaxed-constexpr --compress-mode=size $EXTRA -c $CSRC/$tu.cu -o $OBJ/$tu.o &
 done
 wait
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/build/variants/libenf_$NAME.so $OBJ/*.o -lcudart -ldl
