@@ -55,7 +55,11 @@ constexpr int WY_STAGES = 4;
 constexpr int WY_UBUFS = 4;
 constexpr int WY_SPLIT_WARPS = 4;
 constexpr int WY_EPI_WARPS = 8;
-constexpr int WY_THREADS = 32 * (2 + WY_SPLIT_WARPS + WY_EPI_WARPS + 2);
+#ifndef ENF_WY_ISSUERS
+#define ENF_WY_ISSUERS 2     // threads issuing the MMAs of each GEMM (on alternating chunks / pieces)
+#endif
+constexpr int WY_ISSUERS = ENF_WY_ISSUERS;
+constexpr int WY_THREADS = 32 * (2 + WY_SPLIT_WARPS + WY_EPI_WARPS + 2 + 2 * (WY_ISSUERS - 1));
 
 template <int ND>
 struct WySmem {
@@ -127,7 +131,8 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint64_t* t_free = t_split + 1;                                    // GEMM2 has read Thi / Tlo       (tcgen05.commit)
     uint64_t* v_full = t_free + 1;                                     // [2] a column half of V is final (tcgen05.commit)
     uint64_t* v_free = v_full + 2;                                     // [NKC] a chunk of V is drained  (4 warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_free + NKC);
+    uint64_t* g1_go = v_free + NKC;                                    // the zero-initialising MMAs of a tile have retired (tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g1_go + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (N + WY_TILE_M - 1) / WY_TILE_M;
@@ -144,11 +149,12 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             mbar_init(&u_full[b], 1);
             mbar_init(&u_empty[b], 1);
         }
-        mbar_init(t_full, 1);
+        mbar_init(t_full, WY_ISSUERS);
+        mbar_init(g1_go, 1);
         mbar_init(t_split, WY_EPI_WARPS);
-        mbar_init(t_free, 1);
-        mbar_init(&v_full[0], 1);
-        mbar_init(&v_full[1], 1);
+        mbar_init(t_free, WY_ISSUERS);
+        mbar_init(&v_full[0], WY_ISSUERS);
+        mbar_init(&v_full[1], WY_ISSUERS);
         for (int c = 0; c < NKC; ++c) mbar_init(&v_free[c], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -180,18 +186,24 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || (WY_ISSUERS == 2 && warp == 16)) {
         // ===== GEMM1 issuer: T(i) = X(i) W into the (main | correction) accumulator pair.  ONE thread runs the whole loop: the
         // tensor core's instruction queue is shallow (tools/mma_rate.cu: every cycle the issuing thread spends on barriers,
-        // re-convergence or commits between two MMAs is a cycle the tensor pipe idles), so the loop carries nothing warp-wide =====
+        // re-convergence or commits between two MMAs is a cycle the tensor pipe idles), so the loop carries nothing warp-wide,
+        // and TWO such threads (warps 1 and 16) take alternating chunks: while one sits in its waits and commits, the other
+        // one's MMAs keep the pipe fed.  The only order that matters is that the zero-initialising MMA of a tile comes first:
+        // the second thread starts a tile once the first one's chunk 0 has retired (g1_go) =====
         constexpr uint32_t idesc_n128 = make_idesc_tf32(WY_TILE_M, 2 * WY_KT);
         constexpr uint32_t idesc_n64 = make_idesc_tf32(WY_TILE_M, WY_KT);
         const uint32_t tM = tmem_base + S::T_COL, tC = tM + S::TC_OFF;
+        const int me = warp == 1 ? 0 : 1;
         if (lane == 0) {
             uint32_t it = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 if (i >= 1) mbar_wait(t_free, uint32_t(i - 1) & 1u);                   // GEMM2 of tile i-1 has read Thi | Tlo
+                if (me == 1) mbar_wait(g1_go, uint32_t(i) & 1u);
                 for (int kc = 0; kc < NKC; ++kc, ++it) {
+                    if (WY_ISSUERS == 2 && (kc & 1) != me) continue;
                     const int s = it % WY_STAGES;
                     mbar_wait(&w_full[s], (it / WY_STAGES) & 1);
                     mbar_wait(&split[s], (it / WY_STAGES) & 1);
@@ -209,14 +221,16 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         umma_tf32_ts(tC, tXL + uint32_t(j * 8), dw + adv, idesc_n64, 1);       // correction += xl . Wh
                     }
                     umma_commit(&empty[s]);
-                    if (kc == NKC - 1) umma_commit(t_full);
+                    if (WY_ISSUERS == 2 && kc == 0) umma_commit(g1_go);
+                    if (kc >= NKC - WY_ISSUERS) umma_commit(t_full);                   // this thread's last chunk of the tile
                 }
             }
         }
-    } else if (warp == 15) {
+    } else if (warp == 15 || (WY_ISSUERS == 2 && warp == 17)) {
         // ===== GEMM2 issuer (one thread, see GEMM1): V(j) += T(j) U'^T, A = Thi | Tlo in tensor memory, B = the pieces of U' =====
         constexpr uint32_t idesc2 = make_idesc_tf32(WY_TILE_M, HALF);
         const uint32_t tHI = tmem_base + S::T_COL, tLO = tHI + S::TC_OFF;
+        const int me = warp == 15 ? 0 : 1;                                             // two threads on alternating pieces (see GEMM1)
         if (lane == 0) {
             uint32_t q = 0;
             for (int j = 0; j < my_tiles; ++j) {
@@ -229,6 +243,7 @@ wy_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const uint32_t tD = tV + uint32_t(h * HALF);
 #pragma unroll
                     for (int pc = 0; pc < 4; ++pc, ++q) {
+                        if (WY_ISSUERS == 2 && (pc & 1) != me) continue;
                         const uint32_t b = q % WY_UBUFS;
                         mbar_wait(&u_full[b], (q / WY_UBUFS) & 1u);
                         WY_T(3, j, 1 + 4 * h + pc)
