@@ -50,6 +50,7 @@ SYMBOLS = [
     ("enf_d2h", _i, [_vp, _vp, _vp, _sz]),
     ("enf_memset", _i, [_vp, _vp, _i, _sz]),
     ("enf_fill_normal", _i, [_vp, _i, _vp, _i, _i64, _i64, _u64]),
+    ("enf_convert", _i, [_vp, _i, _vp, _i, _vp, _i64]),
     ("enf_chain_create", _i, [_vp, _i, _i, _i, C.POINTER(enf_op), _pvp]),
     ("enf_chain_set_params", _i, [_vp, _vp]),
     ("enf_chain_num_params", _i, [_vp, C.POINTER(_i64)]),

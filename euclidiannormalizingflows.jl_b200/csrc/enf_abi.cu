@@ -766,6 +766,17 @@ extern "C" int enf_fill_normal(enf_ctx* ctx, int dtype, void* x, int D, int64_t 
     return ENF_OK;
 }
 
+extern "C" int enf_convert(enf_ctx* ctx, int dst_dtype, void* dst, int src_dtype, const void* src, int64_t n) {
+    if (!ctx || (n > 0 && (!dst || !src))) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
+    if ((dst_dtype != ENF_F32 && dst_dtype != ENF_F64) || (src_dtype != ENF_F32 && src_dtype != ENF_F64))
+        return fail(ctx, ENF_ERR_INVALID, "bad dtype %d <- %d", dst_dtype, src_dtype);
+    if (n < 0) return fail(ctx, ENF_ERR_INVALID, "bad element count %lld", (long long)n);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, launch_convert(dst_dtype, dst, src_dtype, src, n, ctx->stream));
+    ctx->launches += 1;
+    return ENF_OK;
+}
+
 // ------------------------------------------------------------------ chains
 // Parameter domain of the kernels.  CenterStretch / CenterContract are evaluated with w = e^{-b|x|} and ln2/b, i.e. for
 // b > 0: the reference itself writes exp(abs(b*x)) and sign(x) (src/center_stretch.jl:6-7), which is the b > 0 branch of

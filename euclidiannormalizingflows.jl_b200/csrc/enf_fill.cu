@@ -41,7 +41,26 @@ __global__ void fill_normal_kernel(T* x, int64_t n_elems, int64_t elem0, uint64_
     }
 }
 
+template <typename TD, typename TS>
+__global__ void convert_kernel(TD* __restrict__ dst, const TS* __restrict__ src, int64_t n) {
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) dst[i] = TD(src[i]);
+}
+
 }  // namespace
+
+cudaError_t launch_convert(int dst_dtype, void* dst, int src_dtype, const void* src, int64_t n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int threads = 256;
+    int64_t blocks = (n + threads - 1) / threads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (dst_dtype == 1 && src_dtype == 0)
+        convert_kernel<double, float><<<unsigned(blocks), threads, 0, st>>>(static_cast<double*>(dst), static_cast<const float*>(src), n);
+    else if (dst_dtype == 0 && src_dtype == 1)
+        convert_kernel<float, double><<<unsigned(blocks), threads, 0, st>>>(static_cast<float*>(dst), static_cast<const double*>(src), n);
+    else
+        return cudaMemcpyAsync(dst, src, size_t(n) * (dst_dtype == 0 ? 4 : 8), cudaMemcpyDeviceToDevice, st);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_fill_normal(int dtype, void* x, int D, int64_t N, int64_t col0, uint64_t seed, cudaStream_t st) {
     const int64_t n = int64_t(D) * N;

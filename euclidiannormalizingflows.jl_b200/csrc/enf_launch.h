@@ -105,5 +105,6 @@ cudaError_t launch_johnsonsu(int dtype, int op, const void* x, void* out, int64_
 
 // synthetic data (enf_fill.cu)
 cudaError_t launch_fill_normal(int dtype, void* x, int D, int64_t N, int64_t col0, uint64_t seed, cudaStream_t st);
+cudaError_t launch_convert(int dst_dtype, void* dst, int src_dtype, const void* src, int64_t n, cudaStream_t st);
 
 }  // namespace enf

@@ -172,5 +172,15 @@ class B200Matrix:
         return B200Matrix(self.ctx, self.D, stop - start, self.dtype,
                           _ptr=self.ptr + start * self.D * self.dtype.itemsize, _owner=self)
 
+    def astype(self, dtype) -> "B200Matrix":
+        """Device-side conversion to the other sample type (enf_convert); self if the type already matches."""
+        dtype = np.dtype(dtype)
+        if dtype == self.dtype:
+            return self
+        m = B200Matrix(self.ctx, self.D, self.N, dtype)
+        L.check(self.ctx._lib.enf_convert(self.ctx.handle, enf_dtype(dtype), C.c_void_p(m.ptr), enf_dtype(self.dtype),
+                                          C.c_void_p(self.ptr), self.D * self.N), self.ctx.handle)
+        return m
+
     def empty_like(self, D: Optional[int] = None) -> "B200Matrix":
         return B200Matrix(self.ctx, self.D if D is None else D, self.N, self.dtype)

@@ -250,8 +250,11 @@ def _evaluate(f, x, want_ladj: bool, out=None, ctx=None):
     if isinstance(x, B200Matrix):
         dt = result_dtype(f, x.dtype)
         if dt != x.dtype:
-            raise TypeError(f"device samples are {x.dtype} but the chain promotes to {dt}; convert the samples "
-                            "(the C ABI is all-f32 or all-f64, src/center_stretch.jl:5)")
+            # float(promote_type(eltype(x), eltype(params)...)) (src/center_stretch.jl:5): Float32 samples meeting Float64
+            # parameters give a Float64 result.  A chain is all-f32 or all-f64, so the samples are widened on the device.
+            if out is not None:
+                raise TypeError(f"device samples are {x.dtype} but the chain promotes to {dt}: out= buffers need converted samples")
+            x = x.astype(dt)
         ch = get_chain(f, x.D, dt, x.ctx)
         y = out[0] if out is not None else x.empty_like()
         lib = x.ctx._lib
@@ -306,10 +309,7 @@ def mvnormal_negll_trafo(trafo, X) -> float:
 
 def _as_device(X, trafo) -> B200Matrix:
     if isinstance(X, B200Matrix):
-        dt = result_dtype(trafo, X.dtype)
-        if dt != X.dtype:
-            raise TypeError(f"device samples are {X.dtype} but the chain promotes to {dt}")
-        return X
+        return X.astype(result_dtype(trafo, X.dtype))      # promotion as in src/center_stretch.jl:5
     X = np.asarray(X)
     dt = result_dtype(trafo, X.dtype if X.dtype.kind == "f" else np.float64)
     return B200Matrix.from_host(np.asarray(X, dtype=dt))

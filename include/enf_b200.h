@@ -99,6 +99,12 @@ int enf_memset(enf_ctx* ctx, void* dst_dev, int value, size_t bytes);
  * (SURVEY §8d). */
 int enf_fill_normal(enf_ctx* ctx, int dtype, void* x_dev, int D, int64_t N, int64_t col0, uint64_t seed);
 
+/* Element-wise conversion between the two sample types on the device (n elements, async on the context's stream).
+ * Replaces the promotion the reference does implicitly, `float(promote_type(eltype(x), eltype(params)...))`
+ * (src/center_stretch.jl:5, src/johnson_trafo.jl:30, src/scale_shift_trafo.jl:15): a chain is all-Float32 or
+ * all-Float64, so Float32 samples meeting Float64 parameters are widened with this call before the chain runs. */
+int enf_convert(enf_ctx* ctx, int dst_dtype, void* dst_dev, int src_dtype, const void* src_dev, int64_t n);
+
 /* ---- chains -------------------------------------------------------------------
  * A chain is the flattened op list of a trafo tree plus device-resident derived
  * constants.  Replaces dispatch on the trafo structs themselves. */

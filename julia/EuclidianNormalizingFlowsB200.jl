@@ -120,8 +120,24 @@ end
 # ---- the generic functions of the hot path -------------------------------------------
 const Trafo = Union{Leaf,Base.ComposedFunction}
 
+# The reference computes in float(promote_type(eltype(x), eltype(params)...)) (src/center_stretch.jl:5,
+# src/johnson_trafo.jl:30, src/scale_shift_trafo.jl:15).  A chain is all-Float32 or all-Float64, so Float32 samples
+# meeting Float64 parameters are widened on the device (enf_convert) - never the parameters narrowed.
+paramtype(f::Leaf) = promote_type((eltype(getfield(f, n)) for n in fieldnames(typeof(f)))...)
+paramtype(f::Base.ComposedFunction) = promote_type(paramtype(f.inner), paramtype(f.outer))
+enf_dtype(::Type{Float32}) = Cint(0); enf_dtype(::Type{Float64}) = Cint(1)
+function Base.convert(::Type{B200Matrix{P}}, x::B200Matrix{T}) where {P,T}
+    P === T && return x
+    y = B200Matrix{P}(x.ctx, size(x)...)
+    check(ccall((:enf_convert, libenf), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64),
+                x.ctx.handle, enf_dtype(P), y.ptr, enf_dtype(T), x.ptr, length(x)), x.ctx.handle)
+    y
+end
+promoted(f::Trafo, x::B200Matrix{T}) where {T} = convert(B200Matrix{float(promote_type(T, paramtype(f)))}, x)
+
 # (f::Trafo)(x): src/center_stretch.jl:37,61; johnson_trafo.jl:74,99; scale_shift_trafo.jl:15-16; householder_trafo.jl:156-157
-function apply(f::Trafo, x::B200Matrix{T}) where {T}
+apply(f::Trafo, x::B200Matrix) = _apply(f, promoted(f, x))
+function _apply(f::Trafo, x::B200Matrix{T}) where {T}
     ch, _ = chain(x.ctx, f, size(x, 1), T)
     y = B200Matrix{T}(x.ctx, size(x)...)
     check(ccall((:enf_forward, libenf), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}), ch, x.ptr, size(x, 2), y.ptr), x.ctx.handle)
@@ -134,7 +150,8 @@ end
 
 # with_logabsdet_jacobian: src/center_stretch.jl:39,63; johnson_trafo.jl:76,101; scale_shift_trafo.jl:18;
 # householder_trafo.jl:159-160.  ladj comes back as the 1 x N Adjoint row of src/abstract_trafo.jl:9.
-function with_logabsdet_jacobian(f::Trafo, x::B200Matrix{T}) where {T}
+with_logabsdet_jacobian(f::Trafo, x::B200Matrix) = _with_logabsdet_jacobian(f, promoted(f, x))
+function _with_logabsdet_jacobian(f::Trafo, x::B200Matrix{T}) where {T}
     ch, _ = chain(x.ctx, f, size(x, 1), T)
     y = B200Matrix{T}(x.ctx, size(x)...)
     l = B200Matrix{T}(x.ctx, size(x, 2), 1)
@@ -144,7 +161,8 @@ function with_logabsdet_jacobian(f::Trafo, x::B200Matrix{T}) where {T}
 end
 
 # src/optimize_whitening.jl:7-15
-function mvnormal_negll_trafo(f::Trafo, x::B200Matrix{T}) where {T}
+mvnormal_negll_trafo(f::Trafo, x::B200Matrix) = _mvnormal_negll_trafo(f, promoted(f, x))
+function _mvnormal_negll_trafo(f::Trafo, x::B200Matrix{T}) where {T}
     ch, _ = chain(x.ctx, f, size(x, 1), T)
     out = Ref{Float64}(0)
     check(ccall((:enf_negll, libenf), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Float64}), ch, x.ptr, size(x, 2), out), x.ctx.handle)
@@ -168,7 +186,8 @@ function unpack(f::Leaf, g, D, pos)
 end
 
 # src/optimize_whitening.jl:18-22 (value as Zygote reports it: src/abstract_trafo.jl:30-33)
-function mvnormal_negll_trafograd(f::Trafo, x::B200Matrix{T}) where {T}
+mvnormal_negll_trafograd(f::Trafo, x::B200Matrix) = _mvnormal_negll_trafograd(f, promoted(f, x))
+function _mvnormal_negll_trafograd(f::Trafo, x::B200Matrix{T}) where {T}
     ch, leaves = chain(x.ctx, f, size(x, 1), T)
     np = Ref{Int64}(0)
     check(ccall((:enf_chain_num_params, libenf), Cint, (Ptr{Cvoid}, Ref{Int64}), ch, np), x.ctx.handle)

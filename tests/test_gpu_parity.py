@@ -224,9 +224,30 @@ def test_errors_are_reported_not_fatal(ctx):
         E.get_chain(E.ScaleShiftTrafo(np.ones(5000), np.zeros(5000)), 5000, np.float32, ctx)   # D too large
     with pytest.raises(ValueError):
         E.get_chain(E.ScaleShiftTrafo(np.ones(3), np.zeros(3)), 4, np.float32, ctx)            # shape mismatch
-    X = E.B200Matrix.from_host(np.zeros((4, 8), dtype=np.float32), ctx)
-    with pytest.raises(TypeError):
-        E.with_logabsdet_jacobian(E.ScaleShiftTrafo(np.ones(4), np.zeros(4)), X)               # f64 params, f32 data
+
+
+def test_mixed_dtypes_promote_like_the_reference(ctx):
+    """float(promote_type(eltype(x), eltype(params)...)) (src/center_stretch.jl:5, johnson_trafo.jl:30): Float32 samples
+    with Float64 parameters give a Float64 result (the samples are widened on the device, enf_convert); Float64 samples
+    with Float32 parameters too."""
+    import enf_b200 as E
+    rng = np.random.default_rng(3)
+    X32 = rng.standard_normal((4, 257)).astype(np.float32)
+    a, b, c = np.full(4, 0.5), np.full(4, 1.25), np.full(4, -0.25)           # float64 parameters
+    fe, fo = E.CenterStretch(a, b, c), O.CenterStretch(a, b, c)
+    Y, L = E.with_logabsdet_jacobian(fe, E.B200Matrix.from_host(X32, ctx))
+    assert Y.dtype == np.float64 and L.dtype == np.float64
+    y_ref, l_ref = O.with_logabsdet_jacobian(fo, X32.astype(np.float64))
+    assert_close(Y.to_host(), y_ref, np.float64, "promoted y")
+    assert_close(L.to_host()[0], l_ref, np.float64, "promoted ladj")
+    f32 = E.CenterStretch(a.astype(np.float32), b.astype(np.float32), c.astype(np.float32))
+    Y2 = f32(E.B200Matrix.from_host(X32.astype(np.float64), ctx))
+    assert Y2.dtype == np.float64
+    assert_close(Y2.to_host(), y_ref, np.float64, "f64 samples, f32 parameters")
+    v = E.mvnormal_negll_trafo(fe, E.B200Matrix.from_host(X32, ctx))
+    assert abs(v - O.mvnormal_negll_trafo(fo, X32.astype(np.float64))) < 1e-10 * (abs(v) + 1)
+    Xd = E.B200Matrix.from_host(X32, ctx)
+    assert Xd.astype(np.float32) is Xd and np.array_equal(Xd.astype(np.float64).astype(np.float32).to_host(), X32)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
