@@ -158,10 +158,28 @@ __global__ void __launch_bounds__(256) fit_update_kernel(const __grid_constant__
     const int D = fd.D;
     __shared__ double s_red[256];
     if (partials != nullptr) {
-        for (int i = threadIdx.x; i < fd.n_raw; i += blockDim.x) {
+        // fixed order, eight lanes per output with four loads in flight each (as reduce_partials_kernel): one thread
+        // walking all CTAs is a chain of n_blocks dependent L2 round trips on the critical path of every step
+        const int j = threadIdx.x & 7;
+        for (int i0 = 0; i0 < fd.n_raw; i0 += blockDim.x >> 3) {
+            const int i = i0 + (threadIdx.x >> 3);
             double s = 0.0;
-            for (int b = 0; b < n_blocks; ++b) s += partials[size_t(b) * fd.n_raw + i];
-            sums[i] = s;
+            if (i < fd.n_raw) {
+                int b = j;
+                for (; b + 24 < n_blocks; b += 32) {
+                    const double p0 = partials[size_t(b) * fd.n_raw + i], p1 = partials[size_t(b + 8) * fd.n_raw + i];
+                    const double p2 = partials[size_t(b + 16) * fd.n_raw + i], p3 = partials[size_t(b + 24) * fd.n_raw + i];
+                    s += p0;
+                    s += p1;
+                    s += p2;
+                    s += p3;
+                }
+                for (; b < n_blocks; b += 8) s += partials[size_t(b) * fd.n_raw + i];
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (i < fd.n_raw && j == 0) sums[i] = s;
         }
         if (threadIdx.x == 0) sums[fd.n_raw] = count;
         __syncthreads();
