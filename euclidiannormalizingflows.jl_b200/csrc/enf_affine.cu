@@ -112,21 +112,21 @@ affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer.  ONE thread runs the whole loop with a single wait per chunk (split[s]: the splitters have seen the
+        // TMA transaction of the stage, W chunks included, complete): the tensor core's instruction queue is shallow, so
+        // every cycle the issuing thread spends in a second wait, a warp re-convergence or a commit is a cycle the tensor
+        // pipe idles (tools/mma_rate.cu; the warp-wide form of this loop cost ~450 clk per chunk next to 1536 clk of MMAs) =====
         constexpr uint32_t idesc = make_idesc_tf32(AF_TILE_M, ND);
-        uint32_t it = 0, tcount = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-            const uint32_t buf = tcount & 1;
-            if (tcount >= 2) mbar_wait(&acc_empty[buf], ((tcount >> 1) - 1) & 1);   // epilogue of tile t-2 drained this buffer
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t acc = tmem_base + buf * S::ACC_COLS;
-            for (int kc = 0; kc < NKC; ++kc, ++it) {
-                const int s = it % S::STAGES;
-                const uint32_t ph = (it / S::STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                mbar_wait(&split[s], ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
+        if (lane == 0) {
+            uint32_t it = 0, tcount = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t buf = tcount & 1;
+                if (tcount >= 2) mbar_wait(&acc_empty[buf], ((tcount >> 1) - 1) & 1);   // epilogue of tile t-2 drained this buffer
+                const uint32_t acc = tmem_base + buf * S::ACC_COLS;
+                for (int kc = 0; kc < NKC; ++kc, ++it) {
+                    const int s = it % S::STAGES;
+                    mbar_wait(&split[s], (it / S::STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     unsigned char* st = smem + size_t(s) * S::STAGE_BYTES;
                     const uint64_t dxh = make_desc_kmajor<KC>(st), dxl = make_desc_kmajor<KC>(st + S::X_BYTES);
                     const uint64_t dwh = make_desc_kmajor<KC>(st + 2 * S::X_BYTES);
@@ -141,7 +141,6 @@ affine_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     umma_commit(&empty[s]);                           // frees the stage when these MMAs retire
                     if (kc == NKC - 1) umma_commit(&acc_full[buf]);
                 }
-                __syncwarp();
             }
         }
     } else if (warp < 2 + AF_SPLITTERS / 32) {

@@ -135,21 +135,19 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: P[h] += Xh[h] Xh^T + Xh[h] (2 Xl)^T, both operands MN-major =====
+        // ===== MMA issuer: P[h] += Xh[h] Xh^T + Xh[h] (2 Xl)^T, both operands MN-major.  ONE thread runs the whole loop
+        // with one wait per stage (split[s]; the splitters have seen the TMA land): every cycle the issuer spends in waits,
+        // re-convergence or commits is a cycle the tensor pipe idles (tools/mma_rate.cu) =====
         constexpr uint32_t idesc = make_idesc_tf32(128, ND) | (1u << 15) | (1u << 16);
-        for (int it = 0; it < my_stages; ++it) {
-            const int s = it % S::STAGES;
-            const uint32_t ph = uint32_t(it / S::STAGES) & 1u;
-            const int fs = it % MO_FLUSH_STAGES, period = it / MO_FLUSH_STAGES, buf = period % S::NBUF;
-            if (fs == 0 && period >= S::NBUF) {
-                mbar_wait(&acc_empty[buf], uint32_t(period / S::NBUF - 1) & 1u);   // this accumulator has been drained
+        if (lane == 0) {
+            for (int it = 0; it < my_stages; ++it) {
+                const int s = it % S::STAGES;
+                const int fs = it % MO_FLUSH_STAGES, period = it / MO_FLUSH_STAGES, buf = period % S::NBUF;
+                if (fs == 0 && period >= S::NBUF)
+                    mbar_wait(&acc_empty[buf], uint32_t(period / S::NBUF - 1) & 1u);   // this accumulator has been drained
+                mbar_wait(&split[s], uint32_t(it / S::STAGES) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            mbar_wait(&full[s], ph);
-            mbar_wait(&split[s], ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const bool last = (fs == MO_FLUSH_STAGES - 1) || (it == my_stages - 1);
-            if (lane == 0) {
+                const bool last = (fs == MO_FLUSH_STAGES - 1) || (it == my_stages - 1);
                 const uint32_t xh = smem_u32(smem + size_t(s) * S::STAGE_BYTES), xl = xh + S::X_BYTES;
                 const uint32_t acc = tmem_base + uint32_t(buf * S::NH * ND);
 #pragma unroll
@@ -166,7 +164,6 @@ moments_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ pa
                 umma_commit(&empty[s]);
                 if (last) umma_commit(&acc_full[buf]);
             }
-            __syncwarp();
         }
     } else if (warp < 2 + MO_SPLIT_THREADS / 32) {
         // ===== splitters: x -> xh (in place), 2 (x - xh) (second buffer); row sums for m =====

@@ -300,6 +300,8 @@ def test_against_committed_golden_fixtures(ctx, dtype, name):
     (["hh8"], 64, 127),
     (["hh16", "ss", "hh16"], 128, 2049),
     (["ss", "hh9", "ss"], 256, 100001),   # compact WY with zero-padded reflections, ScaleShift on both sides, ragged last tile
+    (["hh64", "ss"], 256, 1),             # a single sample: every row of the TMA boxes but one is out of bounds
+    (["hh20", "ss"], 256, 18943),         # exactly 148 CTAs, the last one with a one-sample tile
     (["hh33", "hh31"], 256, 40000),       # two stacks = 64 reflections, no ScaleShift
 ])
 def test_affine_chains_on_tensor_cores(ctx, spec, D, N):
