@@ -358,6 +358,17 @@ def main():
         E.with_logabsdet_jacobian(fe, xh, out=(yh, lh), ctx=ctx)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_e2e * world * e2e_steps / e2e_s
+    # the same pipeline without the kernel (ENF_HOST_COPY_ONLY): what the platform's host<->device path carries with all
+    # ranks copying at once -- the ceiling of the end-to-end number
+    os.environ["ENF_HOST_COPY_ONLY"] = "1"
+    E.with_logabsdet_jacobian(fe, xh, out=(yh, lh), ctx=ctx)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        E.with_logabsdet_jacobian(fe, xh, out=(yh, lh), ctx=ctx)
+    copy_s = max_over_ranks(time.perf_counter() - t0)
+    del os.environ["ENF_HOST_COPY_ONLY"]
+    E.with_logabsdet_jacobian(fe, xh, out=(yh, lh), ctx=ctx)      # leave real results in the host buffers
 
     # ---- secondary metric (the "fwd+grad" half of BASELINE.json's metric, and the only path with a collective): the C5
     # optimize_whitening gradient step -- fused loss+gradient kernel on this rank's shard of the batch, all-reduce of the
@@ -621,7 +632,13 @@ def main():
                          "algorithmic_bytes_per_sample": bytes_per_sample},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": n_e2e * D_MAIN * 4,
                     "d2h_bytes_per_step": n_e2e * (D_MAIN + 1) * 4, "samples_per_step": n_e2e, "steps": e2e_steps,
-                    "api": "with_logabsdet_jacobian(chain, pinned host matrix) -> enf_forward_ladj_host"},
+                    "api": "with_logabsdet_jacobian(chain, pinned host matrix) -> enf_forward_ladj_host",
+                    "pcie_gbs_per_rank_each_way": [n_e2e * D_MAIN * 4 * e2e_steps / e2e_s / 1e9, n_e2e * (D_MAIN + 1) * 4 * e2e_steps / e2e_s / 1e9],
+                    "host_buffers": "pinned, first-touched on the NUMA node of the rank's GPU when the topology is visible (enf_host_alloc)",
+                    "copy_only_value": n_e2e * world * e2e_steps / copy_s,
+                    "frac_of_copy_only": copy_s / e2e_s,
+                    "copy_only": "the same chunked H2D / D2H pipeline with the kernel launch skipped (ENF_HOST_COPY_ONLY=1), all ranks "
+                                 "at once: the host<->device ceiling of this box for this traffic pattern"},
             "gpu_launches": launches, "clocks": clocks, "extras": extras,
         }
         if cpu is not None:

@@ -9,6 +9,8 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
+#include <sys/mman.h>
 #include <nccl.h>  // types only; the library is dlopen'ed (see NcclApi)
 
 #include <cmath>
@@ -17,6 +19,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -66,6 +69,9 @@ struct enf_ctx {
     cudaEvent_t timing[ENF_N_EVENTS] = {};
     int64_t launches = 0;
     std::string last_error;
+    // pinned host buffers placed on the GPU's NUMA node (enf_host_alloc): base -> mapped bytes
+    std::map<void*, size_t> numa_allocs;
+    int numa_node = -2;             // -2: not looked up yet, -1: unknown
     // NCCL group
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -656,6 +662,10 @@ extern "C" int enf_destroy(enf_ctx* ctx) {
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     for (int i = 0; i < ENF_N_EVENTS; ++i)
         if (ctx->timing[i]) cudaEventDestroy(ctx->timing[i]);
+    for (auto& kv : ctx->numa_allocs) {                 // host buffers the caller never freed
+        cudaHostUnregister(kv.first);
+        munmap(kv.first, kv.second);
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ENF_OK;
@@ -714,10 +724,75 @@ extern "C" int enf_free(enf_ctx* ctx, void* dptr) {
     return ENF_OK;
 }
 
+// NUMA node the GPU hangs off (sysfs), or -1
+static int gpu_numa_node(int device) {
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* c = bus; *c; ++c) *c = char(tolower(*c));
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+// the CPUs of a NUMA node that this thread may run on ("0-31,64-95" in sysfs)
+static bool node_cpus(int node, const cpu_set_t& allowed, cpu_set_t& out) {
+    char path[96];
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    CPU_ZERO(&out);
+    int n = 0, lo = 0, hi = 0;
+    while (fscanf(f, "%d", &lo) == 1) {
+        hi = lo;
+        int c = fgetc(f);
+        if (c == '-') {
+            if (fscanf(f, "%d", &hi) != 1) break;
+            c = fgetc(f);
+        }
+        for (int i = lo; i <= hi && i < CPU_SETSIZE; ++i)
+            if (CPU_ISSET(i, &allowed)) { CPU_SET(i, &out); ++n; }
+        if (c != ',') break;
+    }
+    fclose(f);
+    return n > 0;
+}
+
+// Pinned host memory for the host-matrix entry points.  With several GPUs per box every rank streams ~90 GB/s through
+// its buffers; if they all sit on the NUMA node the processes happened to start on, the ranks of the other socket pull
+// everything across the inter-socket link and one node's DRAM carries all of it (round 1: 0.18 weak-scaling efficiency
+// of the end-to-end leg at 8 GPUs).  So the pages are placed on the node the GPU hangs off: the calling thread is moved
+// onto that node's CPUs while it first-touches an anonymous mapping (local allocation policy; needs no CAP_SYS_NICE,
+// unlike mbind), and the mapping is then pinned with cudaHostRegister.  Falls back to cudaMallocHost when the topology
+// is not visible or anything fails (ENF_NO_NUMA=1 forces that).
 extern "C" int enf_host_alloc(enf_ctx* ctx, size_t bytes, void** hptr) {
     if (!ctx || !hptr) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
     CU(ctx, cudaSetDevice(ctx->device));
     *hptr = nullptr;
+    if (ctx->numa_node == -2) ctx->numa_node = getenv("ENF_NO_NUMA") ? -1 : gpu_numa_node(ctx->device);
+    cpu_set_t old_set, node_set;
+    if (bytes >= (size_t(1) << 20) && ctx->numa_node >= 0 && sched_getaffinity(0, sizeof old_set, &old_set) == 0 &&
+        node_cpus(ctx->numa_node, old_set, node_set)) {
+        const size_t map_bytes = (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+        void* p = mmap(nullptr, map_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            madvise(p, map_bytes, MADV_HUGEPAGE);
+            const bool moved = sched_setaffinity(0, sizeof node_set, &node_set) == 0;
+            std::memset(p, 0, map_bytes);                                  // first touch on the GPU's node
+            if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+            if (moved && cudaHostRegister(p, map_bytes, cudaHostRegisterDefault) == cudaSuccess) {
+                ctx->numa_allocs[p] = map_bytes;
+                *hptr = p;
+                return ENF_OK;
+            }
+            cudaGetLastError();
+            munmap(p, map_bytes);
+        }
+    }
     cudaError_t e = cudaMallocHost(hptr, bytes ? bytes : 16);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -730,6 +805,13 @@ extern "C" int enf_host_free(enf_ctx* ctx, void* hptr) {
     if (!ctx) return fail(ctx, ENF_ERR_INVALID, "ctx is NULL");
     if (!hptr) return ENF_OK;
     CU(ctx, cudaSetDevice(ctx->device));
+    auto it = ctx->numa_allocs.find(hptr);
+    if (it != ctx->numa_allocs.end()) {
+        CU(ctx, cudaHostUnregister(hptr));
+        munmap(hptr, it->second);
+        ctx->numa_allocs.erase(it);
+        return ENF_OK;
+    }
     CU(ctx, cudaFreeHost(hptr));
     return ENF_OK;
 }
@@ -1043,6 +1125,7 @@ extern "C" int enf_forward_ladj_host(enf_chain* ch, const void* x_host, int64_t 
     CU(ctx, cudaEventRecord(ctx->ev, ctx->stream));
     for (int i = 0; i < HOST_SLOTS; ++i) CU(ctx, cudaStreamWaitEvent(ctx->slot_stream[i], ctx->ev, 0));
     const size_t xb_al = (x_bytes + 255) / 256 * 256;
+    const bool copy_only = getenv("ENF_HOST_COPY_ONLY") != nullptr;
     int64_t done = 0;
     for (int it = 0; done < N; ++it) {
         const int s = it % HOST_SLOTS;
@@ -1054,7 +1137,8 @@ extern "C" int enf_forward_ladj_host(enf_chain* ch, const void* x_host, int64_t 
         cudaStream_t st = ctx->slot_stream[s];
         CU(ctx, cudaMemcpyAsync(dx, static_cast<const char*>(x_host) + size_t(done) * col_bytes, size_t(n) * col_bytes,
                                 cudaMemcpyHostToDevice, st));
-        int rc = forward_impl(ch, dx, n, dy, dl, ladj_host != nullptr, st);
+        // ENF_HOST_COPY_ONLY=1 (diagnostic): the same pipeline without the kernel = the copy ceiling of the platform
+        int rc = copy_only ? ENF_OK : forward_impl(ch, dx, n, dy, dl, ladj_host != nullptr, st);
         if (rc != ENF_OK) return rc;
         CU(ctx, cudaMemcpyAsync(static_cast<char*>(y_host) + size_t(done) * col_bytes, dy, size_t(n) * col_bytes,
                                 cudaMemcpyDeviceToHost, st));

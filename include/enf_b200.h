@@ -87,7 +87,7 @@ int enf_sync(enf_ctx* ctx);                                   /* blocking */
 
 int enf_alloc(enf_ctx* ctx, size_t bytes, void** dptr);
 int enf_free(enf_ctx* ctx, void* dptr);
-int enf_host_alloc(enf_ctx* ctx, size_t bytes, void** hptr); /* pinned host memory */
+int enf_host_alloc(enf_ctx* ctx, size_t bytes, void** hptr); /* pinned host memory, placed on the GPU's NUMA node */
 int enf_host_free(enf_ctx* ctx, void* hptr);
 int enf_h2d(enf_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* async on ctx stream */
 int enf_d2h(enf_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* blocking */
