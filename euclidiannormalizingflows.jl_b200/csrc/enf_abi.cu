@@ -908,12 +908,17 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
     ch->ctx = ctx;
     ch->dtype = dtype;
     ch->D = D;
-    if (!make_plan(dtype, D, ch->plan)) {
+    ChainDesc& d = ch->desc;
+    // Lay the op list out for a plan.  The three-vectors-per-lane plans (make_plan) triple the per-thread accumulators of
+    // the gradient kernel against the one-vector layout the power-of-two plan would give it: if those no longer fit the
+    // shared memory, the chain takes the power-of-two plan.
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    if (!make_plan(dtype, D, ch->plan, attempt == 0)) {
         delete ch;
         return fail(ctx, ENF_ERR_INVALID, "D=%d is not supported (max %d rows for this dtype)", D,
                     dtype == ENF_F32 ? 1024 : 512);
     }
-    ChainDesc& d = ch->desc;
+    ch->ops.clear();
     std::memset(&d, 0, sizeof d);
     d.n_ops = n_ops;
     d.D = D;
@@ -948,6 +953,14 @@ extern "C" int enf_chain_create(enf_ctx* ctx, int dtype, int D, int n_ops, const
     d.n_scalars = soff;
     d.n_save = save;
     ch->n_raw = d.n_rowslots * d.Dp + d.n_scalars + 2;
+    if (attempt == 0 && ch->plan.CH == 3) {
+        KernelSet ks;
+        if (!select_kernels(dtype, ch->plan, MODE_VEC, ks) || grad_smem_bytes(dtype, d, ks, true) > 227 * 1024 ||
+            fwd_smem_bytes(dtype, d) > 200 * 1024)
+            continue;
+    }
+    break;
+    }
     ch->affine = affine_supported(dtype, D, d);
     ch->wy = ch->affine && wy_rank(dtype, D, d) > 0;
     ch->moments = ch->affine && moments_supported(dtype, D) && getenv("ENF_NO_MOMENTS") == nullptr;

@@ -52,7 +52,7 @@ bool select_kernels(int dtype, const Plan& plan, int mode, KernelSet& k) {
     return mode == MODE_VEC ? select_f64_vec(plan, k) : select_f64_scalar(plan, k);
 }
 
-bool make_plan(int dtype, int D, Plan& plan) {
+bool make_plan(int dtype, int D, Plan& plan, bool allow_three) {
     const int VE = dtype == 0 ? 4 : 2;
     plan = Plan{};
     if (D < 1) return false;
@@ -90,6 +90,19 @@ bool make_plan(int dtype, int D, Plan& plan) {
     plan.gLG = LG;
     plan.gCH = CHp;
     while (plan.gCH > 1 && plan.gLG < 5) { ++plan.gLG; plan.gCH >>= 1; }
+    // Three vectors per lane where that pads fewer rows than the power-of-two plan (nvec = 3, 5-6, 9-12, 17-24, ...:
+    // D = 24 ran with a quarter of its lanes idle, D = 20 with three eighths).  Forward and gradient kernels share the
+    // padded row count, so both take the (lanes, 3) layout.
+    if (allow_three && !getenv("ENF_NO_CH3"))
+        for (int lg = 0; lg <= 5; ++lg) {
+            const int cap = 3 << lg;
+            if (cap >= nvec && cap * VE < plan.Dp) {
+                plan.LG = plan.gLG = lg;
+                plan.CH = plan.gCH = 3;
+                plan.Dp = cap * VE;
+                break;
+            }
+        }
     return true;
 }
 

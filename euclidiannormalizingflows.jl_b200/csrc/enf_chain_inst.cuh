@@ -50,6 +50,8 @@ bool select_group_fwd(int LG, int CH, KernelSet& k) {
 #define ENF_CASE(lg, ch) if (LG == lg && CH == ch) { fill_fwd<T, lg, ch, MODE, 0>(k); return true; }
     ENF_CASE(0, 1) ENF_CASE(0, 2) ENF_CASE(1, 2) ENF_CASE(2, 2) ENF_CASE(3, 2) ENF_CASE(4, 2)
     ENF_CASE(5, 2) ENF_CASE(5, 4) ENF_CASE(5, 8) ENF_CASE(2, 1) ENF_CASE(0, 4)
+    // three vectors per lane: D = 12, 24, 48, 96, ... (and the sizes just below) without a quarter of the lanes idle
+    ENF_CASE(0, 3) ENF_CASE(1, 3) ENF_CASE(2, 3) ENF_CASE(3, 3) ENF_CASE(4, 3) ENF_CASE(5, 3)
 #undef ENF_CASE
     return false;
 }
@@ -61,6 +63,7 @@ bool select_group_grad(int LG, int CH, KernelSet& k) {
 #define ENF_CASE(lg, ch) if (LG == lg && CH == ch) { fill_grad<T, lg, ch, MODE, 0>(k); return true; }
     ENF_CASE(0, 1) ENF_CASE(1, 1) ENF_CASE(2, 1) ENF_CASE(3, 1) ENF_CASE(4, 1) ENF_CASE(5, 1)
     ENF_CASE(5, 2) ENF_CASE(5, 4) ENF_CASE(5, 8)
+    ENF_CASE(0, 3) ENF_CASE(1, 3) ENF_CASE(2, 3) ENF_CASE(3, 3) ENF_CASE(4, 3) ENF_CASE(5, 3)
 #undef ENF_CASE
     return false;
 }

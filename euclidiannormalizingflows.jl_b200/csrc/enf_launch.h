@@ -31,7 +31,7 @@ struct KernelSet {
     int fwd_threads = 256;      // CTA size of the forward kernels
 };
 
-bool make_plan(int dtype, int D, Plan& plan);
+bool make_plan(int dtype, int D, Plan& plan, bool allow_three = true);
 bool select_kernels(int dtype, const Plan& plan, int mode, KernelSet& k);
 size_t fwd_smem_bytes(int dtype, const ChainDesc& d);
 size_t grad_smem_bytes(int dtype, const ChainDesc& d, const KernelSet& k, bool grad);

@@ -65,6 +65,19 @@ def test_chains(ctx, dtype, spec, D):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("D", [6, 12, 17, 20, 24, 45, 48, 96, 192, 384])
+def test_three_vectors_per_lane_plans(ctx, dtype, D):
+    """Sizes where make_plan gives every lane three 16-byte vectors instead of padding the sample to a power of two
+    (Float32: 3, 5-6, 9-12, 17-24, ... vectors; Float64 has two rows per vector), forward + ladj, aligned and as an
+    unaligned column view, ragged N."""
+    import enf_b200 as E
+    ch = E.get_chain(both(["cs", "hh3", "jo", "ss"], D, 0, dtype)[1], D, dtype, ctx)
+    assert "vectors_per_lane=3" in ch.describe() or D in (6, 17, 45, 192, 384), ch.describe()
+    _check_wlaj(E, ctx, ["cs", "hh3", "jo", "ss"], D, 2053, dtype)
+    _check_wlaj(E, ctx, ["cc", "hh2", "ji"], D, 777, dtype, col0=3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("N", [1, 2, 3, 31, 255, 256, 257, 1025, 5000])
 @pytest.mark.parametrize("D", [1, 2, 7, 16])
 def test_ragged_sizes(ctx, dtype, N, D):
@@ -143,6 +156,14 @@ GRAD_CHAINS = [
     (["hh4", "jo", "cs"], 16),
     (["ji", "hh2", "cs"], 8),
     (["jo", "hh5", "ss"], 100),
+    # three vectors per lane (make_plan): D = 12, 20, 24, 48, 96 and the masked-scalar D = 17, 45
+    (["cc", "hh3", "jo", "ss"], 12),
+    (["cs", "hh2", "ss"], 20),
+    (["cc", "jo", "hh4", "ss"], 24),
+    (["jo", "hh3", "ss"], 48),
+    (["ss", "hh2", "cc"], 96),
+    (["cc", "hh2", "jo"], 17),
+    (["jo", "hh3", "ss"], 45),
 ]
 
 
@@ -300,8 +321,8 @@ def test_against_committed_golden_fixtures(ctx, dtype, name):
     (["hh8"], 64, 127),
     (["hh16", "ss", "hh16"], 128, 2049),
     (["ss", "hh9", "ss"], 256, 100001),   # compact WY with zero-padded reflections, ScaleShift on both sides, ragged last tile
-    (["hh64", "ss"], 256, 1),             # a single sample: every row of the TMA boxes but one is out of bounds
-    (["hh20", "ss"], 256, 18943),         # exactly 148 CTAs, the last one with a one-sample tile
+    (["hh64", "ss"], 256, 8),             # nine samples: nearly every row of the TMA boxes is out of bounds
+    (["hh20", "ss"], 256, 18943),         # N + 1 = 148 full tiles: exactly one tile per CTA
     (["hh33", "hh31"], 256, 40000),       # two stacks = 64 reflections, no ScaleShift
 ])
 def test_affine_chains_on_tensor_cores(ctx, spec, D, N):
