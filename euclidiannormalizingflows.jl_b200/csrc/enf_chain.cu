@@ -176,13 +176,22 @@ cudaError_t launch_fwd(int dtype, const KernelSet& k, const ChainDesc& desc, con
 cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
                         int64_t N, bool grad, double* partials, int max_blocks, int* blocks_used, int sm_count,
                         cudaStream_t st) {
-    const void* fn = grad ? k.grad : k.negll;
-    const size_t smem = grad_smem_bytes(dtype, desc, k, grad);
+    const int64_t items = (N + k.LN - 1) / k.LN;
+    KernelSet ks = k;
+    static const bool no_small = getenv("ENF_NO_SMALL_GRAD") != nullptr;
+    if (k.grad_small && !no_small && (items + k.grad_items_per_tile - 1) / k.grad_items_per_tile < sm_count) {
+        // fewer regular tiles than SMs: the one-vector-per-thread variant spreads the batch over more of them
+        ks.grad = k.grad_small;
+        ks.negll = k.negll_small;
+        ks.grad_items_per_tile = k.grad_small_items_per_tile;
+        ks.grad_tile_elems = k.grad_small_tile_elems;
+    }
+    const void* fn = grad ? ks.grad : ks.negll;
+    const size_t smem = grad_smem_bytes(dtype, desc, ks, grad);
     int per_sm = 0;
     cudaError_t e = prepare_kernel(fn, smem, per_sm);
     if (e != cudaSuccess) return e;
-    const int64_t items = (N + k.LN - 1) / k.LN;
-    int64_t tiles = (items + k.grad_items_per_tile - 1) / k.grad_items_per_tile;
+    int64_t tiles = (items + ks.grad_items_per_tile - 1) / ks.grad_items_per_tile;
     if (tiles < 1) tiles = 1;
     int64_t cap = int64_t(per_sm) * sm_count;
     if (cap > max_blocks) cap = max_blocks;

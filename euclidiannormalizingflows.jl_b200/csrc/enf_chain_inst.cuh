@@ -43,6 +43,15 @@ void fill_grad(KernelSet& k) {
     k.VE = CG::VE;
 }
 
+template <typename T, int LG, int CH, int MODE, int PD>
+void fill_grad_small(KernelSet& k) {
+    using CG = Cfg<T, LG, CH, MODE, PD, 1>;
+    k.grad_small = reinterpret_cast<const void*>(&chain_grad_kernel<CG, true>);
+    k.negll_small = reinterpret_cast<const void*>(&chain_grad_kernel<CG, false>);
+    k.grad_small_items_per_tile = CG::SB * CG::SPT;
+    k.grad_small_tile_elems = CG::SPT * CG::CH * CG::VE;
+}
+
 // (log2 lanes per sample, vectors per lane) pairs make_plan() can produce for the forward kernels
 // (two vectors per lane where possible) plus (2,1) and (0,4) for the ENF_PLAN_LG tuning override ...
 template <typename T, int MODE>

@@ -6,6 +6,7 @@ template <typename T, int MODE, int PD>
 void fill(KernelSet& k) {
     fill_fwd<T, 0, 1, MODE, PD>(k);
     fill_grad<T, 0, 1, MODE, PD>(k);
+    fill_grad_small<T, 0, 1, MODE, PD>(k);
 }
 }  // namespace
 bool select_pack(int dtype, int PD, int mode, KernelSet& k) {

@@ -25,6 +25,12 @@ struct KernelSet {
     int fwd_items_per_tile = 0;
     int grad_items_per_tile = 0;
     int grad_tile_elems = 0;
+    // one vector per thread per tile: the variant for batches too small to give every SM a tile of the regular kernel
+    // (packed modes only: the D = 1 fit of BASELINE configs[1] runs 1e5-sample batches = 25 regular tiles on 148 SMs)
+    const void* grad_small = nullptr;
+    const void* negll_small = nullptr;
+    int grad_small_items_per_tile = 0;
+    int grad_small_tile_elems = 0;
     int LN = 1;  // samples per item (packed modes)
     int G = 1, CH = 1, VE = 4;
     size_t fwd_ring_bytes = 0;  // TMA input ring of the forward kernels (MODE_VEC)
