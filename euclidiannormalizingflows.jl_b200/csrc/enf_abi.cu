@@ -107,7 +107,11 @@ NcclApi g_nccl;
 int load_nccl(enf_ctx* ctx) {
     std::lock_guard<std::mutex> lk(g_nccl_mu);
     if (g_nccl.handle) return ENF_OK;
-    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    // ENF_NCCL_LIB: a specific libnccl.so.2.  The dynamic linker keeps ONE library per soname and process, so a process
+    // that will also load another NCCL user later (e.g. PyTorch with its bundled, newer NCCL) must load that copy first.
+    void* h = nullptr;
+    if (const char* p = getenv("ENF_NCCL_LIB")) h = dlopen(p, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!h) return fail(ctx, ENF_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
     NcclApi a;

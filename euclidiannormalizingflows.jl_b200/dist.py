@@ -3,9 +3,12 @@
 Forward / inverse / ladj need no communication (columns are independent,
 parameters are replicated).  The loss+gradient step has exactly one exchange:
 an all-reduce (sum, float64) of the raw loss and parameter-gradient sums
-(SURVEY §8e).  On GPUs that is an ncclAllReduce issued by the library on its own
-stream (enf_negll_grad_group); `torch.distributed` is used only as plumbing to
-hand the NCCL unique id to every rank.
+(SURVEY §8e).  On GPUs that is one kernel over NVLink peer memory (or an
+ncclAllReduce) issued by the library on its own stream (enf_negll_grad_group).
+The only thing the ranks must exchange on the host is the 128-byte NCCL unique
+id: `init_group` hands it out over a plain TCP socket (MASTER_ADDR / MASTER_PORT,
+no PyTorch involved), or over an already initialised torch.distributed group if
+the caller has one.
 """
 from __future__ import annotations
 
@@ -62,16 +65,93 @@ def allreduce_sums(sums: np.ndarray, n_local: int):
     return out[:-1].reshape(np.shape(sums)), int(round(out[-1]))
 
 
-def init_group(ctx) -> Tuple[int, int]:
-    """Create the library's NCCL communicator for `ctx` from an initialised
-    torch.distributed process group.  Returns (rank, world)."""
-    import torch
-    import torch.distributed as dist
-    if not dist.is_initialized():
-        raise RuntimeError("torch.distributed is not initialised")
-    rank, world = dist.get_rank(), dist.get_world_size()
+def exchange_bytes(payload: bytes, rank: int, world: int, addr: str = "127.0.0.1", port: int = 29400, timeout: float = 120.0) -> bytes:
+    """Rank 0 sends `payload` to every other rank over TCP; every rank returns rank 0's payload.  A torch-free
+    rendezvous for the NCCL unique id (the Julia shim would use Sockets the same way)."""
+    import socket
+    import struct
+    import time
+    if world <= 1:
+        return payload
+    if rank == 0:
+        with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as srv:
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind((addr, port))
+            srv.listen(world)
+            srv.settimeout(timeout)
+            seen = set()
+            while len(seen) < world - 1:
+                conn, _ = srv.accept()
+                with conn:
+                    conn.settimeout(timeout)
+                    (r,) = struct.unpack("!i", _recv_exact(conn, 4))
+                    conn.sendall(struct.pack("!i", len(payload)) + payload)
+                    seen.add(r)
+        return payload
+    deadline = time.monotonic() + timeout
+    while True:
+        try:
+            with socket.create_connection((addr, port), timeout=timeout) as c:
+                c.sendall(struct.pack("!i", rank))
+                (n,) = struct.unpack("!i", _recv_exact(c, 4))
+                return _recv_exact(c, n)
+        except (ConnectionRefusedError, ConnectionResetError, socket.timeout):
+            if time.monotonic() > deadline:
+                raise
+            time.sleep(0.05)
+
+
+def _recv_exact(sock, n: int) -> bytes:
+    buf = b""
+    while len(buf) < n:
+        part = sock.recv(n - len(buf))
+        if not part:
+            raise ConnectionResetError("peer closed the rendezvous socket")
+        buf += part
+    return buf
+
+
+def init_group(ctx, rank: int = None, world: int = None, addr: str = None, port: int = None) -> Tuple[int, int]:
+    """Create the library's NCCL communicator (and the peer-memory exchange buffers) for `ctx`.  Returns (rank, world).
+
+    With an initialised torch.distributed process group and no explicit rank/world, the unique id travels over that
+    group.  Otherwise rank / world come from the arguments or RANK / WORLD_SIZE, and the id travels over a TCP socket
+    on MASTER_ADDR : MASTER_PORT + 1 (`exchange_bytes`): no PyTorch on this path."""
+    import os
     lib = ctx._lib
     ident = (C.c_ubyte * L.ENF_UNIQUE_ID_BYTES)()
+    use_torch = False
+    if rank is None and world is None:
+        try:
+            import torch.distributed as dist
+            use_torch = dist.is_initialized()
+        except ImportError:
+            use_torch = False
+    if not use_torch:
+        if "ENF_NCCL_LIB" not in os.environ:
+            # one libnccl.so.2 per process: prefer the copy of the nvidia-nccl wheel (what PyTorch would load) if it is
+            # installed, so that importing torch later in this process still works
+            try:
+                import importlib.util
+                spec = importlib.util.find_spec("nvidia.nccl")
+                cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2") if spec else None
+                if cand and os.path.exists(cand):
+                    os.environ["ENF_NCCL_LIB"] = cand
+            except (ImportError, ValueError, IndexError):
+                pass
+        rank = int(os.environ.get("RANK", 0)) if rank is None else int(rank)
+        world = int(os.environ.get("WORLD_SIZE", 1)) if world is None else int(world)
+        addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
+        port = int(port) if port is not None else int(os.environ.get("MASTER_PORT", 29399)) + 1
+        if rank == 0:
+            L.check(lib.enf_group_unique_id(ident))
+        raw = exchange_bytes(bytes(ident), rank, world, addr, port)
+        ident = (C.c_ubyte * L.ENF_UNIQUE_ID_BYTES).from_buffer_copy(raw)
+        L.check(lib.enf_group_init(ctx.handle, world, rank, ident), ctx.handle)
+        return rank, world
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
     if rank == 0:
         L.check(lib.enf_group_unique_id(ident))
     t = torch.tensor(list(bytes(ident)), dtype=torch.uint8)

@@ -72,3 +72,26 @@ def test_sharded_batches_allreduce_world2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) < 1e-12
+
+
+def _rendezvous_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import enf_b200 as E
+    payload = bytes(range(128)) if rank == 0 else b""
+    got = E.dist.exchange_bytes(payload, rank, world, "127.0.0.1", port, timeout=30.0)
+    out.put((rank, got == bytes(range(128))))
+
+
+def test_torch_free_rendezvous_world3():
+    """The NCCL unique id travels from rank 0 to the other ranks over a plain TCP socket (no torch.distributed on the
+    library's path): three processes, rank 0 started last so that the others have to retry."""
+    ctx = mp.get_context("spawn")
+    port, out = _free_port(), None
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_rendezvous_worker, args=(r, 3, port, out)) for r in (1, 2, 0)]
+    for p in procs:
+        p.start()
+    res = dict(out.get(timeout=60) for _ in range(3))
+    for p in procs:
+        p.join(timeout=30)
+    assert res == {0: True, 1: True, 2: True}

@@ -16,15 +16,14 @@ WORKER = textwrap.dedent("""
     import os, sys
     import numpy as np
     sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
-    import torch, torch.distributed as dist
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
     import enf_b200 as E
     from chains import both, flat_grads
     from oracle import enf_oracle as O
     ctx = E.Context(rank)
-    E.dist.init_group(ctx)
+    # no torch.distributed anywhere in this process: the NCCL unique id travels over a TCP socket (MASTER_PORT + 1)
+    assert E.dist.init_group(ctx, rank=rank, world=world) == (rank, world)
+    assert "torch" not in sys.modules
     D, N = 32, 10007
     fo, fe = both(["cc", "jo", "hh4", "ss"], D, 3, np.float64)
     X = np.random.default_rng(4).standard_normal((D, N))
@@ -90,7 +89,7 @@ WORKER = textwrap.dedent("""
         raise SystemExit("mismatching batch counts were not detected")
     except E.EnfError as exc:
         assert "disagree" in str(exc), exc
-    dist.barrier(); dist.destroy_process_group()
+    ctx.sync()
     print("rank", rank, "ok")
 """) % (ROOT, ROOT)
 
