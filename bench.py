@@ -430,6 +430,22 @@ def main():
                          "fma_pipe_frac": (elems_per_s * prof["fma_pipe_cycles_per_element"] / issue_peak) if prof.get("fma_pipe_cycles_per_element") else None,
                          "source": "profiles/r2_grad_c5.json (ncu --set full of the same kernel)"},
         }
+        # the same steps with the loop on the device (enf_optimize_whitening: gradient kernel + one kernel that reduces the
+        # partials, exchanges the sums over NVLink peer memory, finishes and applies the ADAGrad update): no host round
+        # trip per step, so no rank skew from the host side either
+        try:
+            Xdl = Xg.cols(0, 8 * nb)
+            E.optimize_whitening(Xdl, ge, E.ADAGrad(), nbatches=8, nepochs=1, device_loop=True, group=grp)
+            ctx.sync()
+            barrier()
+            t0 = time.perf_counter()
+            rdl = E.optimize_whitening(Xdl, ge, E.ADAGrad(), nbatches=8, nepochs=5, device_loop=True, group=grp)
+            dl_s = max_over_ranks(time.perf_counter() - t0) / 40
+            secondary["device_loop"] = {"ms_per_step": dl_s * 1e3, "value": nb * world / dl_s, "unit": "samples/s", "steps": 40,
+                                        "negll_first_last": [rdl["negll_history"][0], rdl["negll_history"][-1]],
+                                        "step": "optimize_whitening(device_loop=True): 2 launches per step, exchange fused into the update kernel"}
+        except Exception as exc:  # noqa: BLE001
+            secondary["device_loop"] = {"error": f"{type(exc).__name__}: {exc}"}
         if grp:
             err = None
             if rank == 0:
