@@ -1123,7 +1123,8 @@ extern "C" int enf_forward_ladj_host(enf_chain* ch, const void* x_host, int64_t 
     const size_t es = elem_size(ch->dtype);
     const size_t col_bytes = size_t(ch->D) * es;
     // chunk: ~32 MiB of samples, a multiple of 1024 columns so every chunk stays 16-byte aligned
-    int64_t chunk = int64_t((size_t(32) << 20) / col_bytes);
+    static const size_t chunk_mb = getenv("ENF_HOST_CHUNK_MB") ? size_t(atoi(getenv("ENF_HOST_CHUNK_MB"))) : 32;   // tuning aid
+    int64_t chunk = int64_t(((chunk_mb ? chunk_mb : 32) << 20) / col_bytes);
     chunk = (chunk / 1024) * 1024;
     if (chunk < 1024) chunk = 1024;
     if (chunk > N) chunk = N;
