@@ -213,7 +213,13 @@ def test_grad_reproducible_and_ragged(ctx, dtype):
 
 def test_optimize_whitening_matches_oracle(ctx):
     """A short fit: same loss history and final parameters as the oracle's
-    restatement of the reference loop (src/optimize_whitening.jl:25-45)."""
+    restatement of the reference loop (src/optimize_whitening.jl:25-45).
+
+    What this does and does not pin: the host optimizer (whitening.py: setup / update / _ht_normalize / batch_ranges)
+    is the oracle's own restatement of Optimisers.jl 0.2's ADAGrad rule and of the functor rebuild, so agreement here
+    checks the KERNELS (loss and gradients of every step) and the loop plumbing, not the ADAGrad rule itself.  That
+    rule lives in an un-vendored Julia package (Optimisers.jl, not under /root/reference) and stays "parity unpinned"
+    (DESIGN.md section 4); an independent check would need the Julia package."""
     import enf_b200 as E
     rng = np.random.default_rng(0)
     Xw = rng.standard_normal((2, 4000))
