@@ -612,7 +612,19 @@ def main():
             t0 = time.perf_counter()
             rr = E.optimize_whitening(X2, f2, E.ADAGrad(), nbatches=100, nepochs=2, group=world > 1)
             host_s = max_over_ranks(time.perf_counter() - t0) / len(rr["negll_history"])
+            # ... and in Float64 (C2 is quoted for both types)
+            n2d = n2 // 2
+            one64 = np.ones(1, dtype=np.float64)
+            f2d = E.compose(E.JohnsonTrafo(0 * one64, 5 * one64, 0 * one64, 5 * one64), E.ScaleShiftTrafo(one64.copy(), 0 * one64))
+            X2d = E.B200Matrix(ctx, 1, n2d, np.float64, _ptr=Y.ptr, _owner=Y)
+            E._lib.check(ctx._lib.enf_fill_normal(ctx.handle, 1, C.c_void_p(X2d.ptr), 1, n2d, rank * n2d, SEED), ctx.handle)
+            E.optimize_whitening(X2d, f2d, E.ADAGrad(), nbatches=50, nepochs=1, device_loop=True, group=world > 1)
+            ctx.sync(); barrier()
+            t0 = time.perf_counter()
+            rrd = E.optimize_whitening(X2d, f2d, E.ADAGrad(), nbatches=50, nepochs=20, device_loop=True, group=world > 1)
+            dev64_s = max_over_ranks(time.perf_counter() - t0) / len(rrd["negll_history"])
             extras["fit_c2_d1"] = {"batch_per_gpu": n2 // 100, "us_per_step_device_loop": dev_s * 1e6, "us_per_step_host_loop": host_s * 1e6,
+                                   "us_per_step_device_loop_f64": dev64_s * 1e6,
                                    "samples_per_s_device_loop": (n2 // 100) * world / dev_s,
                                    "group_parity_err": fit_parity,
                                    "note": "optimize_whitening steps; device loop = enf_optimize_whitening (2 launches/step, CUDA graph per epoch)"}
