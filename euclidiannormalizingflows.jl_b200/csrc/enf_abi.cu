@@ -777,7 +777,8 @@ extern "C" int enf_host_alloc(enf_ctx* ctx, size_t bytes, void** hptr) {
     if (!ctx || !hptr) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
     CU(ctx, cudaSetDevice(ctx->device));
     *hptr = nullptr;
-    if (ctx->numa_node == -2) ctx->numa_node = getenv("ENF_NO_NUMA") ? -1 : gpu_numa_node(ctx->device);
+    if (ctx->numa_node == -2)      // ENF_NUMA_NODE=<n> overrides the sysfs lookup (boxes that hide the topology; tests)
+        ctx->numa_node = getenv("ENF_NO_NUMA") ? -1 : getenv("ENF_NUMA_NODE") ? atoi(getenv("ENF_NUMA_NODE")) : gpu_numa_node(ctx->device);
     cpu_set_t old_set, node_set;
     if (bytes >= (size_t(1) << 20) && ctx->numa_node >= 0 && sched_getaffinity(0, sizeof old_set, &old_set) == 0 &&
         node_cpus(ctx->numa_node, old_set, node_set)) {

@@ -727,3 +727,35 @@ def test_device_loop_with_explicit_batches_and_scalar_fields(ctx, dtype):
     h1d, h1h = np.array(r1d["negll_history"]), np.array(r1h["negll_history"])
     assert np.max(np.abs(h1d - h1h) / (np.abs(h1h) + 1)) < (2e-4 if dtype == np.float32 else 1e-9)
     assert np.ndim(E.flatten(r1d["result"])[0].gamma) == 0
+
+
+def test_numa_placed_pinned_host_buffers():
+    """enf_host_alloc on the NUMA-placement path (anonymous mapping first-touched from the node's CPUs + cudaHostRegister;
+    ENF_NUMA_NODE=0 forces it on boxes that report no node for the GPU): the host-matrix pipeline reads and writes such
+    buffers like cudaMallocHost ones, and they are released cleanly.  Own context in a child process (the lookup is
+    cached per context and the variable must be set before the library reads it)."""
+    import subprocess
+    import sys
+    import textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import os, sys
+        import numpy as np
+        os.environ["ENF_NUMA_NODE"] = "0"
+        sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+        import enf_b200 as E
+        from chains import both
+        from oracle import enf_oracle as O
+        ctx = E.Context(0)
+        D, N = 16, 300_000
+        fo, fe = both(["hh4", "jo", "cs"], D, 1, np.float32)
+        xh = ctx.pinned_empty((D, N), np.float32); yh = ctx.pinned_empty((D, N), np.float32); lh = ctx.pinned_empty((1, N), np.float32)
+        xh[...] = np.random.default_rng(0).standard_normal((D, N)).astype(np.float32)
+        E.with_logabsdet_jacobian(fe, xh, out=(yh, lh), ctx=ctx)
+        y_ref, l_ref = O.with_logabsdet_jacobian(fo, np.asarray(xh, dtype=np.float64))
+        ey = np.max(np.abs(yh - y_ref) / (np.abs(y_ref) + np.sqrt(np.mean(y_ref ** 2))))
+        assert ey < 1e-5, ey
+        print("numa ok", ey)
+    """) % (root, root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "numa ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
