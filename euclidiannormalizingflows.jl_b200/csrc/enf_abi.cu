@@ -1690,13 +1690,18 @@ extern "C" int enf_optimize_whitening_batches(enf_chain* ch, const void* x, int6
             KernelSet ks;
             select_kernels(ch->dtype, ch->plan, pick_mode(ch, xb, nullptr), ks);
             int blocks = 0;
+            // gradient kernel -> update kernel -> gradient kernel ... as programmatic dependent launches: each kernel is
+            // scheduled while its predecessor still runs and waits on the device (griddepcontrol.wait), which takes the
+            // launch latency out of a step that is two short kernels (ENF_NO_PDL=1: plain stream order)
+            static const bool pdl = getenv("ENF_NO_PDL") == nullptr;
+            const bool pdl_u = pdl && !(use_group && !(ctx->p2p && size_t(ch->n_raw + 1) <= size_t(P2P_SLOT)));
             CUF(launch_grad(ch->dtype, ks, ch->desc, ch->d_consts, xb, nbt, true, ch->d_partials, ch->max_blocks, &blocks,
-                            ctx->sm_count, ctx->stream));
+                            ctx->sm_count, ctx->stream, pdl_u));
             if (use_group && ctx->p2p && size_t(ch->n_raw + 1) <= size_t(P2P_SLOT)) {
                 // sharded batch, small payload: the update kernel sums the partials, exchanges the sums with the other ranks
                 // through NVLink peer memory and applies the step - still two launches per step
                 CUF(launch_fit_update(ch->dtype, fd, ch->d_sums, ch->d_partials, blocks, double(nbt), d_lconst, d_params, d_state,
-                                      eta, epsilon, flags, d_hist, d_step, ch->d_consts, ctx->stream, &ctx->p2p_desc));
+                                      eta, epsilon, flags, d_hist, d_step, ch->d_consts, ctx->stream, &ctx->p2p_desc, pdl_u));
                 ctx->launches += 2;
             } else if (use_group) {
                 CUF(launch_reduce(ch->d_partials, blocks, ch->n_raw, ch->d_sums, false, ctx->stream));
@@ -1710,7 +1715,7 @@ extern "C" int enf_optimize_whitening_batches(enf_chain* ch, const void* x, int6
                 ctx->launches += 3;
             } else {
                 CUF(launch_fit_update(ch->dtype, fd, ch->d_sums, ch->d_partials, blocks, double(nbt), d_lconst, d_params, d_state,
-                                      eta, epsilon, flags, d_hist, d_step, ch->d_consts, ctx->stream));
+                                      eta, epsilon, flags, d_hist, d_step, ch->d_consts, ctx->stream, nullptr, pdl_u));
                 ctx->launches += 2;
             }
         }

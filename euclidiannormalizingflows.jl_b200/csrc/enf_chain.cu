@@ -175,7 +175,7 @@ cudaError_t launch_fwd(int dtype, const KernelSet& k, const ChainDesc& desc, con
 
 cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
                         int64_t N, bool grad, double* partials, int max_blocks, int* blocks_used, int sm_count,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool pdl) {
     const int64_t items = (N + k.LN - 1) / k.LN;
     KernelSet ks = k;
     static const bool no_small = getenv("ENF_NO_SMALL_GRAD") != nullptr;
@@ -198,7 +198,20 @@ cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, co
     const unsigned grid = unsigned(tiles < cap ? tiles : cap);
     *blocks_used = int(grid);
     void* args[] = {const_cast<ChainDesc*>(&desc), &consts, &x, &N, &partials};
-    return cudaLaunchKernel(fn, dim3(grid), dim3(NT), args, smem, st);
+    if (!pdl) return cudaLaunchKernel(fn, dim3(grid), dim3(NT), args, smem, st);
+    // programmatic dependent launch: may start before the previous kernel of the stream has finished (chain_grad_kernel
+    // waits for it with griddepcontrol.wait before it reads the constants)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
 cudaError_t launch_reduce(const double* partials, int n_blocks, int n_raw, double* sums, bool accumulate,

@@ -1142,12 +1142,20 @@ __global__ void __launch_bounds__(NT, ENF_GRAD_MIN_CTAS) chain_grad_kernel(const
     sm.save = smem_u32(s_save) + uint32_t(tid) * 16u;
     sm.acc = smem_u32(s_acc) + uint32_t(tid) * 16u;
     sm.sc = s_acc + (GRAD ? size_t(desc.n_rowslots) * C::CH * NT * VE : 0);
-    stage_constants<C>(desc, consts, s_c);
+    // Programmatic dependent launch (the device-side fit loop chains gradient kernel -> update kernel -> gradient kernel ...
+    // with the programmatic-serialization launch attribute): do what does not depend on the previous kernel, wait for it
+    // before touching what it wrote (the constants), and let the next kernel of the chain be scheduled.  Both instructions
+    // are no-ops for ordinary launches.
     if (GRAD) {
         const T zero[VE] = {};
         for (int i = 0; i < desc.n_rowslots * C::CH; ++i) st16_shared(s_acc + (size_t(i) * NT + tid) * VE, zero);
         for (int i = 0; i < desc.n_scalars; ++i) sm.sc[size_t(i) * NT + tid] = T(0);
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // only now: the update kernel launched behind this one may read the parameters before ITS wait, which is safe once
+    // the previous update kernel (the one this kernel has just waited for) is complete
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    stage_constants<C>(desc, consts, s_c);
     constexpr int Dp = C::DP;
     T loss_y = T(0), loss_l = T(0);
     double loss_y64 = 0.0, loss_l64 = 0.0;

@@ -157,6 +157,45 @@ __global__ void __launch_bounds__(256) fit_update_kernel(const __grid_constant__
                                                          T* __restrict__ consts, const __grid_constant__ P2PDesc p2p) {
     const int D = fd.D;
     __shared__ double s_red[256];
+    // Small problems (the D = 1 / D = 2 fits of BASELINE configs[0-1]) work out of shared memory: a step of this kernel
+    // used to be a chain of ~10 dependent L2 round trips (sums -> gradients -> state -> parameters -> constants).
+    constexpr int FIT_SMEM_PARAMS = 1024, FIT_SMEM_SUMS = 2048;
+    __shared__ double s_params[FIT_SMEM_PARAMS], s_state[FIT_SMEM_PARAMS], s_sums[FIT_SMEM_SUMS];
+    __shared__ double s_lc[2];
+    __shared__ long long s_step;
+    int n_params = 0;
+    for (int o = 0; o < fd.n_ops; ++o) {
+        const int e = fd.ops[o].poff + (fd.ops[o].kind == OP_HH ? fd.ops[o].K * D : (fd.ops[o].kind == OP_SS ? 2 : fd.ops[o].kind == OP_JO || fd.ops[o].kind == OP_JI ? 4 : 3) * D);
+        n_params = e > n_params ? e : n_params;
+    }
+    const bool small = n_params <= FIT_SMEM_PARAMS && fd.n_raw + 1 <= FIT_SMEM_SUMS;
+    double* const g_params = params;
+    double* const g_state = state;
+    double* const g_sums = sums;
+    // Programmatic dependent launch (see chain_grad_kernel): this CTA may be resident while the gradient kernel still
+    // runs.  Parameters, optimizer state, ladj constants and the step counter were written by the PREVIOUS update kernel,
+    // which is complete (the gradient kernel waited for it before it let this kernel launch): fetch them now, under the
+    // gradient kernel's run time; the partial sums may only be read after the wait.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (small) {
+        for (int i = threadIdx.x; i < n_params; i += blockDim.x) {
+            s_params[i] = g_params[i];
+            s_state[i] = g_state[i];
+        }
+        params = s_params;
+        state = s_state;
+        sums = s_sums;
+    }
+    if (threadIdx.x == 0) {
+        s_lc[0] = lconst[0];
+        s_lc[1] = lconst[1];
+        s_step = *step_ctr;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (partials == nullptr && small) {          // sums already reduced (and all-reduced) in global memory by the caller
+        for (int i = threadIdx.x; i <= fd.n_raw; i += blockDim.x) s_sums[i] = g_sums[i];
+        __syncthreads();
+    }
     if (partials != nullptr) {
         // fixed order, eight lanes per output with four loads in flight each (as reduce_partials_kernel): one thread
         // walking all CTAs is a chain of n_blocks dependent L2 round trips on the critical path of every step
@@ -192,9 +231,9 @@ __global__ void __launch_bounds__(256) fit_update_kernel(const __grid_constant__
     const double Nd = sums[fd.n_raw];
     const double LB = -1.0;
     if (threadIdx.x == 0) {
-        const double lc = lconst[1] + ((flags & 1) ? 0.0 : lconst[0]);   // ENF_NEGLL_ZYGOTE_PRIMAL drops the ScaleShift ladj value
+        const double lc = s_lc[1] + ((flags & 1) ? 0.0 : s_lc[0]);      // ENF_NEGLL_ZYGOTE_PRIMAL drops the ScaleShift ladj value
         // the step counter lives on the device so that one captured epoch (a CUDA graph) can be replayed
-        const long long step = *step_ctr;
+        const long long step = s_step;
         history[step] = (sums[fd.n_raw - 2] + 0.5 * LOG2PI_D * Nd * D - (sums[fd.n_raw - 1] + Nd * lc)) / Nd;
         *step_ctr = step + 1;
     }
@@ -270,6 +309,14 @@ __global__ void __launch_bounds__(256) fit_update_kernel(const __grid_constant__
         __syncthreads();
     }
     fit_derive<T>(fd, params, consts, lconst, s_red);     // constants for the next step
+    if (small) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_params; i += blockDim.x) {
+            g_params[i] = s_params[i];
+            g_state[i] = s_state[i];
+        }
+        for (int i = threadIdx.x; i <= fd.n_raw; i += blockDim.x) g_sums[i] = s_sums[i];
+    }
 }
 
 }  // namespace
@@ -284,16 +331,24 @@ cudaError_t launch_fit_derive(int dtype, const FitDesc& fd, const double* params
 // p2p != nullptr (and partials != nullptr): the batch is sharded over the ranks of p2p; the kernel all-reduces the sums itself
 cudaError_t launch_fit_update(int dtype, const FitDesc& fd, double* sums, const double* partials, int n_blocks, double count,
                               double* lconst, double* params, double* state, double eta, double eps, int flags,
-                              double* history, long long* step_ctr, void* consts, cudaStream_t st, const P2PDesc* p2p) {
+                              double* history, long long* step_ctr, void* consts, cudaStream_t st, const P2PDesc* p2p, bool pdl) {
     P2PDesc none = {};
     const P2PDesc& pd = p2p ? *p2p : none;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
     if (dtype == 0)
-        fit_update_kernel<float><<<1, 256, 0, st>>>(fd, sums, partials, n_blocks, count, lconst, params, state, eta, eps, flags,
-                                                    history, step_ctr, static_cast<float*>(consts), pd);
-    else
-        fit_update_kernel<double><<<1, 256, 0, st>>>(fd, sums, partials, n_blocks, count, lconst, params, state, eta, eps, flags,
-                                                     history, step_ctr, static_cast<double*>(consts), pd);
-    return cudaGetLastError();
+        return cudaLaunchKernelEx(&cfg, fit_update_kernel<float>, fd, sums, partials, n_blocks, count, lconst, params, state, eta, eps,
+                                  flags, history, step_ctr, static_cast<float*>(consts), pd);
+    return cudaLaunchKernelEx(&cfg, fit_update_kernel<double>, fd, sums, partials, n_blocks, count, lconst, params, state, eta, eps,
+                              flags, history, step_ctr, static_cast<double*>(consts), pd);
 }
 
 }  // namespace enf

@@ -46,7 +46,7 @@ cudaError_t launch_fwd(int dtype, const KernelSet& k, const ChainDesc& desc, con
                        void* y, void* ladj, int64_t N, double ladj_const, int sm_count, cudaStream_t st);
 cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, const void* consts, const void* x,
                         int64_t N, bool grad, double* partials, int max_blocks, int* blocks_used, int sm_count,
-                        cudaStream_t st);
+                        cudaStream_t st, bool pdl = false);
 cudaError_t launch_reduce(const double* partials, int n_blocks, int n_raw, double* sums, bool accumulate,
                           cudaStream_t st);
 
@@ -102,7 +102,8 @@ cudaError_t launch_fit_derive(int dtype, const FitDesc& fd, const double* params
                               cudaStream_t st);
 cudaError_t launch_fit_update(int dtype, const FitDesc& fd, double* sums, const double* partials, int n_blocks, double count,
                               double* lconst, double* params, double* state, double eta, double eps, int flags,
-                              double* history, long long* step_ctr, void* consts, cudaStream_t st, const P2PDesc* p2p = nullptr);
+                              double* history, long long* step_ctr, void* consts, cudaStream_t st, const P2PDesc* p2p = nullptr,
+                              bool pdl = false);
 
 // JohnsonSU distribution operations (enf_johnsonsu.cu); `op` values are the ABI's enf_johnsonsu_op
 enum : int { JSU_PDF = 0, JSU_LOGPDF = 1, JSU_CDF = 2, JSU_LOGCDF = 3, JSU_CCDF = 4, JSU_LOGCCDF = 5, JSU_QUANTILE = 6 };
