@@ -728,6 +728,8 @@ extern "C" int enf_free(enf_ctx* ctx, void* dptr) {
     return ENF_OK;
 }
 
+static std::mutex g_host_mu;      // guards enf_ctx::numa_allocs / numa_node (host buffers may be managed from several threads)
+
 // NUMA node the GPU hangs off (sysfs), or -1
 static int gpu_numa_node(int device) {
     char bus[64] = {0};
@@ -777,11 +779,14 @@ extern "C" int enf_host_alloc(enf_ctx* ctx, size_t bytes, void** hptr) {
     if (!ctx || !hptr) return fail(ctx, ENF_ERR_INVALID, "NULL argument");
     CU(ctx, cudaSetDevice(ctx->device));
     *hptr = nullptr;
+    std::unique_lock<std::mutex> lk(g_host_mu);
     if (ctx->numa_node == -2)      // ENF_NUMA_NODE=<n> overrides the sysfs lookup (boxes that hide the topology; tests)
         ctx->numa_node = getenv("ENF_NO_NUMA") ? -1 : getenv("ENF_NUMA_NODE") ? atoi(getenv("ENF_NUMA_NODE")) : gpu_numa_node(ctx->device);
+    const int node = ctx->numa_node;
+    lk.unlock();
     cpu_set_t old_set, node_set;
-    if (bytes >= (size_t(1) << 20) && ctx->numa_node >= 0 && sched_getaffinity(0, sizeof old_set, &old_set) == 0 &&
-        node_cpus(ctx->numa_node, old_set, node_set)) {
+    if (bytes >= (size_t(1) << 20) && node >= 0 && sched_getaffinity(0, sizeof old_set, &old_set) == 0 &&
+        node_cpus(node, old_set, node_set)) {
         const size_t map_bytes = (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
         void* p = mmap(nullptr, map_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (p != MAP_FAILED) {
@@ -790,6 +795,7 @@ extern "C" int enf_host_alloc(enf_ctx* ctx, size_t bytes, void** hptr) {
             std::memset(p, 0, map_bytes);                                  // first touch on the GPU's node
             if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
             if (moved && cudaHostRegister(p, map_bytes, cudaHostRegisterDefault) == cudaSuccess) {
+                lk.lock();
                 ctx->numa_allocs[p] = map_bytes;
                 *hptr = p;
                 return ENF_OK;
@@ -810,11 +816,18 @@ extern "C" int enf_host_free(enf_ctx* ctx, void* hptr) {
     if (!ctx) return fail(ctx, ENF_ERR_INVALID, "ctx is NULL");
     if (!hptr) return ENF_OK;
     CU(ctx, cudaSetDevice(ctx->device));
-    auto it = ctx->numa_allocs.find(hptr);
-    if (it != ctx->numa_allocs.end()) {
+    size_t mapped = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        auto it = ctx->numa_allocs.find(hptr);
+        if (it != ctx->numa_allocs.end()) {
+            mapped = it->second;
+            ctx->numa_allocs.erase(it);
+        }
+    }
+    if (mapped) {
         CU(ctx, cudaHostUnregister(hptr));
-        munmap(hptr, it->second);
-        ctx->numa_allocs.erase(it);
+        munmap(hptr, mapped);
         return ENF_OK;
     }
     CU(ctx, cudaFreeHost(hptr));
