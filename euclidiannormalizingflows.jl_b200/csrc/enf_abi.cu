@@ -1714,7 +1714,8 @@ extern "C" int enf_optimize_whitening_batches(enf_chain* ch, const void* x, int6
                 // sharded batch, small payload: the update kernel sums the partials, exchanges the sums with the other ranks
                 // through NVLink peer memory and applies the step - still two launches per step
                 CUF(launch_fit_update(ch->dtype, fd, ch->d_sums, ch->d_partials, blocks, double(nbt), d_lconst, d_params, d_state,
-                                      eta, epsilon, flags, d_hist, d_step, ch->d_consts, ctx->stream, &ctx->p2p_desc, pdl_u));
+                                      eta, epsilon, flags, d_hist, d_step, ch->d_consts, ctx->stream, &ctx->p2p_desc,
+                                      pdl_u && blocks < ctx->sm_count));
                 ctx->launches += 2;
             } else if (use_group) {
                 CUF(launch_reduce(ch->d_partials, blocks, ch->n_raw, ch->d_sums, false, ctx->stream));
@@ -1728,7 +1729,8 @@ extern "C" int enf_optimize_whitening_batches(enf_chain* ch, const void* x, int6
                 ctx->launches += 3;
             } else {
                 CUF(launch_fit_update(ch->dtype, fd, ch->d_sums, ch->d_partials, blocks, double(nbt), d_lconst, d_params, d_state,
-                                      eta, epsilon, flags, d_hist, d_step, ch->d_consts, ctx->stream, nullptr, pdl_u));
+                                      eta, epsilon, flags, d_hist, d_step, ch->d_consts, ctx->stream, nullptr,
+                                      pdl_u && blocks < ctx->sm_count));
                 ctx->launches += 2;
             }
         }

@@ -198,7 +198,9 @@ cudaError_t launch_grad(int dtype, const KernelSet& k, const ChainDesc& desc, co
     const unsigned grid = unsigned(tiles < cap ? tiles : cap);
     *blocks_used = int(grid);
     void* args[] = {const_cast<ChainDesc*>(&desc), &consts, &x, &N, &partials};
-    if (!pdl) return cudaLaunchKernel(fn, dim3(grid), dim3(NT), args, smem, st);
+    // (only for grids smaller than the GPU: a step of two short kernels is latency-bound and gains ~2 %; with a full-size
+    // grid the early-resident CTAs of the next kernel cost more than the hidden launch latency - measured -1.4 % on C5)
+    if (!pdl || int(grid) >= sm_count) return cudaLaunchKernel(fn, dim3(grid), dim3(NT), args, smem, st);
     // programmatic dependent launch: may start before the previous kernel of the stream has finished (chain_grad_kernel
     // waits for it with griddepcontrol.wait before it reads the constants)
     cudaLaunchConfig_t cfg = {};

@@ -56,7 +56,9 @@ constexpr int P2P_MAX_RANKS = 16;
 constexpr int P2P_SLOT = 8192;                         // doubles per rank and parity
 constexpr size_t P2P_SEQ_OFF = 0, P2P_ERR_OFF = 8, P2P_FLAG_OFF = 256, P2P_DATA_OFF = 1024;
 constexpr long long P2P_SPIN_LIMIT = 400000000;        // ~2 minutes of waiting for a peer (rank skew: first-call set-up, host jitter) before giving up
-inline size_t p2p_bytes(int nranks) { return P2P_DATA_OFF + size_t(2) * nranks * P2P_SLOT * sizeof(double); }
+// data area: [parity][source rank][P2P_SLOT] entries of 16 bytes: every double travels as two 8-byte words
+// {32 data bits, 32-bit sequence number} (enf_p2p.cuh)
+inline size_t p2p_bytes(int nranks) { return P2P_DATA_OFF + size_t(2) * nranks * P2P_SLOT * 16; }
 struct P2PDesc {
     void* peer[P2P_MAX_RANKS];                         // peer[r]: rank r's buffer as mapped in this process
     int nranks, rank;

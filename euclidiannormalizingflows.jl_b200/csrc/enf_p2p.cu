@@ -2,11 +2,12 @@
 //
 // The exchange of a step is a few KB of float64 sums: pure latency.  Instead of a library collective, every rank
 // keeps a small buffer that all the other ranks of the node map through CUDA IPC (NVLink / NVSwitch peer memory).
-// One kernel per rank does the whole all-reduce: it STORES its sums into its slot of every peer's buffer, publishes
-// a sequence number with a system-scope release store, waits (bounded) for the sequence numbers of the other ranks
-// in its own buffer and adds the slots in rank order - every rank obtains the bitwise identical result.  The
-// sequence counter lives on the device, so the kernel can sit inside a captured CUDA graph (enf_optimize_whitening).
-// Data slots are double-buffered by sequence parity: a rank can only be one all-reduce ahead of the slowest one.
+// One kernel per rank does the whole all-reduce: it STORES its sums into its slot of every peer's buffer as 8-byte
+// words that carry the exchange's sequence number next to 32 data bits each, polls its own buffer until the words of
+// every other rank show that number, and adds the slots in rank order - every rank obtains the bitwise identical
+// result with one NVLink store latency and no fence (enf_p2p.cuh).  The sequence counter lives on the device, so the
+// kernel can sit inside a captured CUDA graph (enf_optimize_whitening).  Data slots are double-buffered by sequence
+// parity: a rank can only be one all-reduce ahead of the slowest one.
 #include <cuda_runtime.h>
 
 #include <cstdint>
