@@ -808,7 +808,8 @@ __device__ __forceinline__ void bwd_elem(const Tile<C>& xt, const Tile<C>& yt, T
 #pragma unroll
                 for (int k = 0; k < NR; ++k) {
                     float2 acc;
-                    if (FULL) acc = add2(r[k].v, make_float2(ra[k][e], ra[k][e + 1]));
+                    if (u == 0) acc = FULL ? r[k].v : mul2(make_float2(m[u][C::slot(e)], m[u][C::slot(e + 1)]), r[k].v);   // ra starts here
+                    else if (FULL) acc = add2(r[k].v, make_float2(ra[k][e], ra[k][e + 1]));
                     else acc = fma2(make_float2(m[u][C::slot(e)], m[u][C::slot(e + 1)]), r[k].v, make_float2(ra[k][e], ra[k][e + 1]));
                     ra[k][e] = acc.x;
                     ra[k][e + 1] = acc.y;
@@ -839,8 +840,26 @@ __device__ __forceinline__ void bwd_elem(const Tile<C>& xt, const Tile<C>& yt, T
             }
             gt.v[u][q][e] = gx;
 #pragma unroll
-            for (int k = 0; k < NR; ++k) ra[k][e] = FULL ? ra[k][e] + r[k] : Prim<T>::fma_(m[u][C::slot(e)], r[k], ra[k][e]);
+            for (int k = 0; k < NR; ++k)
+                ra[k][e] = u == 0 ? (FULL ? r[k] : m[u][C::slot(e)] * r[k])
+                                  : (FULL ? ra[k][e] + r[k] : Prim<T>::fma_(m[u][C::slot(e)], r[k], ra[k][e]));
         }
+}
+
+// ... and the tile's contribution to the op's per-thread raw sums (the number of row slots is a compile-time property of
+// the op kind here: no zero-initialised spare slots, no predicated updates)
+template <class C, int KIND, bool FULL>
+__device__ __forceinline__ void bwd_elem_acc(const Tile<C>& xt, const Tile<C>& yt, Tile<C>& gt, int q,
+                                             const typename C::T (&m)[C::SPT][C::LN],
+                                             const typename C::T (&c0)[C::VE], const typename C::T (&c1)[C::VE],
+                                             const typename C::T (&c2)[C::VE], const typename C::T (&c3)[C::VE],
+                                             const typename C::T (&c4)[C::VE], const typename C::T (&c5)[C::VE], uint32_t acc0) {
+    using T = typename C::T;
+    constexpr int NR = n_rowslots_of(KIND, 0);
+    T ra[4][C::VE];                      // written by the first sample of the tile (bwd_elem), slots >= NR never touched
+    bwd_elem<C, KIND, FULL>(xt, yt, gt, q, m, c0, c1, c2, c3, c4, c5, ra);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) acc16_shared<T, C::VE>(acc0 + uint32_t(k * C::CH) * uint32_t(NT * 16), ra[k]);
 }
 
 // -log p(z) and its derivative for the Gaussian-mixture target of the ELBO objective (log-sum-exp over the components).
@@ -1092,22 +1111,14 @@ __device__ __forceinline__ void grad_bwd_tile(const ChainDesc& desc, const GradS
                 lds16(cb + uint32_t((4 * Dp + co) * int(sizeof(T))), c4);
             }
             if (op.kind == OP_CS || op.kind == OP_CC || op.kind == OP_JI) lds16(cb + uint32_t((5 * Dp + co) * int(sizeof(T))), c5);
-            T ra[4][VE];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int e = 0; e < VE; ++e) ra[k][e] = T(0);
+            const uint32_t acc0 = sm.acc + uint32_t(op.roff * C::CH + q) * uint32_t(NT * 16);   // slot k of vector q: + k CH NT 16
             switch (op.kind) {
-                case OP_SS: bwd_elem<C, OP_SS, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                case OP_CS: bwd_elem<C, OP_CS, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                case OP_CC: bwd_elem<C, OP_CC, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                case OP_JO: bwd_elem<C, OP_JO, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
-                default: bwd_elem<C, OP_JI, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, ra); break;
+                case OP_SS: bwd_elem_acc<C, OP_SS, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, acc0); break;
+                case OP_CS: bwd_elem_acc<C, OP_CS, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, acc0); break;
+                case OP_CC: bwd_elem_acc<C, OP_CC, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, acc0); break;
+                case OP_JO: bwd_elem_acc<C, OP_JO, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, acc0); break;
+                default: bwd_elem_acc<C, OP_JI, FULL>(xt, zt, gt, q, m, c0, c1, c2, c3, c4, c5, acc0); break;
             }
-            const int nr = n_rowslots_of(op.kind, 0);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k < nr) acc16_shared<T, VE>(sm.acc + uint32_t((op.roff + k) * C::CH + q) * uint32_t(NT * 16), ra[k]);
         }
         zt = xt;   // the input of this op is the output of the previous one
     }
