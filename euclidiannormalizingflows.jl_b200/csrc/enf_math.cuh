@@ -361,8 +361,9 @@ __device__ __forceinline__ void cs_fwd_v(T* v, const T* nb2, const T* Ah, const 
             if (LADJ) {
                 const float2 wg = mul2(w, g);
                 const float2 p2 = fma2(g, g, mul2(w, w));
-                pd2 = mul2(pd2, fma2(ld2(k1 + e), wg, p2));
-                pn2 = mul2(pn2, fma2(ld2(k2 + e), wg, p2));
+                // (the first pair starts the products: the packed-multiply intrinsic is not folded against a constant 1)
+                pd2 = e == 0 ? fma2(ld2(k1 + e), wg, p2) : mul2(pd2, fma2(ld2(k1 + e), wg, p2));
+                pn2 = e == 0 ? fma2(ld2(k2 + e), wg, p2) : mul2(pn2, fma2(ld2(k2 + e), wg, p2));
             }
         }
         if (LADJ) {
@@ -427,8 +428,8 @@ __device__ __forceinline__ void cc_fwd_v(T* v, const T* nb2, const T* A, const T
             v[e] = copysignf(y.x, u.x);
             v[e + 1] = copysignf(y.y, u.y);
             if (LADJ) {
-                pn2 = mul2(pn2, fma2(w, n1, n2));                  // S = n3 / (n1 n2)
-                ls2 = add2(ls2, add2(L1, L2));
+                pn2 = e == 0 ? fma2(w, n1, n2) : mul2(pn2, fma2(w, n1, n2));   // S = n3 / (n1 n2)
+                ls2 = e == 0 ? add2(L1, L2) : add2(ls2, add2(L1, L2));
             }
         }
         if (LADJ) {
@@ -489,7 +490,7 @@ __device__ __forceinline__ void jo_fwd_v(T* v, const T* il, const T* c0, const T
             const float2 y = fma2(ld2(delta2 + e), a, ld2(gamma + e));
             v[e] = y.x;
             v[e + 1] = y.y;
-            if (LADJ) pr2 = mul2(pr2, r);
+            if (LADJ) pr2 = e == 0 ? r : mul2(pr2, r);
         }
         if (LADJ) {
             const float prod = pr2.x * pr2.y;
@@ -553,7 +554,7 @@ __device__ __forceinline__ void ji_fwd_v(T* v, const T* k0, const T* k1, const T
             const float2 y = fma2(ld2(lam + e), sh, ld2(xi + e));
             v[e] = y.x;
             v[e + 1] = y.y;
-            pc2 = mul2(pc2, ch);
+            pc2 = e == 0 ? ch : mul2(pc2, ch);
         }
         if (LADJ) {
             const float prod = pc2.x * pc2.y;
